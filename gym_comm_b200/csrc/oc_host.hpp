@@ -1,0 +1,220 @@
+// Host-side compilation of an oc_config into the kernel parameter block + table blob.
+// Pure C++ (no CUDA calls) so the same code feeds oc_create and the CPU emulation harness that
+// tests/emu uses to debug the device logic without a GPU (tests only; never a product path).
+#pragma once
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/overcooked_b200.h"
+#include "oc_params.h"
+
+namespace ock {
+
+struct HostImage {
+    OcParams p;
+    std::vector<uint8_t> blob;
+    std::vector<float> ts;
+    int obs_off[OC_NUM_OBS_KEYS], obs_size[OC_NUM_OBS_KEYS];
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static inline void bfs_path_dist(const oc_config* c, std::vector<uint8_t>& pd) {
+    // World.get_path_distance_between (gym_cooking/utils/world.py:61-92,114-131) tabulated.
+    const int W = c->width, H = c->height, n = W * H, M = 2 * (W + H) + 1;
+    pd.assign((size_t)n * n, (uint8_t)M);
+    static const int dx[4] = {0, 0, -1, 1}, dy[4] = {1, -1, 0, 0};
+    std::vector<int> dist(n), queue(n);
+    for (int src = 0; src < n; ++src) {
+        if (c->tiles[src] != 0) continue;            // source node missing -> MAX_PATH (world.py:126-127)
+        std::fill(dist.begin(), dist.end(), -1);
+        int qh = 0, qt = 0;
+        dist[src] = 0; queue[qt++] = src;
+        while (qh < qt) {
+            const int u = queue[qh++], ux = u % W, uy = u / W;
+            for (int a = 0; a < 4; ++a) {
+                const int vx = ux + dx[a], vy = uy + dy[a];
+                if (vx < 0 || vy < 0 || vx >= W || vy >= H) continue;
+                const int v = vy * W + vx;
+                if (c->tiles[v] == 0 && dist[v] < 0) { dist[v] = dist[u] + 1; queue[qt++] = v; }
+            }
+        }
+        for (int dst = 0; dst < n; ++dst) {
+            int best = M;
+            if (c->tiles[dst] == 0) { if (dist[dst] >= 0) best = dist[dst]; }
+            else {
+                const int tx = dst % W, ty = dst / W;
+                for (int a = 0; a < 4; ++a) {
+                    const int vx = tx + dx[a], vy = ty + dy[a];
+                    if (vx < 0 || vy < 0 || vx >= W || vy >= H) continue;
+                    const int v = vy * W + vx;
+                    if (c->tiles[v] == 0 && dist[v] >= 0) best = std::min(best, dist[v] + 1);
+                }
+            }
+            pd[(size_t)src * n + dst] = (uint8_t)std::min(best, M);
+        }
+    }
+}
+
+
+// returns OC_OK or OC_ERR_INVALID (message in err)
+static inline int compile_config(const oc_config* c, HostImage& h, std::string& err) {
+#define OC_BAD(msg) do { err = (msg); return OC_ERR_INVALID; } while (0)
+    if (!c) OC_BAD("null argument");
+    if (c->abi_version != OC_ABI_VERSION) OC_BAD("abi_version mismatch");
+    const int W = c->width, H = c->height, n = W * H, A = c->num_agents, S = c->num_subtasks, C = c->num_communication;
+    const int M = 2 * (W + H) + 1;
+    if (c->num_envs <= 0) OC_BAD("num_envs must be positive");
+    if (A < 2 || A > OC_MAX_AGENTS) OC_BAD("num_agents must be 2..4");
+    if (W <= 0 || H <= 0 || n > OC_MAX_CELLS || M + W + H > 255) OC_BAD("grid too large");
+    if (c->max_path != 0 && c->max_path != M) OC_BAD("max_path must be 2*(w+h)+1");
+    if (S <= 0 || S > OC_MAX_SUBTASKS) OC_BAD("num_subtasks out of range");
+    if (C <= 0 || C > OC_MAX_COMM) OC_BAD("num_communication out of range");
+    if (c->max_num_timesteps < 0 || c->max_num_timesteps > 65534) OC_BAD("max_num_timesteps out of range");
+    if (c->max_num_timesteps == 0) OC_BAD("max_num_timesteps == 0 makes the timestep observation t/0 (the reference raises ZeroDivisionError)");
+    if (c->num_objects <= 0 || c->num_objects > OC_MAX_OBJECTS) OC_BAD("num_objects out of range");
+    if (c->num_items < 1 || c->num_items > 4) OC_BAD("num_items out of range");
+    if (!c->tiles) OC_BAD("tiles is null");
+    if (c->fow_radius < 0) OC_BAD("fow_radius must be >= 0");
+    for (int i = 0; i < n; ++i) if (c->tiles[i] > 3) OC_BAD("bad tile code");
+    for (int k = 0; k < A; ++k)
+        if (c->start_cell[k] >= n || c->tiles[c->start_cell[k]] != 0) OC_BAD("agent start must be a floor cell");
+    // domain: every Food at most once (otherwise the reference itself is ill-defined: it indexes
+    // list(set(locations))[0], overcooked_environment.py:288,380) -- see DESIGN.md
+    int food_seen = 0;
+    for (int s = 0; s < c->num_objects; ++s) {
+        const int b = c->object_contents[s];
+        if (b != 1 && b != 2 && b != 4 && b != 8) OC_BAD("object_contents must be a single content bit");
+        if (b != 8) { if (food_seen & b) OC_BAD("each Food may appear at most once in a level"); food_seen |= b; }
+        if (c->object_cell[s] >= 0 && (c->object_cell[s] >= n || c->tiles[c->object_cell[s]] == 0))
+            OC_BAD("fixed objects must sit on a non-floor tile");
+    }
+
+    OcParams& p = h.p;
+    memset(&p, 0, sizeof(p));
+    p.E = c->num_envs; p.A = A; p.NOBJ = c->num_objects <= 4 ? 4 : 6;
+    p.W = W; p.H = H; p.ncell = n; p.T = c->max_num_timesteps; p.C = C; p.S = S;
+    p.F = 23 + S + 2 * C; p.fow = c->fow_radius; p.M = M;
+    p.row_bytes = A * p.F;
+    p.row_stride = (int)align_up(p.row_bytes, 4);
+    if (((p.row_stride >> 2) & 1) == 0) p.row_stride += 4;          // odd word stride: conflict-free byte scatter
+    for (int k = 0; k < OC_MAX_AGENTS; ++k) {
+        p.can_move[k] = c->can_move[k]; p.allergic[k] = c->allergic[k]; p.blind[k] = c->blind[k];
+        p.start_cell[k] = c->start_cell[k];
+    }
+    p.comm_on = c->communication_on != 0; p.ego_led = c->ego_led != 0; p.ego_blind = c->blind[0] != 0;
+    p.seed = c->seed;
+
+    // observation layout: key-sorted order of the reference's Dict space (overcooked_env.py:66-78)
+    {
+        const int sizes[OC_NUM_OBS_KEYS] = {C, 2, C, 2, 2, S, 4, 4, 4, 4, 1};
+        int off = 0;
+        for (int i = 0; i < OC_NUM_OBS_KEYS; ++i) { h.obs_off[i] = off; h.obs_size[i] = sizes[i]; off += sizes[i]; }
+        p.off_a1comm = h.obs_off[0]; p.off_a1loc = h.obs_off[1]; p.off_a2comm = h.obs_off[2];
+        p.off_a2loc = h.obs_off[3]; p.off_hold = h.obs_off[4]; p.off_completed = h.obs_off[5];
+        p.off_hidden = h.obs_off[6]; p.off_encx = h.obs_off[7]; p.off_ency = h.obs_off[8];
+        p.off_state = h.obs_off[9]; p.off_ts = h.obs_off[10];
+    }
+
+    // delivery / counters
+    std::vector<uint8_t> counters; int delivery0 = -1; std::vector<int> deliveries;
+    for (int i = 0; i < n; ++i) {
+        if (c->tiles[i] == 1) counters.push_back((uint8_t)i);
+        if (c->tiles[i] == 3) { deliveries.push_back(i); if (delivery0 < 0) delivery0 = i; }
+    }
+    if (delivery0 < 0) OC_BAD("level has no Delivery tile");
+    p.delivery0 = (uint8_t)delivery0;
+    p.ncounters = (int)counters.size();
+
+    // reset image: objects in world insertion order; stamp = insertion index + 1; key ranks in
+    // first-insert order (world.py:236-237)
+    uint64_t ranks = 0; uint32_t nkeys = 0; p.nrandom = 0;
+    for (int s = 0; s < c->num_objects; ++s) {
+        const uint32_t b = c->object_contents[s];
+        uint32_t cell = 0;
+        if (c->object_cell[s] < 0) p.random_slot[p.nrandom++] = (uint8_t)s; else cell = (uint32_t)c->object_cell[s];
+        p.init_obj[s] = b | (OCK_HOLDER_NONE << 8) | (cell << 16) | ((uint32_t)(s + 1) << 24);
+        if (((ranks >> (4 * b)) & 15) == 0) { ++nkeys; ranks |= (uint64_t)nkeys << (4 * b); }
+    }
+    if (p.nrandom > p.ncounters) OC_BAD("more random objects than Counter tiles");
+    p.init_ranks = ranks;
+    p.init_w0 = ((uint32_t)c->num_objects << 16) | (nkeys << 24);
+
+    // subtask tables
+    std::vector<uint32_t> tmlut(128, 0);
+    int nchop = 0;
+    for (int i = 0; i < S; ++i) {
+        const int kind = c->subtask_kind[i], goal = c->subtask_goal[i];
+        if (kind < 0 || kind > 2 || goal <= 0 || goal > 127 || (goal & 7) == 0) OC_BAD("bad subtask entry");
+        tmlut[goal] |= 1u << i;
+        if (kind == 2) {
+            p.deliver_mask |= 1u << i;
+            if (p.ndeliver >= OCK_MAX_DELIVER) OC_BAD("too many Deliver subtasks");
+            p.deliver_sig[p.ndeliver] = (uint8_t)goal; p.deliver_idx[p.ndeliver] = (uint8_t)i; ++p.ndeliver;
+        } else {
+            p.nondeliver_mask |= 1u << i;
+            if (kind == 0) {
+                const int f = c->subtask_arg0[i];
+                if (f != 1 && f != 2 && f != 4) OC_BAD("Chop subtask needs a single food bit");
+                p.chop_mask[f == 1 ? 0 : (f == 2 ? 1 : 2)] |= 1u << i;
+                ++nchop;
+            }
+        }
+    }
+    if (p.ndeliver == 0) OC_BAD("no delivery subtask (overcooked_environment.py:251 asserts)");
+    p.npairs = 0;
+    for (int i = 0; i < c->num_items; ++i)
+        for (int j = i + 1; j < c->num_items; ++j) { p.pair_x[p.npairs] = c->items[i]; p.pair_y[p.npairs] = c->items[j]; ++p.npairs; }
+
+    // tables
+    std::vector<uint8_t> pd;
+    if (c->path_dist) pd.assign(c->path_dist, c->path_dist + (size_t)n * n); else bfs_path_dist(c, pd);
+    std::vector<uint8_t> mv(n * 4), xy(n * 2), dmin(n);
+    static const int dx[4] = {0, 0, -1, 1}, dy[4] = {1, -1, 0, 0};
+    for (int i = 0; i < n; ++i) {
+        const int x = i % W, y = i / W;
+        xy[2 * i] = (uint8_t)x; xy[2 * i + 1] = (uint8_t)y;
+        for (int a = 0; a < 4; ++a) {
+            const int vx = std::min(std::max(x + dx[a], 0), W - 1), vy = std::min(std::max(y + dy[a], 0), H - 1);
+            mv[4 * i + a] = (uint8_t)(vy * W + vx);
+        }
+        int best = 1 << 20;
+        for (int d : deliveries) best = std::min(best, (int)pd[(size_t)i * n + d] + abs(x - d % W) + abs(y - d / W));
+        dmin[i] = (uint8_t)best;
+    }
+    const int nq = std::max(std::max(2 * M + std::max(nchop - 1, 0) * 2 * M, p.npairs * M), M + W + H) + 1;
+    std::vector<double> q(nq);
+    for (int i = 0; i < nq; ++i) q[i] = (double)i / (double)M;      // == Python int / int (correctly rounded)
+    std::vector<float>& ts = h.ts; ts.assign(p.T + 1, 0.f);
+    for (int t = 0; t <= p.T; ++t) ts[t] = (float)((double)t / (double)p.T);   // np.float32(t / T)
+
+    size_t off = 0;
+    p.o_q = (int)off; off += align_up(q.size() * 8, 16);
+    p.o_tmlut = (int)off; off += 128 * 4;
+    p.o_tile = (int)off; off += align_up(n, 16);
+    p.o_mv = (int)off; off += align_up(n * 4, 16);
+    p.o_xy = (int)off; off += align_up(n * 2, 16);
+    p.o_dmin = (int)off; off += align_up(n, 16);
+    p.o_counters = (int)off; off += align_up(std::max<size_t>(counters.size(), 1), 16);
+    p.o_pd = (int)off; off += align_up((size_t)n * n, 16);
+    p.blob_bytes = (int)off;
+    std::vector<uint8_t>& blob = h.blob; blob.assign(off, 0);
+    memcpy(blob.data() + p.o_q, q.data(), q.size() * 8);
+    memcpy(blob.data() + p.o_tmlut, tmlut.data(), 128 * 4);
+    memcpy(blob.data() + p.o_tile, c->tiles, n);
+    memcpy(blob.data() + p.o_mv, mv.data(), mv.size());
+    memcpy(blob.data() + p.o_xy, xy.data(), xy.size());
+    memcpy(blob.data() + p.o_dmin, dmin.data(), dmin.size());
+    if (!counters.empty()) memcpy(blob.data() + p.o_counters, counters.data(), counters.size());
+    memcpy(blob.data() + p.o_pd, pd.data(), pd.size());
+
+    return OC_OK;
+#undef OC_BAD
+}
+
+}  // namespace ock

@@ -1,0 +1,341 @@
+// sm_100a kernels + C ABI of the batched Overcooked simulator (include/overcooked_b200.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/overcooked_b200.h"
+#include "oc_device.cuh"
+#include "oc_host.hpp"
+
+using namespace ock;
+
+// =============================================================================================
+// kernels
+// =============================================================================================
+
+// dynamic shared memory: [table blob][per warp: 32 byte-rows][per warp: 32 timestep floats]
+template <int A, int NOBJ>
+__global__ void __launch_bounds__(256)
+oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
+               const int32_t* __restrict__ actions, float* __restrict__ obs,
+               float* __restrict__ rew32, double* __restrict__ rew64, uint8_t* __restrict__ done_out,
+               float* __restrict__ term_obs, uint32_t flags) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = env < p.E;
+
+    // global loads first so their latency overlaps the table copy
+    Env<A, NOBJ> e;
+    int nav[A], comm[A];
+    if (valid) {
+        load_env<A, NOBJ>(e, state, p.E, env);
+        const int2* a2 = reinterpret_cast<const int2*>(actions) + (size_t)env * A;
+#pragma unroll
+        for (int k = 0; k < A; ++k) { const int2 v = __ldg(a2 + k); nav[k] = v.x & 3; comm[k] = v.y; }
+    }
+    load_tables(p, smem);
+    uint8_t* wrows = smem + p.blob_bytes + (size_t)warp * 32 * p.row_stride;
+    float* wts = reinterpret_cast<float*>(smem + p.blob_bytes + (size_t)nwarps * 32 * p.row_stride) + warp * 32;
+    warp_zero_rows(wrows, 32 * p.row_stride, lane);
+    __syncthreads();
+    const Tables tb = make_tables(p, smem);
+    uint8_t* myrow = wrows + lane * p.row_stride;
+
+    if (valid) {
+        step_one_env<A, NOBJ>(e, p, tb, nav, comm[0], comm[1], (uint32_t)env, myrow, wts, lane,
+                              rew32, rew64, done_out, term_obs, flags);
+        store_env<A, NOBJ>(e, state, p.E, env);
+    }
+    __syncwarp();
+    const int env0 = blockIdx.x * blockDim.x + warp * 32;
+    const int nvalid = min(32, p.E - env0);
+    if (nvalid > 0) warp_expand_rows(p, wrows, wts, obs + (size_t)env0 * p.row_bytes, nvalid, lane);
+}
+
+// n_steps steps per launch, state in registers, Philox actions (SURVEY section 8d synthetic inputs)
+template <int A, int NOBJ>
+__global__ void __launch_bounds__(256)
+oc_rollout_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, int n_steps, uint32_t step0,
+                  float* __restrict__ obs, float* __restrict__ rew32, uint8_t* __restrict__ done_out,
+                  int32_t* __restrict__ actions_out) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = env < p.E;
+    Env<A, NOBJ> e;
+    if (valid) load_env<A, NOBJ>(e, state, p.E, env);
+    load_tables(p, smem);
+    uint8_t* wrows = smem + p.blob_bytes + (size_t)warp * 32 * p.row_stride;
+    float* wts = reinterpret_cast<float*>(smem + p.blob_bytes + (size_t)nwarps * 32 * p.row_stride) + warp * 32;
+    __syncthreads();
+    const Tables tb = make_tables(p, smem);
+    uint8_t* myrow = wrows + lane * p.row_stride;
+    const int env0 = blockIdx.x * blockDim.x + warp * 32;
+    const int nvalid = min(32, p.E - env0);
+    const size_t step_floats = (size_t)p.E * p.row_bytes;
+
+    for (int s = 0; s < n_steps; ++s) {
+        if (obs != nullptr) { warp_zero_rows(wrows, 32 * p.row_stride, lane); __syncwarp(); }
+        if (valid) {
+            rollout_one_env<A, NOBJ>(e, p, tb, (uint32_t)env, (uint32_t)s, step0, myrow, wts, lane,
+                                     obs != nullptr, rew32, done_out, actions_out);
+        }
+        if (obs != nullptr) {
+            __syncwarp();
+            if (nvalid > 0)
+                warp_expand_rows(p, wrows, wts, obs + (size_t)s * step_floats + (size_t)env0 * p.row_bytes, nvalid, lane);
+            __syncwarp();
+        }
+    }
+    if (valid) store_env<A, NOBJ>(e, state, p.E, env);
+}
+
+// reset (masked) + observation of every env
+template <int A, int NOBJ>
+__global__ void __launch_bounds__(256)
+oc_reset_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, const uint8_t* __restrict__ mask,
+                const int32_t* __restrict__ placements, float* __restrict__ obs, int initial) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = env < p.E;
+    Env<A, NOBJ> e;
+    if (valid && !initial) load_env<A, NOBJ>(e, state, p.E, env);
+    load_tables(p, smem);
+    uint8_t* wrows = smem + p.blob_bytes + (size_t)warp * 32 * p.row_stride;
+    float* wts = reinterpret_cast<float*>(smem + p.blob_bytes + (size_t)nwarps * 32 * p.row_stride) + warp * 32;
+    warp_zero_rows(wrows, 32 * p.row_stride, lane);
+    __syncthreads();
+    const Tables tb = make_tables(p, smem);
+    if (valid) {
+        reset_one_env<A, NOBJ>(e, p, tb, (uint32_t)env, initial != 0, mask, placements, obs != nullptr,
+                               wrows + lane * p.row_stride, wts, lane);
+        store_env<A, NOBJ>(e, state, p.E, env);
+    }
+    __syncwarp();
+    const int env0 = blockIdx.x * blockDim.x + warp * 32;
+    const int nvalid = min(32, p.E - env0);
+    if (obs != nullptr && nvalid > 0) warp_expand_rows(p, wrows, wts, obs + (size_t)env0 * p.row_bytes, nvalid, lane);
+}
+
+// packed state <-> [E, 16] u32 rows
+__global__ void oc_state_export_kernel(const uint4* __restrict__ planes, uint32_t* __restrict__ rows, int E) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E * 4) return;
+    const int env = i >> 2, pl = i & 3;
+    reinterpret_cast<uint4*>(rows)[(size_t)env * 4 + pl] = planes[(size_t)pl * E + env];
+}
+__global__ void oc_state_import_kernel(uint4* __restrict__ planes, const uint32_t* __restrict__ rows, int E) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E * 4) return;
+    const int env = i >> 2, pl = i & 3;
+    planes[(size_t)pl * E + env] = reinterpret_cast<const uint4*>(rows)[(size_t)env * 4 + pl];
+}
+__global__ void oc_stats_kernel(const uint4* __restrict__ planes, uint32_t* __restrict__ episodes,
+                                uint32_t* __restrict__ last_completed, int E) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E) return;
+    if (episodes) episodes[i] = planes[i].y;
+    if (last_completed) last_completed[i] = planes[(size_t)E + i].y & 0xFFu;
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return fail(OC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+    } while (0)
+
+struct oc_env {
+    OcParams p;
+    int device = 0;
+    int threads = 64;
+    size_t smem_bytes = 0;
+    uint4* state = nullptr;
+    uint8_t* blob = nullptr;
+    float* ts = nullptr;
+    uint64_t launches = 0;
+    uint32_t rollout_step = 0;
+    int obs_off[OC_NUM_OBS_KEYS], obs_size[OC_NUM_OBS_KEYS];
+};
+
+template <typename F>
+static int dispatch(int A, int NOBJ, F&& f) {
+#define OC_CASE(a, n) if (A == a && NOBJ == n) return f(std::integral_constant<int, a>(), std::integral_constant<int, n>());
+    OC_CASE(2, 4) OC_CASE(3, 4) OC_CASE(4, 4) OC_CASE(2, 6) OC_CASE(3, 6) OC_CASE(4, 6)
+#undef OC_CASE
+    return fail(OC_ERR_INVALID, "unsupported (num_agents, num_objects)");
+}
+
+extern "C" int oc_abi_version(void) { return OC_ABI_VERSION; }
+extern "C" const char* oc_last_error(void) { return g_err.c_str(); }
+
+extern "C" int oc_create(const oc_config* c, oc_env** out) {
+    if (!c || !out) return fail(OC_ERR_INVALID, "null argument");
+    *out = nullptr;
+    oc_env* h = new (std::nothrow) oc_env();
+    if (!h) return fail(OC_ERR_ALLOC, "out of host memory");
+    HostImage img;
+    std::string err;
+    if (compile_config(c, img, err) != OC_OK) { delete h; return fail(OC_ERR_INVALID, err); }
+    h->p = img.p;
+    memcpy(h->obs_off, img.obs_off, sizeof(h->obs_off));
+    memcpy(h->obs_size, img.obs_size, sizeof(h->obs_size));
+    OcParams& p = h->p;
+    const std::vector<uint8_t>& blob = img.blob;
+    const std::vector<float>& ts = img.ts;
+    int dev = 0;
+    {   // there is no CPU fallback: without a CUDA device creation fails
+        cudaError_t ce0 = cudaGetDevice(&dev);
+        if (ce0 != cudaSuccess) { delete h; return fail(OC_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(ce0)); }
+    }
+    h->device = dev;
+
+    const char* tenv = getenv("OC_BLOCK_THREADS");
+    h->threads = tenv ? atoi(tenv) : 64;
+    if (h->threads < 32 || h->threads > 256 || (h->threads & 31)) h->threads = 64;
+    auto smem_for = [&](int threads) { return (size_t)p.blob_bytes + (size_t)(threads / 32) * (32 * (size_t)p.row_stride + 128); };
+    while (h->threads > 32 && smem_for(h->threads) > 200 * 1024) h->threads -= 32;
+    h->smem_bytes = smem_for(h->threads);
+    if (h->smem_bytes > 227 * 1024) { delete h; return fail(OC_ERR_INVALID, "observation row too wide for shared memory"); }
+
+    cudaError_t ce;
+    if ((ce = cudaMalloc(&h->state, (size_t)p.E * 64)) != cudaSuccess ||
+        (ce = cudaMalloc(&h->blob, blob.size())) != cudaSuccess ||
+        (ce = cudaMalloc(&h->ts, ts.size() * 4)) != cudaSuccess ||
+        (ce = cudaMemcpy(h->blob, blob.data(), blob.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (ce = cudaMemcpy(h->ts, ts.data(), ts.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        std::string m = std::string("device allocation/copy failed: ") + cudaGetErrorString(ce);
+        oc_destroy(h);
+        return fail(ce == cudaErrorMemoryAllocation ? OC_ERR_ALLOC : OC_ERR_CUDA, m);
+    }
+    p.blob = h->blob; p.ts_table = h->ts;
+
+    // opt in to large dynamic shared memory for every instantiation we may launch
+    int rc = dispatch(p.A, p.NOBJ, [&](auto a, auto nobj) -> int {
+        constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
+        CUDA_TRY(cudaFuncSetAttribute(oc_step_kernel<AA, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        CUDA_TRY(cudaFuncSetAttribute(oc_rollout_kernel<AA, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        CUDA_TRY(cudaFuncSetAttribute(oc_reset_kernel<AA, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        const int grid = (p.E + h->threads - 1) / h->threads;
+        oc_reset_kernel<AA, NN><<<grid, h->threads, h->smem_bytes, 0>>>(p, h->state, nullptr, nullptr, nullptr, 1);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaDeviceSynchronize());
+        return OC_OK;
+    });
+    if (rc != OC_OK) { std::string m = g_err; oc_destroy(h); return fail(rc, m); }
+    h->launches += 1;
+    *out = h;
+    return OC_OK;
+}
+
+extern "C" int oc_destroy(oc_env* h) {
+    if (!h) return OC_OK;
+    if (h->state) cudaFree(h->state);
+    if (h->blob) cudaFree(h->blob);
+    if (h->ts) cudaFree(h->ts);
+    delete h;
+    return OC_OK;
+}
+
+extern "C" int oc_obs_width(const oc_env* h) { return h ? h->p.F : OC_ERR_INVALID; }
+
+extern "C" int oc_obs_layout(const oc_env* h, int32_t* offsets, int32_t* sizes) {
+    if (!h || !offsets || !sizes) return fail(OC_ERR_INVALID, "null argument");
+    for (int i = 0; i < OC_NUM_OBS_KEYS; ++i) { offsets[i] = h->obs_off[i]; sizes[i] = h->obs_size[i]; }
+    return OC_OK;
+}
+
+static bool misaligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) != 0; }
+
+extern "C" int oc_reset(oc_env* h, const uint8_t* mask, const int32_t* placements, float* obs, void* stream) {
+    if (!h) return fail(OC_ERR_INVALID, "null handle");
+    if (obs && misaligned16(obs)) return fail(OC_ERR_INVALID, "obs must be 16-byte aligned");
+    const OcParams& p = h->p;
+    int rc = dispatch(p.A, p.NOBJ, [&](auto a, auto nobj) -> int {
+        constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
+        const int grid = (p.E + h->threads - 1) / h->threads;
+        oc_reset_kernel<AA, NN><<<grid, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(p, h->state, mask, placements, obs, 0);
+        CUDA_TRY(cudaGetLastError());
+        return OC_OK;
+    });
+    if (rc == OC_OK) h->launches += 1;
+    return rc;
+}
+
+extern "C" int oc_step(oc_env* h, const int32_t* actions, float* obs, float* rew_f32, double* rew_f64,
+                       uint8_t* done, float* term_obs, uint32_t flags, void* stream) {
+    if (!h || !actions || !obs || !done) return fail(OC_ERR_INVALID, "null argument");
+    if (misaligned16(obs) || (reinterpret_cast<uintptr_t>(actions) & 7)) return fail(OC_ERR_INVALID, "obs must be 16-byte and actions 8-byte aligned");
+    const OcParams& p = h->p;
+    int rc = dispatch(p.A, p.NOBJ, [&](auto a, auto nobj) -> int {
+        constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
+        const int grid = (p.E + h->threads - 1) / h->threads;
+        oc_step_kernel<AA, NN><<<grid, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(
+            p, h->state, actions, obs, rew_f32, rew_f64, done, term_obs, flags);
+        CUDA_TRY(cudaGetLastError());
+        return OC_OK;
+    });
+    if (rc == OC_OK) h->launches += 1;
+    return rc;
+}
+
+extern "C" int oc_rollout(oc_env* h, int32_t n_steps, float* obs, float* rew_f32, uint8_t* done,
+                          int32_t* actions_out, void* stream) {
+    if (!h || n_steps <= 0) return fail(OC_ERR_INVALID, "bad argument");
+    if (obs && misaligned16(obs)) return fail(OC_ERR_INVALID, "obs must be 16-byte aligned");
+    const OcParams& p = h->p;
+    int rc = dispatch(p.A, p.NOBJ, [&](auto a, auto nobj) -> int {
+        constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
+        const int grid = (p.E + h->threads - 1) / h->threads;
+        oc_rollout_kernel<AA, NN><<<grid, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(
+            p, h->state, n_steps, h->rollout_step, obs, rew_f32, done, actions_out);
+        CUDA_TRY(cudaGetLastError());
+        return OC_OK;
+    });
+    if (rc == OC_OK) { h->launches += 1; h->rollout_step += (uint32_t)n_steps; }
+    return rc;
+}
+
+extern "C" int oc_get_state(oc_env* h, uint32_t* state, void* stream) {
+    if (!h || !state) return fail(OC_ERR_INVALID, "null argument");
+    if (misaligned16(state)) return fail(OC_ERR_INVALID, "state must be 16-byte aligned");
+    const int n = h->p.E * 4;
+    oc_state_export_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->state, state, h->p.E);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    return OC_OK;
+}
+
+extern "C" int oc_set_state(oc_env* h, const uint32_t* state, void* stream) {
+    if (!h || !state) return fail(OC_ERR_INVALID, "null argument");
+    if (misaligned16(state)) return fail(OC_ERR_INVALID, "state must be 16-byte aligned");
+    const int n = h->p.E * 4;
+    oc_state_import_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->state, state, h->p.E);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    return OC_OK;
+}
+
+extern "C" int oc_get_stats(oc_env* h, uint32_t* episodes, uint32_t* last_completed, void* stream) {
+    if (!h) return fail(OC_ERR_INVALID, "null handle");
+    oc_stats_kernel<<<(h->p.E + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->state, episodes, last_completed, h->p.E);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    return OC_OK;
+}
+
+extern "C" uint64_t oc_launch_count(const oc_env* h) { return h ? h->launches : 0; }

@@ -1,0 +1,63 @@
+// Kernel-side view of one compiled env configuration (passed BY VALUE as a __grid_constant__
+// kernel parameter: uniform reads come from the constant bank, no global __constant__ state, so
+// several handles with different levels can coexist in one process).
+#pragma once
+#include <stdint.h>
+
+#define OCK_MAX_AGENTS 4
+#define OCK_MAX_OBJECTS 6
+#define OCK_MAX_PAIRS 6
+#define OCK_MAX_DELIVER 4
+
+// ---- packed per-env state: 16 x u32, stored as 4 SoA planes of uint4 (plane p, env e at
+//      state[p * E + e]) so a warp's 32 envs load/store 512 contiguous bytes per plane.
+// w0  t[0:16] | next_stamp[16:24] | nkeys[24:32]
+// w1  episodes finished
+// w2  completed_subtasks bits            (overcooked_environment.py:202)
+// w3  goal_objects_count bits (0/1 each) (overcooked_environment.py:201; see DESIGN.md domain note)
+// w4  agent cells, 4 x u8
+// w5  last_completed[0:8] (popcount of completed at the end of the last episode)
+// w6,w7  world.objects key ranks: 16 x 4 bit, index = contents mask, 0 = key absent, else rank+1
+// w8..w13 objects: contents[0:4] | chopped[4:7] | holder[8:11] (7 = not held) | cell[16:24] | stamp[24:32]
+//         (word 0 = dead slot)
+// w14 comm index agent0 [0:16] | agent1 [16:32]   (0xFFFF = all-zero vector)
+// w15 reserved
+#define OCK_HOLDER_NONE 7u
+#define OCK_COMM_NONE 0xFFFFu
+
+struct OcParams {
+    int32_t E, A, NOBJ;
+    int32_t W, H, ncell;
+    int32_t T, C, S, F;
+    int32_t fow, M;
+    int32_t row_bytes;        // A * F
+    int32_t row_stride;       // smem byte-row stride per env (multiple of 4, odd word count)
+    uint8_t can_move[OCK_MAX_AGENTS];
+    uint8_t allergic[OCK_MAX_AGENTS];
+    uint8_t blind[OCK_MAX_AGENTS];
+    uint8_t start_cell[OCK_MAX_AGENTS];
+    uint8_t comm_on, ego_led, ego_blind, delivery0;
+    // reset image
+    uint32_t init_obj[OCK_MAX_OBJECTS];     // object words at reset (cell = 0 for random ones)
+    uint8_t  random_slot[OCK_MAX_OBJECTS];  // slots placed on a random counter, phase-4 order
+    int32_t  nrandom, ncounters;
+    uint32_t init_w0;                       // t=0 | next_stamp | nkeys
+    uint64_t init_ranks;                    // ranks AFTER all initial inserts
+    // reward tables
+    uint32_t deliver_mask, nondeliver_mask;
+    uint32_t chop_mask[3];                  // per food bit: the Chop(food) subtasks
+    int32_t  ndeliver;
+    uint8_t  deliver_sig[OCK_MAX_DELIVER];  // in table order
+    uint8_t  deliver_idx[OCK_MAX_DELIVER];
+    int32_t  npairs;
+    uint8_t  pair_x[OCK_MAX_PAIRS], pair_y[OCK_MAX_PAIRS];
+    // observation layout (float offsets inside one observer row)
+    int32_t off_a1comm, off_a1loc, off_a2comm, off_a2loc, off_hold, off_completed,
+            off_hidden, off_encx, off_ency, off_state, off_ts;
+    uint64_t seed;
+    // table blob (device pointer) and the byte offsets of its sections; copied to smem per CTA
+    const uint8_t* blob;
+    int32_t blob_bytes;        // multiple of 16
+    int32_t o_q, o_tmlut, o_tile, o_mv, o_xy, o_dmin, o_counters, o_pd;
+    const float* ts_table;     // [T+1] float32(t / T)   (overcooked_env.py:146)
+};

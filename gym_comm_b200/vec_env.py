@@ -1,0 +1,308 @@
+"""Batched Overcooked env on the GPU behind the reference's env API.
+
+``OvercookedVecEnv``  -- E lock-step envs, state in HBM, every call one CUDA launch through the
+                         C ABI (include/overcooked_b200.h); tensors in, tensors out, no host sync.
+``OvercookedMultiEnv`` -- the reference's 2-player ``SimultaneousEnv`` surface
+                         (gym_comm/envs/overcooked_env.py:15-297: ``multi_step`` / ``multi_reset`` /
+                         ``get_observation2`` with the 11-key dict observation) on top of it.
+
+The dynamics live in gym_comm_b200/csrc (hand-written sm_100a CUDA).  Nothing here computes
+env logic on the host, and nothing falls back to a CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .arglist import normalize
+from .level_compiler import NAV_ACTIONS, CompiledLevel, compile_level
+
+
+# --------------------------------------------------------------------------- gym-free spaces
+class Box:
+    def __init__(self, low, high, shape=None, dtype=np.float32):
+        self.low, self.high, self.dtype = low, high, dtype
+        self.shape = tuple(shape) if shape is not None else np.asarray(low).shape
+
+
+class MultiBinary:
+    def __init__(self, n):
+        self.n, self.shape, self.dtype = n, (n,), np.int8
+
+
+class MultiDiscrete:
+    def __init__(self, nvec):
+        self.nvec = np.asarray(nvec)
+        self.shape, self.dtype = self.nvec.shape, np.int64
+
+
+class Dict:
+    def __init__(self, spaces):
+        # gym.spaces.Dict sorts a plain dict by key; that order is the flat feature order
+        self.spaces = dict(sorted(spaces.items()))
+
+
+class OvercookedVecEnv:
+    """E Overcooked envs stepped in lock-step on one GPU.
+
+    ``arglist``: Namespace / dict with the reference's keys (arglist.py:96-121).
+    Observations are flat float32 rows ``[E, A, F]`` (F = 23 + S + 2C) in the key-sorted order of
+    the reference's Dict space -- what ``FlattenedDictExtractor`` would concatenate
+    (gym_comm/extractors/CustomExtractor.py:119-128); ``obs_dict`` gives zero-copy per-key views.
+    """
+
+    def __init__(self, arglist, num_envs: int = 1, device="cuda", seed: int = 0, auto_reset: bool = True,
+                 level_text: Optional[str] = None, subtasks=None, lib: Optional[_cabi.OcLibrary] = None):
+        self.arglist = normalize(arglist)
+        a = self.arglist
+        self.lib = lib if lib is not None else _cabi.default_library()
+        self.device = torch.device(device)
+        if self.lib.prefix == "oc_":
+            if self.device.type != "cuda":
+                raise RuntimeError("OvercookedVecEnv runs on a CUDA device only (no CPU fallback)")
+            if not torch.cuda.is_available():
+                raise RuntimeError("no CUDA device available; the Overcooked kernels are sm_100a CUDA only")
+        self.num_envs = int(num_envs)
+        self.num_agents = int(a.num_agents)
+        self.auto_reset = bool(auto_reset)
+        self.level: CompiledLevel = compile_level(a.level, self.num_agents, level_text=level_text, subtasks=subtasks)
+        cfg, self._keep = _cabi.make_config(
+            self.level, num_envs=self.num_envs, num_agents=self.num_agents,
+            max_num_timesteps=a.max_num_timesteps, num_communication=a.num_communication,
+            communication_on=a.communication_on, ego_led=a.ego_led, fow_radius=a.fow_radius,
+            ego_config=a.ego_config, partner_config=a.partner_config, seed=seed)
+        self._handle = C.c_void_p()
+        with self._device_guard():
+            self.lib.check(self.lib.create(C.byref(cfg), C.byref(self._handle)), "oc_create")
+        self.obs_width = self.lib.obs_width(self._handle)
+        off = (C.c_int32 * _cabi.OC_NUM_OBS_KEYS)()
+        size = (C.c_int32 * _cabi.OC_NUM_OBS_KEYS)()
+        self.lib.check(self.lib.obs_layout(self._handle, off, size), "oc_obs_layout")
+        self.obs_layout = {k: slice(off[i], off[i] + size[i]) for i, k in enumerate(_cabi.OBS_KEYS)}
+        S, Cn = len(self.level.subtasks), a.num_communication
+        w, h = self.level.width, self.level.height
+        self.observation_space = Dict({
+            "timestep": Box(0.0, 1.0, (1,), np.float32),
+            "object_encodings_x": Box(-w, w, (4,), np.int64),
+            "object_encodings_y": Box(h, h, (4,), np.int64),          # sic: low == high in the reference (:62)
+            "state_encodings": MultiBinary(4), "is_hidden": MultiBinary(4),
+            "completed_subtasks": MultiBinary(S),
+            "agent1_location": Box(np.array([0, 0]), np.array([w - 1, h - 1]), dtype=np.float32),
+            "agent2_location": Box(np.array([0, 0]), np.array([w - 1, h - 1]), dtype=np.float32),
+            "agent_is_holding": MultiBinary(2),
+            "agent1_comm": MultiBinary(Cn), "agent2_comm": MultiBinary(Cn)})
+        self.action_space = MultiDiscrete([len(NAV_ACTIONS), Cn])      # overcooked_env.py:85
+        E, A, F = self.num_envs, self.num_agents, self.obs_width
+        kw = dict(device=self.device)
+        self.obs = torch.zeros((E, A, F), dtype=torch.float32, **kw)
+        self.rewards = torch.zeros((E, A), dtype=torch.float32, **kw)
+        self.rewards64 = torch.zeros((E,), dtype=torch.float64, **kw)
+        self.dones = torch.zeros((E,), dtype=torch.uint8, **kw)
+        self._closed = False
+
+    # ------------------------------------------------------------------ plumbing
+    def _device_guard(self):
+        return torch.cuda.device(self.device) if self.device.type == "cuda" else _NullCtx()
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream) if self.device.type == "cuda" else None
+
+    @staticmethod
+    def _ptr(t: Optional[torch.Tensor]):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def _check_tensor(self, t, shape, dtype, name):
+        if t.device != self.obs.device or t.dtype != dtype or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+            raise ValueError("%s must be a contiguous %s tensor of shape %s on %s (got %s %s on %s)" %
+                             (name, dtype, tuple(shape), self.obs.device, t.dtype, tuple(t.shape), t.device))
+
+    # ------------------------------------------------------------------ env API
+    def reset(self, mask: Optional[torch.Tensor] = None, placements: Optional[torch.Tensor] = None,
+              obs_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Reset all envs (or those with ``mask[e] != 0``).  ``placements`` int32 [E, R] pins the cells
+        of the R random (phase-4) objects; default: drawn on the device."""
+        obs = self.obs if obs_out is None else obs_out
+        self._check_tensor(obs, self.obs.shape, torch.float32, "obs_out")
+        if mask is not None:
+            self._check_tensor(mask, (self.num_envs,), torch.uint8, "mask")
+        if placements is not None:
+            self._check_tensor(placements, (self.num_envs, self.level.num_random), torch.int32, "placements")
+        with self._device_guard():
+            self.lib.check(self.lib.reset(self._handle, self._ptr(mask), self._ptr(placements), self._ptr(obs),
+                                          self._stream()), "oc_reset")
+        return obs
+
+    def step(self, actions: torch.Tensor, obs_out=None, rew_out=None, done_out=None, term_obs_out=None,
+             want_f64: bool = False):
+        """``actions`` int32 [E, A, 2] = (nav in [0,4), comm in [0,C)) per agent.  Returns
+        (obs [E,A,F] f32, rewards [E,A] f32, dones [E] u8); with ``want_f64`` the reward in the
+        reference's own f64 is also left in ``self.rewards64``.  Asynchronous on the current
+        stream; outputs may be caller-provided rollout-buffer slots."""
+        obs = self.obs if obs_out is None else obs_out
+        rew = self.rewards if rew_out is None else rew_out
+        done = self.dones if done_out is None else done_out
+        self._check_tensor(actions, (self.num_envs, self.num_agents, 2), torch.int32, "actions")
+        self._check_tensor(obs, self.obs.shape, torch.float32, "obs_out")
+        self._check_tensor(rew, self.rewards.shape, torch.float32, "rew_out")
+        self._check_tensor(done, self.dones.shape, torch.uint8, "done_out")
+        if term_obs_out is not None:
+            self._check_tensor(term_obs_out, self.obs.shape, torch.float32, "term_obs_out")
+        flags = _cabi.OC_FLAG_AUTO_RESET if self.auto_reset else 0
+        with self._device_guard():
+            self.lib.check(self.lib.step(self._handle, self._ptr(actions), self._ptr(obs), self._ptr(rew),
+                                         self._ptr(self.rewards64) if want_f64 else None, self._ptr(done),
+                                         self._ptr(term_obs_out), flags, self._stream()), "oc_step")
+        return obs, rew, done
+
+    def rollout(self, n_steps: int, obs_out=None, rew_out=None, done_out=None, actions_out=None):
+        """Fused synthetic rollout: ``n_steps`` steps in ONE launch, uniform random actions from
+        Philox on the device, auto-reset on.  Outputs are [n_steps, E, ...] (any may be None)."""
+        E, A, F = self.num_envs, self.num_agents, self.obs_width
+        if obs_out is not None:
+            self._check_tensor(obs_out, (n_steps, E, A, F), torch.float32, "obs_out")
+        if rew_out is not None:
+            self._check_tensor(rew_out, (n_steps, E, A), torch.float32, "rew_out")
+        if done_out is not None:
+            self._check_tensor(done_out, (n_steps, E), torch.uint8, "done_out")
+        if actions_out is not None:
+            self._check_tensor(actions_out, (n_steps, E, A, 2), torch.int32, "actions_out")
+        with self._device_guard():
+            self.lib.check(self.lib.rollout(self._handle, int(n_steps), self._ptr(obs_out), self._ptr(rew_out),
+                                            self._ptr(done_out), self._ptr(actions_out), self._stream()), "oc_rollout")
+
+    # ------------------------------------------------------------------ state / stats
+    def get_state(self) -> torch.Tensor:
+        st = torch.zeros((self.num_envs, _cabi.OC_STATE_WORDS), dtype=torch.int32, device=self.device)
+        with self._device_guard():
+            self.lib.check(self.lib.get_state(self._handle, self._ptr(st), self._stream()), "oc_get_state")
+        return st
+
+    def set_state(self, st: torch.Tensor):
+        self._check_tensor(st, (self.num_envs, _cabi.OC_STATE_WORDS), torch.int32, "state")
+        with self._device_guard():
+            self.lib.check(self.lib.set_state(self._handle, self._ptr(st), self._stream()), "oc_set_state")
+
+    def stats(self):
+        ep = torch.zeros((self.num_envs,), dtype=torch.int32, device=self.device)
+        lc = torch.zeros((self.num_envs,), dtype=torch.int32, device=self.device)
+        with self._device_guard():
+            self.lib.check(self.lib.get_stats(self._handle, self._ptr(ep), self._ptr(lc), self._stream()), "oc_get_stats")
+        return {"episodes": ep, "num_completed_subtasks": lc}
+
+    def launch_count(self) -> int:
+        return int(self.lib.launch_count(self._handle)) if self.lib.prefix == "oc_" else 0
+
+    def obs_dict(self, obs: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """Zero-copy per-key views ``[..., size]`` of flat observation rows."""
+        obs = self.obs if obs is None else obs
+        return {k: obs[..., s] for k, s in self.obs_layout.items()}
+
+    def decode_state(self, st: Optional[torch.Tensor] = None):
+        """Packed state -> readable numpy fields (layout: gym_comm_b200/csrc/oc_params.h)."""
+        w = (self.get_state() if st is None else st).cpu().numpy().view(np.uint32)
+        A, W = self.num_agents, self.level.width
+        cells = np.stack([(w[:, 4] >> (8 * k)) & 0xFF for k in range(A)], 1)
+        obj = w[:, 8:14]
+        out = dict(
+            t=w[:, 0] & 0xFFFF, next_stamp=(w[:, 0] >> 16) & 0xFF, nkeys=w[:, 0] >> 24,
+            episodes=w[:, 1], completed=w[:, 2], countbits=w[:, 3],
+            agent_cell=cells, agent_x=cells % W, agent_y=cells // W,
+            last_completed=w[:, 5] & 0xFF,
+            ranks=w[:, 6].astype(np.uint64) | (w[:, 7].astype(np.uint64) << np.uint64(32)),
+            obj_contents=obj & 0xF, obj_chopped=(obj >> 4) & 7, obj_holder=(obj >> 8) & 7,
+            obj_cell=(obj >> 16) & 0xFF, obj_stamp=obj >> 24,
+            comm0=w[:, 14] & 0xFFFF, comm1=w[:, 14] >> 16)
+        return out
+
+    def close(self):
+        if not self._closed and self._handle:
+            self.lib.destroy(self._handle)
+            self._closed = True
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+class OvercookedMultiEnv:
+    """The reference's ``OvercookedMultiEnv`` surface (gym_comm/envs/overcooked_env.py:15-297).
+
+    ``multi_step(ego_action, alt_action)`` takes ``(nav, comm)`` per player and returns
+    ``((obs0, obs1), (r, r), done, {})`` with the reference's 11-key numpy dict observations and the
+    reward as a Python float carrying the reference's f64 value; ``multi_reset()`` returns
+    ``(obs0, obs1)``.  It is a thin view on a 1-env (or env ``index`` of an E-env)
+    ``OvercookedVecEnv``; episodes do NOT auto-reset here (the reference leaves that to the caller,
+    pantheonrl/common/multiagentenv.py:217-243)."""
+
+    n_players = 2
+
+    def __init__(self, arglist, ego_agent_idx: int = 0, device="cuda", seed: int = 0,
+                 level_text: Optional[str] = None, subtasks=None, lib=None):
+        self.arglist = normalize(arglist)
+        if self.arglist.num_agents != 2:
+            raise ValueError("OvercookedMultiEnv is a 2-player SimultaneousEnv (multiagentenv.py:390-393); "
+                             "use OvercookedVecEnv for 3-4 agents")
+        if ego_agent_idx != 0:
+            raise ValueError("only ego_agent_idx=0 is supported (the only value the reference's trainer uses)")
+        self.ego_agent_idx = ego_agent_idx
+        self.vec = OvercookedVecEnv(self.arglist, num_envs=1, device=device, seed=seed, auto_reset=False,
+                                    level_text=level_text, subtasks=subtasks, lib=lib)
+        self.observation_space = self.vec.observation_space
+        self.action_space = self.vec.action_space
+        self.lA = len(NAV_ACTIONS)
+        self._actions = torch.zeros((1, 2, 2), dtype=torch.int32, device=self.vec.device)
+        self.multi_reset()
+
+    def _split(self, obs_row: np.ndarray):
+        out = {}
+        for k, s in self.vec.obs_layout.items():
+            v = obs_row[s]
+            if k in ("object_encodings_x", "object_encodings_y", "state_encodings", "is_hidden",
+                     "completed_subtasks"):
+                v = v.astype(np.int64)
+            elif k == "agent_is_holding":
+                v = v.astype(bool) if not self.arglist.ego_config["BLIND"] else v.astype(np.int64)
+            elif k in ("agent1_location", "agent2_location"):
+                v = v.astype(np.int64)
+            else:
+                v = v.astype(np.float64)
+            out[k] = v
+        return out
+
+    def get_observation2(self, agent_idx, radius=None):
+        """Observation of ``agent_idx`` at the configured ``fow_radius`` (the value training sees,
+        overcooked_env.py:282,297)."""
+        return self._split(self.vec.obs[0, agent_idx].cpu().numpy())
+
+    def multi_step(self, ego_action, alt_action):
+        acts = np.array([[[int(ego_action[0]), int(ego_action[1])], [int(alt_action[0]), int(alt_action[1])]]],
+                        dtype=np.int32)
+        self._actions.copy_(torch.from_numpy(acts))
+        obs, _, done = self.vec.step(self._actions, want_f64=True)
+        r = float(self.vec.rewards64[0].item())
+        o = obs[0].cpu().numpy()
+        return (self._split(o[0]), self._split(o[1])), (r, r), bool(done[0].item()), {}
+
+    def multi_reset(self, placements=None):
+        pl = None
+        if placements is not None:
+            pl = torch.tensor(np.asarray(placements, dtype=np.int32).reshape(1, -1), device=self.vec.device)
+        o = self.vec.reset(placements=pl)[0].cpu().numpy()
+        return (self._split(o[0]), self._split(o[1]))
+
+    def close(self):
+        self.vec.close()

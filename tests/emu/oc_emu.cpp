@@ -1,0 +1,148 @@
+// TEST INFRASTRUCTURE ONLY -- CPU emulation of the CUDA kernels' control flow.
+//
+// Executes the device functions of gym_comm_b200/csrc/oc_device.cuh (compiled for the host via
+// oc_emu_shim.h) warp by warp, lane by lane, behind the same C ABI names with an `emu_` prefix.
+// Purpose: debug the packed-state logic against the oracle in a container that has no GPU,
+// before spending GPU minutes.  It is NOT a fallback: the product package never loads it and
+// `oc_create` fails without a CUDA device.  Host-memory pointers everywhere.
+#define OCK_HOST_EMU 1
+#include "../../gym_comm_b200/csrc/oc_device.cuh"
+#include "../../gym_comm_b200/csrc/oc_host.hpp"
+
+#include <string>
+#include <vector>
+
+using namespace ock;
+
+struct emu_env {
+    OcParams p;
+    std::vector<uint8_t> blob;
+    std::vector<float> ts;
+    std::vector<uint4> state;
+    uint32_t rollout_step = 0;
+    int obs_off[OC_NUM_OBS_KEYS], obs_size[OC_NUM_OBS_KEYS];
+};
+static std::string g_err;
+
+template <typename F>
+static int dispatch(int A, int NOBJ, F&& f) {
+#define OC_CASE(a, n) if (A == a && NOBJ == n) return f(std::integral_constant<int, a>(), std::integral_constant<int, n>());
+    OC_CASE(2, 4) OC_CASE(3, 4) OC_CASE(4, 4) OC_CASE(2, 6) OC_CASE(3, 6) OC_CASE(4, 6)
+#undef OC_CASE
+    return OC_ERR_INVALID;
+}
+
+template <int A, int NOBJ, typename Body>
+static void for_each_warp(emu_env* h, float* obs, Body&& body) {
+    const OcParams& p = h->p;
+    const Tables tb = make_tables(p, h->blob.data());
+    std::vector<uint8_t> rows((size_t)32 * p.row_stride);
+    float wts[32];
+    for (int env0 = 0; env0 < p.E; env0 += 32) {
+        const int nvalid = std::min(32, p.E - env0);
+        std::fill(rows.begin(), rows.end(), 0);
+        for (int lane = 0; lane < nvalid; ++lane) body(tb, env0 + lane, lane, rows.data() + (size_t)lane * p.row_stride, wts);
+        if (obs)
+            for (int lane = 0; lane < 32; ++lane)
+                warp_expand_rows(p, rows.data(), wts, obs + (size_t)env0 * p.row_bytes, nvalid, lane);
+    }
+}
+
+extern "C" {
+
+const char* emu_last_error(void) { return g_err.c_str(); }
+
+int emu_create(const oc_config* c, emu_env** out) {
+    emu_env* h = new emu_env();
+    HostImage img;
+    if (compile_config(c, img, g_err) != OC_OK) { delete h; return OC_ERR_INVALID; }
+    h->p = img.p; h->blob = img.blob; h->ts = img.ts;
+    memcpy(h->obs_off, img.obs_off, sizeof(h->obs_off));
+    memcpy(h->obs_size, img.obs_size, sizeof(h->obs_size));
+    h->p.blob = h->blob.data(); h->p.ts_table = h->ts.data();
+    h->state.assign((size_t)h->p.E * 4, uint4{0, 0, 0, 0});
+    dispatch(h->p.A, h->p.NOBJ, [&](auto a, auto n) -> int {
+        constexpr int AA = decltype(a)::value, NN = decltype(n)::value;
+        for_each_warp<AA, NN>(h, nullptr, [&](const Tables& tb, int env, int lane, uint8_t* row, float* wts) {
+            Env<AA, NN> e;
+            reset_one_env<AA, NN>(e, h->p, tb, (uint32_t)env, true, nullptr, nullptr, false, row, wts, lane);
+            store_env<AA, NN>(e, h->state.data(), h->p.E, env);
+        });
+        return 0;
+    });
+    *out = h;
+    return OC_OK;
+}
+int emu_destroy(emu_env* h) { delete h; return OC_OK; }
+int emu_obs_width(const emu_env* h) { return h->p.F; }
+int emu_obs_layout(const emu_env* h, int32_t* off, int32_t* sz) {
+    for (int i = 0; i < OC_NUM_OBS_KEYS; ++i) { off[i] = h->obs_off[i]; sz[i] = h->obs_size[i]; }
+    return OC_OK;
+}
+
+int emu_reset(emu_env* h, const uint8_t* mask, const int32_t* placements, float* obs, void*) {
+    return dispatch(h->p.A, h->p.NOBJ, [&](auto a, auto n) -> int {
+        constexpr int AA = decltype(a)::value, NN = decltype(n)::value;
+        for_each_warp<AA, NN>(h, obs, [&](const Tables& tb, int env, int lane, uint8_t* row, float* wts) {
+            Env<AA, NN> e;
+            load_env<AA, NN>(e, h->state.data(), h->p.E, env);
+            reset_one_env<AA, NN>(e, h->p, tb, (uint32_t)env, false, mask, placements, obs != nullptr, row, wts, lane);
+            store_env<AA, NN>(e, h->state.data(), h->p.E, env);
+        });
+        return OC_OK;
+    });
+}
+
+int emu_step(emu_env* h, const int32_t* actions, float* obs, float* rew32, double* rew64, uint8_t* done,
+             float* term_obs, uint32_t flags, void*) {
+    return dispatch(h->p.A, h->p.NOBJ, [&](auto a, auto n) -> int {
+        constexpr int AA = decltype(a)::value, NN = decltype(n)::value;
+        for_each_warp<AA, NN>(h, obs, [&](const Tables& tb, int env, int lane, uint8_t* row, float* wts) {
+            Env<AA, NN> e;
+            load_env<AA, NN>(e, h->state.data(), h->p.E, env);
+            int nav[AA], comm[AA];
+            for (int k = 0; k < AA; ++k) { nav[k] = actions[((size_t)env * AA + k) * 2] & 3; comm[k] = actions[((size_t)env * AA + k) * 2 + 1]; }
+            step_one_env<AA, NN>(e, h->p, tb, nav, comm[0], comm[1], (uint32_t)env, row, wts, lane, rew32, rew64, done, term_obs, flags);
+            store_env<AA, NN>(e, h->state.data(), h->p.E, env);
+        });
+        return OC_OK;
+    });
+}
+
+int emu_rollout(emu_env* h, int32_t n_steps, float* obs, float* rew32, uint8_t* done, int32_t* actions_out, void*) {
+    const size_t step_floats = (size_t)h->p.E * h->p.row_bytes;
+    int rc = dispatch(h->p.A, h->p.NOBJ, [&](auto a, auto n) -> int {
+        constexpr int AA = decltype(a)::value, NN = decltype(n)::value;
+        for (int s = 0; s < n_steps; ++s)
+            for_each_warp<AA, NN>(h, obs ? obs + (size_t)s * step_floats : nullptr,
+                                  [&](const Tables& tb, int env, int lane, uint8_t* row, float* wts) {
+                Env<AA, NN> e;
+                load_env<AA, NN>(e, h->state.data(), h->p.E, env);
+                rollout_one_env<AA, NN>(e, h->p, tb, (uint32_t)env, (uint32_t)s, h->rollout_step, row, wts, lane,
+                                        obs != nullptr, rew32, done, actions_out);
+                store_env<AA, NN>(e, h->state.data(), h->p.E, env);
+            });
+        return OC_OK;
+    });
+    h->rollout_step += (uint32_t)n_steps;
+    return rc;
+}
+
+int emu_get_state(emu_env* h, uint32_t* state, void*) {
+    for (int env = 0; env < h->p.E; ++env)
+        for (int pl = 0; pl < 4; ++pl) reinterpret_cast<uint4*>(state)[(size_t)env * 4 + pl] = h->state[(size_t)pl * h->p.E + env];
+    return OC_OK;
+}
+int emu_set_state(emu_env* h, const uint32_t* state, void*) {
+    for (int env = 0; env < h->p.E; ++env)
+        for (int pl = 0; pl < 4; ++pl) h->state[(size_t)pl * h->p.E + env] = reinterpret_cast<const uint4*>(state)[(size_t)env * 4 + pl];
+    return OC_OK;
+}
+int emu_get_stats(emu_env* h, uint32_t* episodes, uint32_t* last_completed, void*) {
+    for (int i = 0; i < h->p.E; ++i) {
+        if (episodes) episodes[i] = h->state[i].y;
+        if (last_completed) last_completed[i] = h->state[(size_t)h->p.E + i].y & 0xFFu;
+    }
+    return OC_OK;
+}
+}  // extern "C"
