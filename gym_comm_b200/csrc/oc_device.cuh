@@ -310,36 +310,52 @@ __device__ __forceinline__ void env_step(Env<A, NOBJ>& e, const OcParams& p, con
         nf[f] = (fresh_cell[f] >= 0) ? __popc(~e.completed & p.chop_mask[f]) : 0;
         lenU += nf[f];
     }
-    // (2) item-pair distances: agent independent.  pd(src, .) == MAX_PATH unless src is a floor
-    // cell, i.e. unless the first item's object is being carried (world.py:126-127).
+    // (2) item-pair distances (:319-363): agent independent.  Items = Plate + the Foods of
+    // recipes[0]; pairs in combinations() order (P,f0) (P,f1) (P,f2) (f0,f1) (f0,f2) (f1,f2).
+    // pd(src, .) == MAX_PATH unless src is a floor cell, i.e. unless the FIRST item's object is
+    // being carried (world.py:126-127), and each Food lives in exactly one object (domain rule), so
+    // only a handful of table look-ups are ever needed.
     int lenP = p.npairs, minP = p.M;
     {
-        int m[OCK_MAX_PAIRS];
-#pragma unroll
-        for (int q = 0; q < OCK_MAX_PAIRS; ++q) m[q] = p.M;
         bool any_held = false;
 #pragma unroll
         for (int s = 0; s < NOBJ; ++s) any_held |= (obj_contents(e.obj[s]) != 0 && obj_holder(e.obj[s]) != OCK_HOLDER_NONE);
         if (any_held) {
+            int fc[3] = {-1, -1, -1};
+            bool fh[3] = {false, false, false};
 #pragma unroll
             for (int s = 0; s < NOBJ; ++s) {
-                const uint32_t os = e.obj[s];
-                if (obj_contents(os) == 0 || obj_holder(os) == OCK_HOLDER_NONE) continue;
-                const uint8_t* row = tb.pd + obj_cell(os) * p.ncell;
+                const uint32_t o = e.obj[s];
 #pragma unroll
-                for (int r = 0; r < NOBJ; ++r) {
-                    const uint32_t orr = e.obj[r];
-                    if (obj_contents(orr) == 0) continue;
-                    const int d = row[obj_cell(orr)];
+                for (int i = 0; i < 3; ++i)
+                    if (i < p.nfi && (o & p.fi_bit[i])) { fc[i] = (int)obj_cell(o); fh[i] = obj_holder(o) != OCK_HOLDER_NONE; }
+            }
+            int mP[3] = {p.M, p.M, p.M};
 #pragma unroll
-                    for (int q = 0; q < OCK_MAX_PAIRS; ++q)
-                        if (q < p.npairs && (os & p.pair_x[q]) && (orr & p.pair_y[q])) m[q] = min(m[q], d);
+            for (int s = 0; s < NOBJ; ++s) {
+                const uint32_t o = e.obj[s];
+                if ((o & 8u) && obj_holder(o) != OCK_HOLDER_NONE) {          // a carried plate-bearing object
+                    const uint8_t* row = tb.pd + obj_cell(o) * p.ncell;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+                        if (i < p.nfi && fc[i] >= 0) mP[i] = min(mP[i], (int)row[fc[i]]);
                 }
             }
             lenP = 0;
 #pragma unroll
-            for (int q = 0; q < OCK_MAX_PAIRS; ++q)
-                if (q < p.npairs && m[q] != 0) { lenP += 1; minP = min(minP, m[q]); }
+            for (int i = 0; i < 3; ++i)
+                if (i < p.nfi && mP[i] != 0) { lenP += 1; minP = min(minP, mP[i]); }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                for (int j = i + 1; j < 3; ++j) {
+                    if (j < p.nfi) {
+                        int m = p.M;
+                        if (fh[i] && fc[j] >= 0) m = tb.pd[fc[i] * p.ncell + fc[j]];
+                        if (m != 0) { lenP += 1; minP = min(minP, m); }
+                    }
+                }
+            }
         }
     }
     // (3) Deliver subtasks: dish cell per subtask (table order)
@@ -387,32 +403,36 @@ __device__ __forceinline__ void env_step(Env<A, NOBJ>& e, const OcParams& p, con
 
 // ---------------------------------------------------------------------------------------------
 // get_observation2 (gym_comm/envs/overcooked_env.py:105-159) for every observer of one env,
-// written as one signed byte per feature into this env's shared-memory row; the timestep
-// feature is marked with TS_MARK and its float goes to ts_out.
-#define OCK_TS_MARK 0x80
+// written as ONE BYTE PER FEATURE (value + 128) into this env's shared-memory row.  Rows are
+// pre-filled with 0x80 (= 0.0).  The timestep feature is left at 0.0 here; its float is stored
+// by the owning thread after the warp's cooperative expansion (store_timesteps).
+#define OCK_BIAS 128u
 
 template <int A, int NOBJ>
 __device__ __forceinline__ void env_build_rows(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
-                                               uint8_t* __restrict__ row /* zero-filled, row_stride bytes */) {
-    // winner object per channel: last in world.objects iteration order = max (key rank, stamp)
-    int wx[4], wy[4];
-    uint32_t wst[4], wkey[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) { wx[c] = 0; wy[c] = 0; wst[c] = 0; wkey[c] = 0; }   // key 0 = channel absent
+                                               uint8_t* __restrict__ row /* 0x80-filled, row_stride bytes */) {
+    // per channel the object that is LAST in world.objects iteration order among those containing
+    // it (last writer wins, :121-131).  Each Food lives in exactly one object; only the Plate
+    // channel can have several candidates, ordered by (key creation rank, insertion stamp).
+    int wx[4] = {0, 0, 0, 0}, wy[4] = {0, 0, 0, 0};
+    uint32_t wst[4] = {0, 0, 0, 0};
+    bool has[4] = {false, false, false, false};
+    uint32_t pkey = 0;
+    uint32_t holdmask = 0;                 // bit k: agent k holds something
 #pragma unroll
     for (int s = 0; s < NOBJ; ++s) {
         const uint32_t o = e.obj[s];
         const uint32_t oc = obj_contents(o);
         if (oc == 0) continue;
-        const uint32_t key = ((uint32_t)((e.ranks >> (4 * oc)) & 15ull) << 8) | (o >> 24);
         const uint32_t cell = obj_cell(o);
         const int x = tb.xy[cell * 2], y = tb.xy[cell * 2 + 1];
+        holdmask |= (1u << obj_holder(o));
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            if (((oc >> c) & 1u) && key > wkey[c]) {
-                wkey[c] = key; wx[c] = x; wy[c] = y;
-                wst[c] = (c < 3) ? ((o >> (4 + c)) & 1u) : 0u;
-            }
+        for (int c = 0; c < 3; ++c)
+            if ((oc >> c) & 1u) { has[c] = true; wx[c] = x; wy[c] = y; wst[c] = (o >> (4 + c)) & 1u; }
+        if (oc & 8u) {
+            const uint32_t key = ((uint32_t)((e.ranks >> (4 * oc)) & 15ull) << 8) | (o >> 24);
+            if (key > pkey) { pkey = key; has[3] = true; wx[3] = x; wy[3] = y; }
         }
     }
     const int x0 = tb.xy[e.acell[0] * 2], y0 = tb.xy[e.acell[0] * 2 + 1];
@@ -422,100 +442,100 @@ __device__ __forceinline__ void env_build_rows(const Env<A, NOBJ>& e, const OcPa
     for (int k = 0; k < A; ++k) {
         uint8_t* r = row + k * p.F;
         const bool blind = p.blind[k] != 0;
-        if (c0 != OCK_COMM_NONE) r[p.off_a1comm + c0] = 1;
-        if (c1 != OCK_COMM_NONE) r[p.off_a2comm + c1] = 1;
-        r[p.off_a1loc] = blind ? 0 : x0;  r[p.off_a1loc + 1] = blind ? 0 : y0;     // :139-143
-        r[p.off_a2loc] = blind ? 0 : x1;  r[p.off_a2loc + 1] = blind ? 0 : y1;
-        bool holding = false;
-#pragma unroll
-        for (int s = 0; s < NOBJ; ++s) holding |= (obj_contents(e.obj[s]) != 0 && obj_holder(e.obj[s]) == (uint32_t)k);
-        r[p.off_hold] = (!p.ego_blind && holding) ? 1 : 0;                          // :154
-        r[p.off_hold + 1] = 0;
-        for (int i = 0; i < p.S; ++i) r[p.off_completed + i] = (e.completed >> i) & 1u;
-        const int ax = tb.xy[e.acell[k] * 2], ay = tb.xy[e.acell[k] * 2 + 1];
+        if (c0 != OCK_COMM_NONE) r[p.off_a1comm + c0] = OCK_BIAS + 1;
+        if (c1 != OCK_COMM_NONE) r[p.off_a2comm + c1] = OCK_BIAS + 1;
+        r[p.off_a1loc] = OCK_BIAS + (blind ? 0 : x0);  r[p.off_a1loc + 1] = OCK_BIAS + (blind ? 0 : y0);   // :139-143
+        r[p.off_a2loc] = OCK_BIAS + (blind ? 0 : x1);  r[p.off_a2loc + 1] = OCK_BIAS + (blind ? 0 : y1);
+        r[p.off_hold] = OCK_BIAS + ((!p.ego_blind && ((holdmask >> k) & 1u)) ? 1 : 0);                      // :154
+        for (int i = 0; i < p.S; ++i) r[p.off_completed + i] = OCK_BIAS + ((e.completed >> i) & 1u);
+        int ax = x0, ay = y0;
+        if (k == 1) { ax = x1; ay = y1; }
+        if (k >= 2) { ax = tb.xy[e.acell[k] * 2]; ay = tb.xy[e.acell[k] * 2 + 1]; }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             int dx = 0, dy = 0; uint32_t st = 0, hid = 1;
             if (!blind) {
-                if (wkey[c] != 0) { dx = wx[c] - ax; dy = wy[c] - ay; st = wst[c]; }
+                if (has[c]) { dx = wx[c] - ax; dy = wy[c] - ay; st = wst[c]; }
                 const bool near = (abs(dx) + abs(dy)) <= p.fow;                     // :133-135
                 hid = near ? 0u : 1u;
                 if (near) { dx = 0; dy = 0; }
             }
-            r[p.off_hidden + c] = (uint8_t)hid;
-            r[p.off_encx + c] = (uint8_t)(int8_t)dx;
-            r[p.off_ency + c] = (uint8_t)(int8_t)dy;
-            r[p.off_state + c] = (uint8_t)st;
+            r[p.off_hidden + c] = (uint8_t)(OCK_BIAS + hid);
+            r[p.off_encx + c] = (uint8_t)(OCK_BIAS + dx);
+            r[p.off_ency + c] = (uint8_t)(OCK_BIAS + dy);
+            r[p.off_state + c] = (uint8_t)(OCK_BIAS + st);
         }
-        r[p.off_ts] = OCK_TS_MARK;
     }
 }
 
-// warp-cooperative zero fill of the warp's 32 byte-rows
+// warp-cooperative fill of the warp's 32 byte-rows with 0x80 (= 0.0)
 __device__ __forceinline__ void warp_zero_rows(uint8_t* wrows, int bytes, int lane) {
     uint4* d = reinterpret_cast<uint4*>(wrows);
-    for (int i = lane; i < (bytes >> 4); i += 32) d[i] = make_uint4(0, 0, 0, 0);
+    for (int i = lane; i < (bytes >> 4); i += 32) d[i] = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+}
+
+// byte k of w (value + 128) -> float, on the integer/FP32 pipes only: PRMT builds 0x4B0000bb
+// (= 8388608 + bb as a float), one FADD removes 8388608 + 128.  (I2F runs at quarter rate.)
+__device__ __forceinline__ float biased_byte_to_float(uint32_t w, int k) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + (uint32_t)k)) - 8388736.0f;
 }
 
 // warp-cooperative expansion: 32 byte-rows in shared memory -> float32 rows in global memory,
 // consecutive lanes writing consecutive 16-byte (or 4-byte) pieces of one contiguous region.
 __device__ __forceinline__ void warp_expand_rows(const OcParams& p, const uint8_t* __restrict__ wrows,
-                                                 const float* __restrict__ wts /* [32] timestep per env */,
                                                  float* __restrict__ out /* warp's first env row */,
                                                  int nvalid, int lane) {
     if ((p.row_bytes & 3) == 0) {
         const int r4 = p.row_bytes >> 2;             // float4 per env row
         const int total = nvalid * r4;
-        int env = 0, j = lane;
-        while (j >= r4) { j -= r4; ++env; }
         float4* o4 = reinterpret_cast<float4*>(out);
+        const bool contiguous = p.row_stride == p.row_bytes;
+#pragma unroll 2
         for (int idx = lane; idx < total; idx += 32) {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(wrows + env * p.row_stride + 4 * j);
-            float4 v;
-            v.x = (float)(int8_t)(w & 0xFF);
-            v.y = (float)(int8_t)((w >> 8) & 0xFF);
-            v.z = (float)(int8_t)((w >> 16) & 0xFF);
-            v.w = (float)(int8_t)(w >> 24);
-            const uint32_t z = w ^ 0x80808080u;                     // any byte == TS_MARK ?
-            if ((z - 0x01010101u) & ~z & 0x80808080u) {
-                const float ts = wts[env];
-                if ((w & 0xFF) == OCK_TS_MARK) v.x = ts;
-                if (((w >> 8) & 0xFF) == OCK_TS_MARK) v.y = ts;
-                if (((w >> 16) & 0xFF) == OCK_TS_MARK) v.z = ts;
-                if ((w >> 24) == OCK_TS_MARK) v.w = ts;
+            int off = idx;                                          // word offset inside the warp's rows
+            if (!contiguous) {                                      // padded rows: env = idx / r4 by magic multiply
+                const int env = (int)__umulhi((uint32_t)idx, p.r4_magic);
+                off = env * (p.row_stride >> 2) + (idx - env * r4);
             }
-            __stcs(o4 + idx, v);                                    // streaming store: written once, read by the learner later
-            j += 32;
-            while (j >= r4) { j -= r4; ++env; }
+            const uint32_t w = reinterpret_cast<const uint32_t*>(wrows)[off];
+            float4 v;
+            v.x = biased_byte_to_float(w, 0);
+            v.y = biased_byte_to_float(w, 1);
+            v.z = biased_byte_to_float(w, 2);
+            v.w = biased_byte_to_float(w, 3);
+            __stcs(o4 + idx, v);                                    // streaming: written once, read later by the learner
         }
     } else {
         const int rf = p.row_bytes;
         const int total = nvalid * rf;
-        int env = 0, j = lane;
-        while (j >= rf) { j -= rf; ++env; }
         for (int idx = lane; idx < total; idx += 32) {
-            const uint8_t b = wrows[env * p.row_stride + j];
-            out[idx] = (b == OCK_TS_MARK) ? wts[env] : (float)(int8_t)b;
-            j += 32;
-            while (j >= rf) { j -= rf; ++env; }
+            const int env = (int)__umulhi((uint32_t)idx, p.rf_magic);
+            const uint8_t b = wrows[env * p.row_stride + (idx - env * rf)];
+            out[idx] = (float)((int)b - 128);
         }
     }
+}
+
+// after the expansion (and a __syncwarp): each thread stores the timestep feature of its own env
+// rows, timestep = float32(t / max_num_timesteps)  (overcooked_env.py:146)
+template <int A>
+__device__ __forceinline__ void store_timesteps(const OcParams& p, float* __restrict__ env_row, float ts) {
+#pragma unroll
+    for (int k = 0; k < A; ++k) env_row[k * p.F + p.off_ts] = ts;
 }
 
 // a single thread expands its own row (rare path: terminal observations)
 __device__ __forceinline__ void thread_expand_row(const OcParams& p, const uint8_t* __restrict__ row, float ts,
                                                   float* __restrict__ out) {
-    for (int j = 0; j < p.row_bytes; ++j) {
-        const uint8_t b = row[j];
-        out[j] = (b == OCK_TS_MARK) ? ts : (float)(int8_t)b;
-    }
+    for (int j = 0; j < p.row_bytes; ++j) out[j] = (float)((int)row[j] - 128);
+    for (int k = 0; k < p.A; ++k) out[k * p.F + p.off_ts] = ts;
 }
 
 template <int A, int NOBJ>
-__device__ __forceinline__ void finish_obs(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
-                                           uint8_t* myrow, float* wts, int lane) {
+__device__ __forceinline__ float finish_obs(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
+                                            uint8_t* myrow) {
     env_build_rows<A, NOBJ>(e, p, tb, myrow);
-    wts[lane] = __ldg(p.ts_table + (e.w0 & 0xFFFFu));
+    return __ldg(p.ts_table + (e.w0 & 0xFFFFu));
 }
 
 // terminal bookkeeping + in-place reset of one finished env (SB3 VecEnv auto-reset contract)
@@ -525,7 +545,7 @@ __device__ __forceinline__ void finish_episode(Env<A, NOBJ>& e, const OcParams& 
     if (term_row != nullptr) {                       // infos["terminal_observation"]
         env_build_rows<A, NOBJ>(e, p, tb, myrow);
         thread_expand_row(p, myrow, __ldg(p.ts_table + (e.w0 & 0xFFFFu)), term_row);
-        for (int j = 0; j < (p.row_stride >> 2); ++j) reinterpret_cast<uint32_t*>(myrow)[j] = 0u;
+        for (int j = 0; j < (p.row_stride >> 2); ++j) reinterpret_cast<uint32_t*>(myrow)[j] = 0x80808080u;
     }
     e.w5 = (e.w5 & ~0xFFu) | (uint32_t)__popc(e.completed);    // episode_recorder.py:29
     e.episodes += 1;
@@ -534,9 +554,9 @@ __device__ __forceinline__ void finish_episode(Env<A, NOBJ>& e, const OcParams& 
 
 // everything one thread does for its env in oc_step between loading and storing the state
 template <int A, int NOBJ>
-__device__ __forceinline__ void step_one_env(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
-                                             const int (&nav)[A], int comm0, int comm1, uint32_t env,
-                                             uint8_t* myrow, float* wts, int lane,
+__device__ __forceinline__ float step_one_env(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
+                                              const int (&nav)[A], int comm0, int comm1, uint32_t env,
+                                              uint8_t* myrow,
                                              float* __restrict__ rew32, double* __restrict__ rew64,
                                              uint8_t* __restrict__ done_out, float* __restrict__ term_obs,
                                              uint32_t flags) {
@@ -554,16 +574,16 @@ __device__ __forceinline__ void step_one_env(Env<A, NOBJ>& e, const OcParams& p,
     done_out[env] = done ? 1 : 0;
     if (done && (flags & 1u /*OC_FLAG_AUTO_RESET*/))
         finish_episode<A, NOBJ>(e, p, tb, myrow, term_obs ? term_obs + (size_t)env * p.row_bytes : nullptr, env);
-    finish_obs<A, NOBJ>(e, p, tb, myrow, wts, lane);
+    return finish_obs<A, NOBJ>(e, p, tb, myrow);
 }
 
 // one env, one step of the fused synthetic rollout: Philox actions (nav ~ U{0..3}, comm ~ U{0..C-1}),
 // auto-reset always on.  Draw layout (same in oracle/oc_oracle.c): counter (env, global step,
 // 'ACTS', 0); nav_k = bits [2k, 2k+2) of word 0; comm_0/1 = mulhi(word 1/2, C).
 template <int A, int NOBJ>
-__device__ __forceinline__ void rollout_one_env(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
-                                                uint32_t env, uint32_t s, uint32_t step0,
-                                                uint8_t* myrow, float* wts, int lane, bool want_obs,
+__device__ __forceinline__ float rollout_one_env(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
+                                                 uint32_t env, uint32_t s, uint32_t step0,
+                                                 uint8_t* myrow, bool want_obs,
                                                 float* __restrict__ rew32, uint8_t* __restrict__ done_out,
                                                 int32_t* __restrict__ actions_out) {
     uint32_t r[4];
@@ -586,15 +606,15 @@ __device__ __forceinline__ void rollout_one_env(Env<A, NOBJ>& e, const OcParams&
     }
     if (done_out != nullptr) done_out[(size_t)s * p.E + env] = done ? 1 : 0;
     if (done) finish_episode<A, NOBJ>(e, p, tb, myrow, nullptr, env);
-    if (want_obs) finish_obs<A, NOBJ>(e, p, tb, myrow, wts, lane);
+    return want_obs ? finish_obs<A, NOBJ>(e, p, tb, myrow) : 0.0f;
 }
 
 // oc_reset / initial bring-up of one env
 template <int A, int NOBJ>
-__device__ __forceinline__ void reset_one_env(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb, uint32_t env,
-                                              bool initial, const uint8_t* __restrict__ mask,
-                                              const int32_t* __restrict__ placements, bool want_obs,
-                                              uint8_t* myrow, float* wts, int lane) {
+__device__ __forceinline__ float reset_one_env(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb, uint32_t env,
+                                               bool initial, const uint8_t* __restrict__ mask,
+                                               const int32_t* __restrict__ placements, bool want_obs,
+                                               uint8_t* myrow) {
     const int32_t* pl = placements ? placements + (size_t)env * p.nrandom : nullptr;
     if (initial) {
         e.episodes = 0; e.w5 = 0; e.w15 = 0;
@@ -604,7 +624,7 @@ __device__ __forceinline__ void reset_one_env(Env<A, NOBJ>& e, const OcParams& p
         e.episodes += 1;
         env_reset<A, NOBJ>(e, p, tb, pl, env);
     }
-    if (want_obs) finish_obs<A, NOBJ>(e, p, tb, myrow, wts, lane);
+    return want_obs ? finish_obs<A, NOBJ>(e, p, tb, myrow) : 0.0f;
 }
 
 }  // namespace ock

@@ -101,8 +101,13 @@ static inline int compile_config(const oc_config* c, HostImage& h, std::string& 
     p.W = W; p.H = H; p.ncell = n; p.T = c->max_num_timesteps; p.C = C; p.S = S;
     p.F = 23 + S + 2 * C; p.fow = c->fow_radius; p.M = M;
     p.row_bytes = A * p.F;
+    // byte rows in shared memory: an ODD number of 32-bit words per env makes the per-thread byte
+    // scatter bank-conflict free; when row_bytes itself is such a number the rows stay contiguous
+    // and the expansion needs no index arithmetic at all
     p.row_stride = (int)align_up(p.row_bytes, 4);
-    if (((p.row_stride >> 2) & 1) == 0) p.row_stride += 4;          // odd word stride: conflict-free byte scatter
+    if (((p.row_stride >> 2) & 1) == 0) p.row_stride += 4;
+    p.r4_magic = (p.row_bytes >= 4) ? (uint32_t)((1ull << 32) / (uint64_t)(p.row_bytes >> 2)) + 1u : 0u;
+    p.rf_magic = (uint32_t)((1ull << 32) / (uint64_t)p.row_bytes) + 1u;
     for (int k = 0; k < OC_MAX_AGENTS; ++k) {
         p.can_move[k] = c->can_move[k]; p.allergic[k] = c->allergic[k]; p.blind[k] = c->blind[k];
         p.start_cell[k] = c->start_cell[k];
@@ -167,9 +172,15 @@ static inline int compile_config(const oc_config* c, HostImage& h, std::string& 
         }
     }
     if (p.ndeliver == 0) OC_BAD("no delivery subtask (overcooked_environment.py:251 asserts)");
-    p.npairs = 0;
-    for (int i = 0; i < c->num_items; ++i)
-        for (int j = i + 1; j < c->num_items; ++j) { p.pair_x[p.npairs] = c->items[i]; p.pair_y[p.npairs] = c->items[j]; ++p.npairs; }
+    // items = ['Plate'] + Foods of recipes[0] (overcooked_environment.py:319-321)
+    if (c->items[0] != 8) OC_BAD("items[0] must be Plate");
+    p.nfi = c->num_items - 1;
+    for (int i = 0; i < p.nfi; ++i) {
+        const int b = c->items[1 + i];
+        if (b != 1 && b != 2 && b != 4) OC_BAD("items[1..] must be single Food bits");
+        p.fi_bit[i] = (uint8_t)b;
+    }
+    p.npairs = c->num_items * (c->num_items - 1) / 2;
 
     // tables
     std::vector<uint8_t> pd;

@@ -20,7 +20,7 @@ using namespace ock;
 // kernels
 // =============================================================================================
 
-// dynamic shared memory: [table blob][per warp: 32 byte-rows][per warp: 32 timestep floats]
+// dynamic shared memory: [table blob][per warp: 32 byte-rows]
 template <int A, int NOBJ>
 __global__ void __launch_bounds__(256)
 oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
@@ -43,21 +43,23 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
     }
     load_tables(p, smem);
     uint8_t* wrows = smem + p.blob_bytes + (size_t)warp * 32 * p.row_stride;
-    float* wts = reinterpret_cast<float*>(smem + p.blob_bytes + (size_t)nwarps * 32 * p.row_stride) + warp * 32;
     warp_zero_rows(wrows, 32 * p.row_stride, lane);
     __syncthreads();
     const Tables tb = make_tables(p, smem);
     uint8_t* myrow = wrows + lane * p.row_stride;
 
+    float ts = 0.0f;
     if (valid) {
-        step_one_env<A, NOBJ>(e, p, tb, nav, comm[0], comm[1], (uint32_t)env, myrow, wts, lane,
-                              rew32, rew64, done_out, term_obs, flags);
+        ts = step_one_env<A, NOBJ>(e, p, tb, nav, comm[0], comm[1], (uint32_t)env, myrow,
+                                   rew32, rew64, done_out, term_obs, flags);
         store_env<A, NOBJ>(e, state, p.E, env);
     }
     __syncwarp();
     const int env0 = blockIdx.x * blockDim.x + warp * 32;
     const int nvalid = min(32, p.E - env0);
-    if (nvalid > 0) warp_expand_rows(p, wrows, wts, obs + (size_t)env0 * p.row_bytes, nvalid, lane);
+    if (nvalid > 0) warp_expand_rows(p, wrows, obs + (size_t)env0 * p.row_bytes, nvalid, lane);
+    __syncwarp();                                   // order the float4 stores before the timestep patch
+    if (valid) store_timesteps<A>(p, obs + (size_t)env * p.row_bytes, ts);
 }
 
 // n_steps steps per launch, state in registers, Philox actions (SURVEY section 8d synthetic inputs)
@@ -74,7 +76,6 @@ oc_rollout_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
     if (valid) load_env<A, NOBJ>(e, state, p.E, env);
     load_tables(p, smem);
     uint8_t* wrows = smem + p.blob_bytes + (size_t)warp * 32 * p.row_stride;
-    float* wts = reinterpret_cast<float*>(smem + p.blob_bytes + (size_t)nwarps * 32 * p.row_stride) + warp * 32;
     __syncthreads();
     const Tables tb = make_tables(p, smem);
     uint8_t* myrow = wrows + lane * p.row_stride;
@@ -84,15 +85,17 @@ oc_rollout_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
 
     for (int s = 0; s < n_steps; ++s) {
         if (obs != nullptr) { warp_zero_rows(wrows, 32 * p.row_stride, lane); __syncwarp(); }
+        float ts = 0.0f;
         if (valid) {
-            rollout_one_env<A, NOBJ>(e, p, tb, (uint32_t)env, (uint32_t)s, step0, myrow, wts, lane,
-                                     obs != nullptr, rew32, done_out, actions_out);
+            ts = rollout_one_env<A, NOBJ>(e, p, tb, (uint32_t)env, (uint32_t)s, step0, myrow,
+                                          obs != nullptr, rew32, done_out, actions_out);
         }
         if (obs != nullptr) {
+            float* step_obs = obs + (size_t)s * step_floats;
             __syncwarp();
-            if (nvalid > 0)
-                warp_expand_rows(p, wrows, wts, obs + (size_t)s * step_floats + (size_t)env0 * p.row_bytes, nvalid, lane);
+            if (nvalid > 0) warp_expand_rows(p, wrows, step_obs + (size_t)env0 * p.row_bytes, nvalid, lane);
             __syncwarp();
+            if (valid) store_timesteps<A>(p, step_obs + (size_t)env * p.row_bytes, ts);
         }
     }
     if (valid) store_env<A, NOBJ>(e, state, p.E, env);
@@ -111,19 +114,23 @@ oc_reset_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, c
     if (valid && !initial) load_env<A, NOBJ>(e, state, p.E, env);
     load_tables(p, smem);
     uint8_t* wrows = smem + p.blob_bytes + (size_t)warp * 32 * p.row_stride;
-    float* wts = reinterpret_cast<float*>(smem + p.blob_bytes + (size_t)nwarps * 32 * p.row_stride) + warp * 32;
     warp_zero_rows(wrows, 32 * p.row_stride, lane);
     __syncthreads();
     const Tables tb = make_tables(p, smem);
+    float ts = 0.0f;
     if (valid) {
-        reset_one_env<A, NOBJ>(e, p, tb, (uint32_t)env, initial != 0, mask, placements, obs != nullptr,
-                               wrows + lane * p.row_stride, wts, lane);
+        ts = reset_one_env<A, NOBJ>(e, p, tb, (uint32_t)env, initial != 0, mask, placements, obs != nullptr,
+                                    wrows + lane * p.row_stride);
         store_env<A, NOBJ>(e, state, p.E, env);
     }
     __syncwarp();
     const int env0 = blockIdx.x * blockDim.x + warp * 32;
     const int nvalid = min(32, p.E - env0);
-    if (obs != nullptr && nvalid > 0) warp_expand_rows(p, wrows, wts, obs + (size_t)env0 * p.row_bytes, nvalid, lane);
+    if (obs != nullptr) {
+        if (nvalid > 0) warp_expand_rows(p, wrows, obs + (size_t)env0 * p.row_bytes, nvalid, lane);
+        __syncwarp();
+        if (valid) store_timesteps<A>(p, obs + (size_t)env * p.row_bytes, ts);
+    }
 }
 
 // packed state <-> [E, 16] u32 rows
@@ -207,7 +214,7 @@ extern "C" int oc_create(const oc_config* c, oc_env** out) {
     const char* tenv = getenv("OC_BLOCK_THREADS");
     h->threads = tenv ? atoi(tenv) : 64;
     if (h->threads < 32 || h->threads > 256 || (h->threads & 31)) h->threads = 64;
-    auto smem_for = [&](int threads) { return (size_t)p.blob_bytes + (size_t)(threads / 32) * (32 * (size_t)p.row_stride + 128); };
+    auto smem_for = [&](int threads) { return (size_t)p.blob_bytes + (size_t)(threads / 32) * (32 * (size_t)p.row_stride); };
     while (h->threads > 32 && smem_for(h->threads) > 200 * 1024) h->threads -= 32;
     h->smem_bytes = smem_for(h->threads);
     if (h->smem_bytes > 227 * 1024) { delete h; return fail(OC_ERR_INVALID, "observation row too wide for shared memory"); }

@@ -31,7 +31,8 @@ struct OcParams {
     int32_t T, C, S, F;
     int32_t fow, M;
     int32_t row_bytes;        // A * F
-    int32_t row_stride;       // smem byte-row stride per env (multiple of 4, odd word count)
+    int32_t row_stride;       // smem byte-row stride per env: == row_bytes when that is an odd number of
+                              // words (rows contiguous AND conflict-free), else padded to one
     uint8_t can_move[OCK_MAX_AGENTS];
     uint8_t allergic[OCK_MAX_AGENTS];
     uint8_t blind[OCK_MAX_AGENTS];
@@ -49,8 +50,10 @@ struct OcParams {
     int32_t  ndeliver;
     uint8_t  deliver_sig[OCK_MAX_DELIVER];  // in table order
     uint8_t  deliver_idx[OCK_MAX_DELIVER];
-    int32_t  npairs;
-    uint8_t  pair_x[OCK_MAX_PAIRS], pair_y[OCK_MAX_PAIRS];
+    int32_t  npairs;                        // C(num_items, 2) item pairs of calculate_reward_shaping
+    int32_t  nfi;                           // number of Food items (items[1..]); items[0] is Plate
+    uint8_t  fi_bit[4];                     // their content bits, in item order
+    uint32_t r4_magic, rf_magic;            // floor(2^32 / d) + 1 for d = row_bytes / 4 and row_bytes
     // observation layout (float offsets inside one observer row)
     int32_t off_a1comm, off_a1loc, off_a2comm, off_a2loc, off_hold, off_completed,
             off_hidden, off_encx, off_ency, off_state, off_ts;

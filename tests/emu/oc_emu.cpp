@@ -40,11 +40,14 @@ static void for_each_warp(emu_env* h, float* obs, Body&& body) {
     float wts[32];
     for (int env0 = 0; env0 < p.E; env0 += 32) {
         const int nvalid = std::min(32, p.E - env0);
-        std::fill(rows.begin(), rows.end(), 0);
-        for (int lane = 0; lane < nvalid; ++lane) body(tb, env0 + lane, lane, rows.data() + (size_t)lane * p.row_stride, wts);
-        if (obs)
+        for (int lane = 0; lane < 32; ++lane) warp_zero_rows(rows.data(), 32 * p.row_stride, lane);
+        for (int lane = 0; lane < nvalid; ++lane) wts[lane] = body(tb, env0 + lane, rows.data() + (size_t)lane * p.row_stride);
+        if (obs) {
             for (int lane = 0; lane < 32; ++lane)
-                warp_expand_rows(p, rows.data(), wts, obs + (size_t)env0 * p.row_bytes, nvalid, lane);
+                warp_expand_rows(p, rows.data(), obs + (size_t)env0 * p.row_bytes, nvalid, lane);
+            for (int lane = 0; lane < nvalid; ++lane)
+                store_timesteps<A>(p, obs + (size_t)(env0 + lane) * p.row_bytes, wts[lane]);
+        }
     }
 }
 
@@ -63,10 +66,11 @@ int emu_create(const oc_config* c, emu_env** out) {
     h->state.assign((size_t)h->p.E * 4, uint4{0, 0, 0, 0});
     dispatch(h->p.A, h->p.NOBJ, [&](auto a, auto n) -> int {
         constexpr int AA = decltype(a)::value, NN = decltype(n)::value;
-        for_each_warp<AA, NN>(h, nullptr, [&](const Tables& tb, int env, int lane, uint8_t* row, float* wts) {
+        for_each_warp<AA, NN>(h, nullptr, [&](const Tables& tb, int env, uint8_t* row) -> float {
             Env<AA, NN> e;
-            reset_one_env<AA, NN>(e, h->p, tb, (uint32_t)env, true, nullptr, nullptr, false, row, wts, lane);
+            const float ts = reset_one_env<AA, NN>(e, h->p, tb, (uint32_t)env, true, nullptr, nullptr, false, row);
             store_env<AA, NN>(e, h->state.data(), h->p.E, env);
+            return ts;
         });
         return 0;
     });
@@ -83,11 +87,12 @@ int emu_obs_layout(const emu_env* h, int32_t* off, int32_t* sz) {
 int emu_reset(emu_env* h, const uint8_t* mask, const int32_t* placements, float* obs, void*) {
     return dispatch(h->p.A, h->p.NOBJ, [&](auto a, auto n) -> int {
         constexpr int AA = decltype(a)::value, NN = decltype(n)::value;
-        for_each_warp<AA, NN>(h, obs, [&](const Tables& tb, int env, int lane, uint8_t* row, float* wts) {
+        for_each_warp<AA, NN>(h, obs, [&](const Tables& tb, int env, uint8_t* row) -> float {
             Env<AA, NN> e;
             load_env<AA, NN>(e, h->state.data(), h->p.E, env);
-            reset_one_env<AA, NN>(e, h->p, tb, (uint32_t)env, false, mask, placements, obs != nullptr, row, wts, lane);
+            const float ts = reset_one_env<AA, NN>(e, h->p, tb, (uint32_t)env, false, mask, placements, obs != nullptr, row);
             store_env<AA, NN>(e, h->state.data(), h->p.E, env);
+            return ts;
         });
         return OC_OK;
     });
@@ -97,13 +102,14 @@ int emu_step(emu_env* h, const int32_t* actions, float* obs, float* rew32, doubl
              float* term_obs, uint32_t flags, void*) {
     return dispatch(h->p.A, h->p.NOBJ, [&](auto a, auto n) -> int {
         constexpr int AA = decltype(a)::value, NN = decltype(n)::value;
-        for_each_warp<AA, NN>(h, obs, [&](const Tables& tb, int env, int lane, uint8_t* row, float* wts) {
+        for_each_warp<AA, NN>(h, obs, [&](const Tables& tb, int env, uint8_t* row) -> float {
             Env<AA, NN> e;
             load_env<AA, NN>(e, h->state.data(), h->p.E, env);
             int nav[AA], comm[AA];
             for (int k = 0; k < AA; ++k) { nav[k] = actions[((size_t)env * AA + k) * 2] & 3; comm[k] = actions[((size_t)env * AA + k) * 2 + 1]; }
-            step_one_env<AA, NN>(e, h->p, tb, nav, comm[0], comm[1], (uint32_t)env, row, wts, lane, rew32, rew64, done, term_obs, flags);
+            const float ts = step_one_env<AA, NN>(e, h->p, tb, nav, comm[0], comm[1], (uint32_t)env, row, rew32, rew64, done, term_obs, flags);
             store_env<AA, NN>(e, h->state.data(), h->p.E, env);
+            return ts;
         });
         return OC_OK;
     });
@@ -115,12 +121,13 @@ int emu_rollout(emu_env* h, int32_t n_steps, float* obs, float* rew32, uint8_t* 
         constexpr int AA = decltype(a)::value, NN = decltype(n)::value;
         for (int s = 0; s < n_steps; ++s)
             for_each_warp<AA, NN>(h, obs ? obs + (size_t)s * step_floats : nullptr,
-                                  [&](const Tables& tb, int env, int lane, uint8_t* row, float* wts) {
+                                  [&](const Tables& tb, int env, uint8_t* row) -> float {
                 Env<AA, NN> e;
                 load_env<AA, NN>(e, h->state.data(), h->p.E, env);
-                rollout_one_env<AA, NN>(e, h->p, tb, (uint32_t)env, (uint32_t)s, h->rollout_step, row, wts, lane,
-                                        obs != nullptr, rew32, done, actions_out);
+                const float ts = rollout_one_env<AA, NN>(e, h->p, tb, (uint32_t)env, (uint32_t)s, h->rollout_step, row,
+                                                         obs != nullptr, rew32, done, actions_out);
                 store_env<AA, NN>(e, h->state.data(), h->p.E, env);
+                return ts;
             });
         return OC_OK;
     });

@@ -5,6 +5,7 @@
 #pragma once
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 #include <algorithm>
 #define __device__
 #define __forceinline__ inline
@@ -19,6 +20,13 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
+static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t s) {
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+    return r;
+}
+static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
