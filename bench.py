@@ -99,7 +99,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------- CPU arm
-def cpu_reference_arm(wname, seconds, kind="c"):
+def cpu_reference_arm(wname, seconds, kind="py"):
     from oracle import cpu_baseline
     return cpu_baseline.run_all_cores(WORKLOADS[wname], workload_namespace(WORKLOADS[wname]), seconds, kind)
 
