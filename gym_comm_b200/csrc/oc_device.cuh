@@ -1,7 +1,15 @@
-// Device-side Overcooked dynamics for sm_100a: one THREAD owns one env for the branchy integer
-// logic (a warp instruction then advances 32 envs), and the WARP cooperatively expands the 32
-// envs' compact observation rows into coalesced 16-byte stores.  Reference semantics and their
-// file:line anchors are listed next to each block; DESIGN.md explains the mapping.
+// Device-side Overcooked dynamics for sm_100a.
+//
+// Mapping: one THREAD owns one env for the branchy integer logic (a warp instruction advances 32
+// envs), and the WARP cooperatively streams the 32 envs' observation rows from shared memory to
+// global memory with coalesced 16-byte stores.  The kernels are bound by the integer ALU pipe
+// (ncu: sm__pipe_alu_cycles_active ~50 % = its issue limit), so the code below
+//   * tests object slots with one mask-compare on the packed word (dead slot = OCK_DEAD, which
+//     can never match a holder or a cell),
+//   * walks the objects ONCE per step to gather everything reward, shaping and observation need,
+//   * does the observation arithmetic in float on the FMA pipe (FADD.SAT / FFMA) and keeps
+//     float rows in shared memory when they fit, so the expansion is a plain 16-byte copy.
+// Reference semantics and their file:line anchors are listed next to each block.
 #pragma once
 #ifdef OCK_HOST_EMU
 #include "oc_emu_shim.h"   // tests/emu only: runs this header on the CPU to debug the logic without a GPU
@@ -20,24 +28,26 @@ enum : uint32_t { TILE_FLOOR = 0, TILE_COUNTER = 1, TILE_CUTBOARD = 2, TILE_DELI
 struct Tables {
     const double*   q;        // q[n] = n / MAX_PATH as the reference's Python float (f64)
     const uint32_t* tmlut;    // [128] object signature -> bitmask of subtasks whose goal template it equals
-    const uint8_t*  tile;     // [ncell]
-    const uint8_t*  mv;       // [ncell*4] inbounds(cell + NAV[a])                   world.py:317-320
-    const uint8_t*  xy;       // [ncell*2]
+    const float2*   xyf;      // [256] (x, y) of a cell as floats (index 0xFF = dead slot, harmless)
+    const uint16_t* mvt;      // [ncell*4] inbounds(cell + NAV[a]) | tile(target) << 8     world.py:317-320
+    const uint16_t* xy16;     // [ncell] x | y << 8
     const uint8_t*  dmin;     // [ncell] min over Delivery tiles of pd + manhattan   overcooked_environment.py:383-388
     const uint8_t*  counters; // [ncounters] Counter cells, reading order            overcooked_environment.py:164
     const uint8_t*  pd;       // [ncell*ncell] World.get_path_distance_between       world.py:114-131
+    const uint8_t*  pdm;      // [ncell*ncell] pd + manhattan distance               overcooked_environment.py:380
 };
 
 __device__ __forceinline__ Tables make_tables(const OcParams& p, const uint8_t* smem) {
     Tables t;
     t.q = reinterpret_cast<const double*>(smem + p.o_q);
     t.tmlut = reinterpret_cast<const uint32_t*>(smem + p.o_tmlut);
-    t.tile = smem + p.o_tile;
-    t.mv = smem + p.o_mv;
-    t.xy = smem + p.o_xy;
+    t.xyf = reinterpret_cast<const float2*>(smem + p.o_xyf);
+    t.mvt = reinterpret_cast<const uint16_t*>(smem + p.o_mvt);
+    t.xy16 = reinterpret_cast<const uint16_t*>(smem + p.o_xy16);
     t.dmin = smem + p.o_dmin;
     t.counters = smem + p.o_counters;
     t.pd = smem + p.o_pd;
+    t.pdm = smem + p.o_pdm;
     return t;
 }
 
@@ -94,7 +104,7 @@ __device__ __forceinline__ void store_env(const Env<A, NOBJ>& e, uint4* __restri
     uint32_t cells = 0;
 #pragma unroll
     for (int k = 0; k < A; ++k) cells |= e.acell[k] << (8 * k);
-    uint32_t o[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t o[6] = {OCK_DEAD, OCK_DEAD, OCK_DEAD, OCK_DEAD, OCK_DEAD, OCK_DEAD};
 #pragma unroll
     for (int s = 0; s < NOBJ; ++s) o[s] = e.obj[s];
     st[i] = make_uint4(e.w0, e.episodes, e.completed, e.countbits);
@@ -103,12 +113,14 @@ __device__ __forceinline__ void store_env(const Env<A, NOBJ>& e, uint4* __restri
     st[3 * E + i] = make_uint4(o[4], o[5], e.comm, e.w15);
 }
 
+// object word: contents[0:4] | chopped[4:7] | holder[8:11] (7 = not held) | cell[16:24] | stamp[24:32]
 __device__ __forceinline__ uint32_t obj_contents(uint32_t o) { return o & 0xFu; }
 __device__ __forceinline__ uint32_t obj_chopped(uint32_t o) { return (o >> 4) & 7u; }
 __device__ __forceinline__ uint32_t obj_holder(uint32_t o) { return (o >> 8) & 7u; }
 __device__ __forceinline__ uint32_t obj_cell(uint32_t o) { return (o >> 16) & 0xFFu; }
+__device__ __forceinline__ bool obj_alive(uint32_t o) { return (o & 0xFu) != 0; }
+__device__ __forceinline__ bool obj_held(uint32_t o) { return (o & 0x700u) != 0x700u; }
 __device__ __forceinline__ uint32_t obj_set_cell(uint32_t o, uint32_t c) { return (o & ~0x00FF0000u) | (c << 16); }
-__device__ __forceinline__ uint32_t obj_set_holder(uint32_t o, uint32_t h) { return (o & ~0x00000700u) | (h << 8); }
 
 // ---------------------------------------------------------------------------------------------
 // load_level phase 4 (overcooked_environment.py:157-173): each random object goes to a Counter
@@ -169,7 +181,46 @@ __device__ __forceinline__ void env_reset(Env<A, NOBJ>& e, const OcParams& p, co
 }
 
 // ---------------------------------------------------------------------------------------------
-// One env step.  nav[k] in [0,4); returns sparse reward, the returned (shaped) reward and done.
+// One pass over the object slots gathering what reward, shaping and observation need.
+// Domain rule: every Food exists at most once, so "the object containing food f" is unique;
+// only the Plate channel can have several candidates, and the LAST one in world.objects
+// iteration order wins the observation (last writer, overcooked_env.py:121-131): order = (key
+// creation rank of the object's name, insertion stamp) -- SURVEY A.8-2.
+struct Info {
+    uint32_t fword[3];      // object word holding Tomato / Lettuce / Onion (OCK_DEAD if none)
+    uint32_t pword;         // plate-channel winner (OCK_DEAD if none)
+    uint32_t holdmask;      // bit k: agent k carries something
+    uint32_t pres, deliv;   // subtasks whose goal template exists somewhere / on the first Delivery tile
+};
+
+template <int A, int NOBJ>
+__device__ __forceinline__ Info gather_info(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb) {
+    Info in;
+    in.fword[0] = in.fword[1] = in.fword[2] = OCK_DEAD;
+    in.pword = OCK_DEAD;
+    in.holdmask = 0; in.pres = 0; in.deliv = 0;
+    uint32_t pkey = 0;
+#pragma unroll
+    for (int s = 0; s < NOBJ; ++s) {
+        const uint32_t o = e.obj[s];
+        const uint32_t tm = tb.tmlut[o & 0x7Fu];             // dead slot: signature 0 -> no subtask
+        in.pres |= tm;
+        if ((o & 0x00FF0000u) == ((uint32_t)p.delivery0 << 16)) in.deliv |= tm;   // first Delivery tile only (:259,:402)
+#pragma unroll
+        for (int f = 0; f < 3; ++f)
+            if ((o >> f) & 1u) in.fword[f] = o;
+        if (o & 8u) {
+            const uint32_t key = ((uint32_t)((e.ranks >> (4 * (o & 0xFu))) & 15ull) << 8) | (o >> 24);
+            if (key > pkey) { pkey = key; in.pword = o; }
+        }
+        in.holdmask |= 1u << obj_holder(o);
+    }
+    in.holdmask &= 0xFu;                                     // bit 7 = "nobody"
+    return in;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One env step.  nav[k] in [0,4); returns the returned (shaped) reward and done.
 //   comm write + CAN_MOVE          gym_comm/envs/overcooked_env.py:227-262
 //   t += 1                          overcooked_environment.py:213
 //   check_collisions/is_collision   :543-613
@@ -178,7 +229,7 @@ __device__ __forceinline__ void env_reset(Env<A, NOBJ>& e, const OcParams& p, co
 //   reward/subtask_reward           :399-432
 //   calculate_reward_shaping x2     :272-397
 template <int A, int NOBJ>
-__device__ __forceinline__ void env_step(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
+__device__ __forceinline__ Info env_step(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
                                          const int (&nav)[A], int comm0, int comm1,
                                          double& reward, bool& done) {
     // ---- comm channel write (overcooked_env.py:227-246)
@@ -191,15 +242,17 @@ __device__ __forceinline__ void env_step(Env<A, NOBJ>& e, const OcParams& p, con
     const uint32_t t = e.w0 & 0xFFFFu;
 
     // ---- collisions, on the ORIGINAL actions for every pair (:543-613)
-    uint32_t tgt[A], nxt[A];
+    uint32_t tgt[A], ttile[A], nxt[A];
     bool act[A], ex[A];
 #pragma unroll
     for (int k = 0; k < A; ++k) {
         act[k] = p.can_move[k] != 0;                        // (0,0) iff CAN_MOVE false (:250-262)
-        tgt[k] = tb.mv[e.acell[k] * 4 + nav[k]];            // inbounds(loc + action)
+        const uint32_t m = tb.mvt[e.acell[k] * 4 + nav[k]]; // inbounds(loc + action) | tile << 8
+        tgt[k] = m & 0xFFu;
+        ttile[k] = m >> 8;
         // off-grid targets assert in the reference (world.py:314); here the clamped target is the
         // agent's own (floor) cell, i.e. the agent stays.
-        nxt[k] = (act[k] && tb.tile[tgt[k]] == TILE_FLOOR) ? tgt[k] : e.acell[k];
+        nxt[k] = (act[k] && ttile[k] == TILE_FLOOR) ? tgt[k] : e.acell[k];
         ex[k] = true;
     }
 #pragma unroll
@@ -221,14 +274,11 @@ __device__ __forceinline__ void env_step(Env<A, NOBJ>& e, const OcParams& p, con
 #pragma unroll
     for (int k = 0; k < A; ++k) {
         if (!(act[k] && ex[k])) continue;
-        const uint32_t tg = tgt[k];
-        const uint32_t tt = tb.tile[tg];
-        uint32_t hv = 0, hm = 0;           // held object word / slot mask
+        const uint32_t tg = tgt[k], tt = ttile[k];
+        uint32_t hv = OCK_DEAD, hm = 0;    // held object word / slot mask
 #pragma unroll
-        for (int s = 0; s < NOBJ; ++s) {
-            const uint32_t o = e.obj[s];
-            if (obj_contents(o) != 0 && obj_holder(o) == (uint32_t)k) { hv = o; hm = 1u << s; }
-        }
+        for (int s = 0; s < NOBJ; ++s)
+            if ((e.obj[s] & 0x700u) == ((uint32_t)k << 8)) { hv = e.obj[s]; hm = 1u << s; }
         if (tt == TILE_FLOOR) {            // move; held object moves along (agent.py:311-314)
             e.acell[k] = tg;
 #pragma unroll
@@ -236,17 +286,16 @@ __device__ __forceinline__ void env_step(Env<A, NOBJ>& e, const OcParams& p, con
                 if ((hm >> s) & 1u) e.obj[s] = obj_set_cell(e.obj[s], tg);
             continue;
         }
-        uint32_t ov = 0, om = 0;           // un-held object on the target tile (world.py:217-222)
+        uint32_t ov = OCK_DEAD, om = 0;    // un-held object on the target tile (world.py:217-222)
+        const uint32_t want = (tg << 16) | 0x700u;
 #pragma unroll
-        for (int s = 0; s < NOBJ; ++s) {
-            const uint32_t o = e.obj[s];
-            if (obj_contents(o) != 0 && obj_holder(o) == OCK_HOLDER_NONE && obj_cell(o) == tg) { ov = o; om = 1u << s; }
-        }
+        for (int s = 0; s < NOBJ; ++s)
+            if ((e.obj[s] & 0x00FF0700u) == want) { ov = e.obj[s]; om = 1u << s; }
         uint32_t newh = hv, newo = ov;
         if (hm != 0) {
             const uint32_t hc = obj_contents(hv), hch = obj_chopped(hv);
             const bool h_done = (hc & 7u) == hch;                    // every Food in its last state
-            const uint32_t put = obj_set_holder(obj_set_cell(hv, tg), OCK_HOLDER_NONE);
+            const uint32_t put = obj_set_cell(hv, tg) | 0x700u;      // on the tile, nobody holds it
             if (tt == TILE_DELIVERY) {                               // :25-30, is_deliverable core.py:232-237
                 if (__popc(hc) > 1 && h_done) newh = put;
             } else if (om != 0) {                                    // merge :33-42, mergeable core.py:240-257
@@ -259,7 +308,7 @@ __device__ __forceinline__ void env_step(Env<A, NOBJ>& e, const OcParams& p, con
                         nkeys += 1;
                         e.ranks |= (uint64_t)nkeys << (4 * nm);
                     }
-                    newo = 0;                                        // absorbed object leaves the world
+                    newo = OCK_DEAD;                                 // absorbed object leaves the world
                 }
             } else {                                                 // :48-59
                 if (tt == TILE_CUTBOARD && (hc == 1u || hc == 2u || hc == 4u) && hch == 0u)
@@ -268,7 +317,7 @@ __device__ __forceinline__ void env_step(Env<A, NOBJ>& e, const OcParams& p, con
                     newh = put;                                      // put down
             }
         } else if (om != 0 && tt != TILE_DELIVERY && !p.allergic[k]) {   // pick up :64-71, agent.py:296-305
-            newo = obj_set_holder(obj_set_cell(ov, e.acell[k]), (uint32_t)k);
+            newo = (ov & ~0x00FF0700u) | (e.acell[k] << 16) | ((uint32_t)k << 8);
         }
 #pragma unroll
         for (int s = 0; s < NOBJ; ++s) {
@@ -279,199 +328,199 @@ __device__ __forceinline__ void env_step(Env<A, NOBJ>& e, const OcParams& p, con
     e.w0 = t | (next_stamp << 16) | (nkeys << 24);
 
     // ---- done + sparse reward through the signature -> subtask-mask table
-    uint32_t pres = 0, deliv = 0;
-    int fresh_cell[3] = {-1, -1, -1};
-#pragma unroll
-    for (int s = 0; s < NOBJ; ++s) {
-        const uint32_t o = e.obj[s];
-        if (obj_contents(o) != 0) {
-            const uint32_t sig = o & 0x7Fu;
-            const uint32_t tm = tb.tmlut[sig];
-            pres |= tm;
-            if (obj_cell(o) == p.delivery0) deliv |= tm;     // only the first Delivery tile (:259,:402)
-            if (sig == 1u) fresh_cell[0] = (int)obj_cell(o);
-            if (sig == 2u) fresh_cell[1] = (int)obj_cell(o);
-            if (sig == 4u) fresh_cell[2] = (int)obj_cell(o);
-        }
-    }
-    const uint32_t dl = deliv & p.deliver_mask;
+    const Info in = gather_info<A, NOBJ>(e, p, tb);
+    const uint32_t dl = in.deliv & p.deliver_mask;
     done = (p.T != 0 && t >= (uint32_t)p.T) || (dl == p.deliver_mask);       // :243-270
-    const uint32_t nw = pres & ~e.countbits & p.nondeliver_mask;             // count rose (:409-415)
+    const uint32_t nw = in.pres & ~e.countbits & p.nondeliver_mask;          // count rose (:409-415)
     const int sparse = 3 * __popc(dl) + __popc(nw);
-    e.countbits = pres & p.nondeliver_mask;
+    e.countbits = in.pres & p.nondeliver_mask;
     e.completed |= dl | nw;                                                  // :425-426
 
     // ---- reward shaping (:272-397); f64 additions in reference order
-    // (1) Chop subtasks still open
-    int lenU = 0;
-    int nf[3];
+    // (1) Chop subtasks still open: U = [pd(agent, FreshX)], needs min(U) and len(U)
+    int lenU = 0, nf[3];
 #pragma unroll
     for (int f = 0; f < 3; ++f) {
-        nf[f] = (fresh_cell[f] >= 0) ? __popc(~e.completed & p.chop_mask[f]) : 0;
+        const bool fresh = (in.fword[f] & 0x7Fu) == (1u << f);              // X alone and un-chopped
+        nf[f] = fresh ? __popc(~e.completed & p.chop_mask[f]) : 0;
         lenU += nf[f];
     }
     // (2) item-pair distances (:319-363): agent independent.  Items = Plate + the Foods of
-    // recipes[0]; pairs in combinations() order (P,f0) (P,f1) (P,f2) (f0,f1) (f0,f2) (f1,f2).
-    // pd(src, .) == MAX_PATH unless src is a floor cell, i.e. unless the FIRST item's object is
-    // being carried (world.py:126-127), and each Food lives in exactly one object (domain rule), so
-    // only a handful of table look-ups are ever needed.
+    // recipes[0]; only min(P) and len(P) are used.  pd(src, .) == MAX_PATH unless src is a floor
+    // cell, i.e. unless the FIRST item's object is being carried (world.py:126-127).
     int lenP = p.npairs, minP = p.M;
-    {
-        bool any_held = false;
+    if (in.holdmask != 0) {
+        lenP = 0;
+        int mP[3] = {p.M, p.M, p.M};
 #pragma unroll
-        for (int s = 0; s < NOBJ; ++s) any_held |= (obj_contents(e.obj[s]) != 0 && obj_holder(e.obj[s]) != OCK_HOLDER_NONE);
-        if (any_held) {
-            int fc[3] = {-1, -1, -1};
-            bool fh[3] = {false, false, false};
+        for (int s = 0; s < NOBJ; ++s) {
+            const uint32_t o = e.obj[s];
+            if ((o & 8u) && obj_held(o)) {                                   // a carried plate-bearing object
+                const uint8_t* row = tb.pd + obj_cell(o) * p.ncell;
 #pragma unroll
-            for (int s = 0; s < NOBJ; ++s) {
-                const uint32_t o = e.obj[s];
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-                    if (i < p.nfi && (o & p.fi_bit[i])) { fc[i] = (int)obj_cell(o); fh[i] = obj_holder(o) != OCK_HOLDER_NONE; }
+                for (int f = 0; f < 3; ++f)
+                    if (((p.item_foods >> f) & 1u) && obj_alive(in.fword[f]))
+                        mP[f] = min(mP[f], (int)row[obj_cell(in.fword[f])]);
             }
-            int mP[3] = {p.M, p.M, p.M};
+        }
 #pragma unroll
-            for (int s = 0; s < NOBJ; ++s) {
-                const uint32_t o = e.obj[s];
-                if ((o & 8u) && obj_holder(o) != OCK_HOLDER_NONE) {          // a carried plate-bearing object
-                    const uint8_t* row = tb.pd + obj_cell(o) * p.ncell;
+        for (int f = 0; f < 3; ++f)
+            if (((p.item_foods >> f) & 1u) && mP[f] != 0) { lenP += 1; minP = min(minP, mP[f]); }
+        // Food-Food pairs, first item alphabetically first: (Lettuce, Onion) (Lettuce, Tomato) (Onion, Tomato)
+        const int px[3] = {1, 1, 2}, py[3] = {2, 0, 0};
 #pragma unroll
-                    for (int i = 0; i < 3; ++i)
-                        if (i < p.nfi && fc[i] >= 0) mP[i] = min(mP[i], (int)row[fc[i]]);
-                }
-            }
-            lenP = 0;
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-                if (i < p.nfi && mP[i] != 0) { lenP += 1; minP = min(minP, mP[i]); }
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-#pragma unroll
-                for (int j = i + 1; j < 3; ++j) {
-                    if (j < p.nfi) {
-                        int m = p.M;
-                        if (fh[i] && fc[j] >= 0) m = tb.pd[fc[i] * p.ncell + fc[j]];
-                        if (m != 0) { lenP += 1; minP = min(minP, m); }
-                    }
-                }
+        for (int q = 0; q < 3; ++q) {
+            if (((p.item_foods >> px[q]) & 1u) && ((p.item_foods >> py[q]) & 1u)) {
+                const uint32_t ox = in.fword[px[q]], oy = in.fword[py[q]];
+                int m = p.M;
+                if (obj_alive(ox) && obj_held(ox) && obj_alive(oy)) m = tb.pd[obj_cell(ox) * p.ncell + obj_cell(oy)];
+                if (m != 0) { lenP += 1; minP = min(minP, m); }
             }
         }
     }
-    // (3) Deliver subtasks: dish cell per subtask (table order)
-    int dcell[OCK_MAX_DELIVER];
-#pragma unroll
-    for (int j = 0; j < OCK_MAX_DELIVER; ++j) {
-        dcell[j] = -2;                                        // -2: subtask absent or completed
-        if (j < p.ndeliver && !((e.completed >> p.deliver_idx[j]) & 1u)) {
-            dcell[j] = -1;                                    // -1: no such dish in the world
-#pragma unroll
-            for (int s = 0; s < NOBJ; ++s)
-                if ((e.obj[s] & 0x7Fu) == p.deliver_sig[j]) dcell[j] = (int)obj_cell(e.obj[s]);
-        }
-    }
-    double shaped = (double)sparse;
+    double tp[2];
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
-        const uint32_t ac = e.acell[a];
-        const uint8_t* row = tb.pd + ac * p.ncell;
-        double tp = 0.0;
+        tp[a] = 0.0;
         if (lenU > 0) {
+            const uint8_t* row = tb.pd + e.acell[a] * p.ncell;
             int minU = 1 << 20;
 #pragma unroll
             for (int f = 0; f < 3; ++f)
-                if (nf[f] > 0) minU = min(minU, (int)row[fresh_cell[f]]);
-            tp = tb.q[minU + p.M + (lenU - 1) * 2 * p.M];                       // :303-304
-            if (lenP > 0) tp = __dadd_rn(tp, (double)lenP);                       // :363
+                if (nf[f] > 0) minU = min(minU, (int)row[obj_cell(in.fword[f])]);
+            tp[a] = tb.q[minU + p.M + (lenU - 1) * 2 * p.M];                         // :303-304
+            if (lenP > 0) tp[a] = __dadd_rn(tp[a], (double)lenP);                    // :363
         } else if (lenP > 0) {
-            tp = tb.q[minP + (lenP - 1) * p.M];                                   // :361
+            tp[a] = tb.q[minP + (lenP - 1) * p.M];                                   // :361
         }
-        const int ax = tb.xy[ac * 2], ay = tb.xy[ac * 2 + 1];
-#pragma unroll
-        for (int j = 0; j < OCK_MAX_DELIVER; ++j) {
-            if (dcell[j] == -2) continue;
-            if (dcell[j] == -1) { tp = __dadd_rn(tp, 2.0); continue; }            // :377-378
-            const int dc = dcell[j];
-            const int d = row[dc] + abs(ax - (int)tb.xy[dc * 2]) + abs(ay - (int)tb.xy[dc * 2 + 1]);
-            if (d == 0) tp = __dadd_rn(tp, tb.q[tb.dmin[ac]]);                    // :381-389
-            else tp = __dadd_rn(tp, __dadd_rn(tb.q[d], 1.0));                     // :393
-        }
-        shaped = __dsub_rn(shaped, tp);                                           // overcooked_env.py:282
     }
-    reward = shaped;
+    // (3) Deliver subtasks still open, table order (:370-395)
+    for (int j = 0; j < p.ndeliver; ++j) {
+        if ((e.completed >> p.deliver_idx[j]) & 1u) continue;
+        const uint32_t sig = p.deliver_sig[j];
+        uint32_t dw = OCK_DEAD;
+#pragma unroll
+        for (int s = 0; s < NOBJ; ++s)
+            if ((e.obj[s] & 0x7Fu) == sig) dw = e.obj[s];
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            if (!obj_alive(dw)) { tp[a] = __dadd_rn(tp[a], 2.0); continue; }             // :377-378
+            const int d = tb.pdm[e.acell[a] * p.ncell + obj_cell(dw)];                    // pd + manhattan (:380)
+            if (d == 0) tp[a] = __dadd_rn(tp[a], tb.q[tb.dmin[e.acell[a]]]);              // :381-389
+            else tp[a] = __dadd_rn(tp[a], __dadd_rn(tb.q[d], 1.0));                       // :393
+        }
+    }
+    reward = __dsub_rn(__dsub_rn((double)sparse, tp[0]), tp[1]);                     // overcooked_env.py:282
+    return in;
 }
 
-// ---------------------------------------------------------------------------------------------
-// get_observation2 (gym_comm/envs/overcooked_env.py:105-159) for every observer of one env,
-// written as ONE BYTE PER FEATURE (value + 128) into this env's shared-memory row.  Rows are
-// pre-filled with 0x80 (= 0.0).  The timestep feature is left at 0.0 here; its float is stored
-// by the owning thread after the warp's cooperative expansion (store_timesteps).
+// =============================================================================================
+// Observation rows.  get_observation2 (gym_comm/envs/overcooked_env.py:105-159) for every
+// observer of one env, written into this env's shared-memory row by its owning thread, then
+// streamed to global memory by the whole warp.  Two row formats:
+//   ROWF = true : float32 rows (when they fit in shared memory) -> the expansion is a 16-byte copy
+//   ROWF = false: one biased byte per feature (value + 128) -> PRMT + FADD per float on the way out
+// =============================================================================================
 #define OCK_BIAS 128u
 
+// per observer: is_hidden / object_encodings_x / _y / state_encodings of channel c, as floats
+__device__ __forceinline__ void channel_features(const Tables& tb, uint32_t word, float2 me, float fow, int c,
+                                                 float& hid, float& ex, float& ey, float& st) {
+    const float2 o = tb.xyf[obj_cell(word)];
+    const float dx = o.x - me.x, dy = o.y - me.y;
+    st = (c < 3) ? (float)((word >> (4 + c)) & 1u) : 0.0f;         // Food state_index; Plate has none (:127-128)
+    hid = __saturatef(fabsf(dx) + fabsf(dy) - fow);                // 0 if |dx|+|dy| <= radius else 1 (:133)
+    ex = __fmaf_rn(dx, hid, 0.0f);                                 // near objects report (0,0) (:135); +0.0, never -0.0
+    ey = __fmaf_rn(dy, hid, 0.0f);
+}
+
 template <int A, int NOBJ>
-__device__ __forceinline__ void env_build_rows(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
-                                               uint8_t* __restrict__ row /* 0x80-filled, row_stride bytes */) {
-    // per channel the object that is LAST in world.objects iteration order among those containing
-    // it (last writer wins, :121-131).  Each Food lives in exactly one object; only the Plate
-    // channel can have several candidates, ordered by (key creation rank, insertion stamp).
-    int wx[4] = {0, 0, 0, 0}, wy[4] = {0, 0, 0, 0};
-    uint32_t wst[4] = {0, 0, 0, 0};
-    bool has[4] = {false, false, false, false};
-    uint32_t pkey = 0;
-    uint32_t holdmask = 0;                 // bit k: agent k holds something
-#pragma unroll
-    for (int s = 0; s < NOBJ; ++s) {
-        const uint32_t o = e.obj[s];
-        const uint32_t oc = obj_contents(o);
-        if (oc == 0) continue;
-        const uint32_t cell = obj_cell(o);
-        const int x = tb.xy[cell * 2], y = tb.xy[cell * 2 + 1];
-        holdmask |= (1u << obj_holder(o));
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-            if ((oc >> c) & 1u) { has[c] = true; wx[c] = x; wy[c] = y; wst[c] = (o >> (4 + c)) & 1u; }
-        if (oc & 8u) {
-            const uint32_t key = ((uint32_t)((e.ranks >> (4 * oc)) & 15ull) << 8) | (o >> 24);
-            if (key > pkey) { pkey = key; has[3] = true; wx[3] = x; wy[3] = y; }
-        }
-    }
-    const int x0 = tb.xy[e.acell[0] * 2], y0 = tb.xy[e.acell[0] * 2 + 1];
-    const int x1 = tb.xy[e.acell[1] * 2], y1 = tb.xy[e.acell[1] * 2 + 1];
+__device__ __forceinline__ void build_rows_f32(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
+                                               const Info& in, float ts, float* __restrict__ row /* zero-filled */) {
+    const float2 a0 = tb.xyf[e.acell[0]], a1 = tb.xyf[e.acell[1]];
     const uint32_t c0 = e.comm & 0xFFFFu, c1 = e.comm >> 16;
+    const float fow = (float)p.fow;
+#pragma unroll
+    for (int k = 0; k < A; ++k) {
+        float* r = row + k * p.F;
+        const bool blind = p.blind[k] != 0;                                    // :115-118
+        if (c0 != OCK_COMM_NONE) r[p.off_a1comm + c0] = 1.0f;
+        if (c1 != OCK_COMM_NONE) r[p.off_a2comm + c1] = 1.0f;
+        if (!blind) {                                                          // :139-143
+            r[p.off_a1loc] = a0.x; r[p.off_a1loc + 1] = a0.y;
+            r[p.off_a2loc] = a1.x; r[p.off_a2loc + 1] = a1.y;
+        }
+        if (!p.ego_blind && ((in.holdmask >> k) & 1u)) r[p.off_hold] = 1.0f;   // :154
+        for (int i = 0; i < p.S; ++i)
+            if ((e.completed >> i) & 1u) r[p.off_completed + i] = 1.0f;
+        if (blind) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) r[p.off_hidden + c] = 1.0f;            // :109
+        } else {
+            const float2 me = (k == 0) ? a0 : ((k == 1) ? a1 : tb.xyf[e.acell[k]]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t w = (c < 3) ? in.fword[c] : in.pword;
+                if (obj_alive(w)) {                                            // absent channel: all zeros already
+                    float hid, ex, ey, st;
+                    channel_features(tb, w, me, fow, c, hid, ex, ey, st);
+                    r[p.off_hidden + c] = hid;
+                    r[p.off_encx + c] = ex;
+                    r[p.off_ency + c] = ey;
+                    if (c < 3) r[p.off_state + c] = st;
+                }
+            }
+        }
+        r[p.off_ts] = ts;                                                      // :146
+    }
+}
+
+template <int A, int NOBJ>
+__device__ __forceinline__ void build_rows_u8(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
+                                              const Info& in, uint8_t* __restrict__ row /* 0x80-filled */) {
+    const uint32_t xy0 = tb.xy16[e.acell[0]], xy1 = tb.xy16[e.acell[1]];
+    const uint32_t c0 = e.comm & 0xFFFFu, c1 = e.comm >> 16;
+    const float fow = (float)p.fow;
 #pragma unroll
     for (int k = 0; k < A; ++k) {
         uint8_t* r = row + k * p.F;
         const bool blind = p.blind[k] != 0;
         if (c0 != OCK_COMM_NONE) r[p.off_a1comm + c0] = OCK_BIAS + 1;
         if (c1 != OCK_COMM_NONE) r[p.off_a2comm + c1] = OCK_BIAS + 1;
-        r[p.off_a1loc] = OCK_BIAS + (blind ? 0 : x0);  r[p.off_a1loc + 1] = OCK_BIAS + (blind ? 0 : y0);   // :139-143
-        r[p.off_a2loc] = OCK_BIAS + (blind ? 0 : x1);  r[p.off_a2loc + 1] = OCK_BIAS + (blind ? 0 : y1);
-        r[p.off_hold] = OCK_BIAS + ((!p.ego_blind && ((holdmask >> k) & 1u)) ? 1 : 0);                      // :154
-        for (int i = 0; i < p.S; ++i) r[p.off_completed + i] = OCK_BIAS + ((e.completed >> i) & 1u);
-        int ax = x0, ay = y0;
-        if (k == 1) { ax = x1; ay = y1; }
-        if (k >= 2) { ax = tb.xy[e.acell[k] * 2]; ay = tb.xy[e.acell[k] * 2 + 1]; }
+        if (!blind) {
+            r[p.off_a1loc] = OCK_BIAS + (xy0 & 0xFF);  r[p.off_a1loc + 1] = OCK_BIAS + (xy0 >> 8);
+            r[p.off_a2loc] = OCK_BIAS + (xy1 & 0xFF);  r[p.off_a2loc + 1] = OCK_BIAS + (xy1 >> 8);
+        }
+        if (!p.ego_blind && ((in.holdmask >> k) & 1u)) r[p.off_hold] = OCK_BIAS + 1;
+        for (int i = 0; i < p.S; ++i)
+            if ((e.completed >> i) & 1u) r[p.off_completed + i] = OCK_BIAS + 1;
+        if (blind) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            int dx = 0, dy = 0; uint32_t st = 0, hid = 1;
-            if (!blind) {
-                if (has[c]) { dx = wx[c] - ax; dy = wy[c] - ay; st = wst[c]; }
-                const bool near = (abs(dx) + abs(dy)) <= p.fow;                     // :133-135
-                hid = near ? 0u : 1u;
-                if (near) { dx = 0; dy = 0; }
+            for (int c = 0; c < 4; ++c) r[p.off_hidden + c] = OCK_BIAS + 1;
+        } else {
+            const float2 me = tb.xyf[e.acell[k]];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t w = (c < 3) ? in.fword[c] : in.pword;
+                if (obj_alive(w)) {
+                    float hid, ex, ey, st;
+                    channel_features(tb, w, me, fow, c, hid, ex, ey, st);
+                    r[p.off_hidden + c] = (uint8_t)(OCK_BIAS + (int)hid);
+                    r[p.off_encx + c] = (uint8_t)(OCK_BIAS + (int)ex);
+                    r[p.off_ency + c] = (uint8_t)(OCK_BIAS + (int)ey);
+                    if (c < 3) r[p.off_state + c] = (uint8_t)(OCK_BIAS + (int)st);
+                }
             }
-            r[p.off_hidden + c] = (uint8_t)(OCK_BIAS + hid);
-            r[p.off_encx + c] = (uint8_t)(OCK_BIAS + dx);
-            r[p.off_ency + c] = (uint8_t)(OCK_BIAS + dy);
-            r[p.off_state + c] = (uint8_t)(OCK_BIAS + st);
         }
     }
 }
 
-// warp-cooperative fill of the warp's 32 byte-rows with 0x80 (= 0.0)
-__device__ __forceinline__ void warp_zero_rows(uint8_t* wrows, int bytes, int lane) {
+// warp-cooperative fill of the warp's 32 rows with the "all features 0.0" pattern
+template <bool ROWF>
+__device__ __forceinline__ void warp_clear_rows(uint8_t* wrows, int bytes, int lane) {
+    const uint32_t z = ROWF ? 0u : 0x80808080u;
     uint4* d = reinterpret_cast<uint4*>(wrows);
-    for (int i = lane; i < (bytes >> 4); i += 32) d[i] = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+    for (int i = lane; i < (bytes >> 4); i += 32) d[i] = make_uint4(z, z, z, z);
 }
 
 // byte k of w (value + 128) -> float, on the integer/FP32 pipes only: PRMT builds 0x4B0000bb
@@ -480,13 +529,20 @@ __device__ __forceinline__ float biased_byte_to_float(uint32_t w, int k) {
     return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + (uint32_t)k)) - 8388736.0f;
 }
 
-// warp-cooperative expansion: 32 byte-rows in shared memory -> float32 rows in global memory,
-// consecutive lanes writing consecutive 16-byte (or 4-byte) pieces of one contiguous region.
+// warp-cooperative expansion: the warp's 32 rows in shared memory -> float32 rows in global
+// memory, consecutive lanes writing consecutive 16-byte (or 4-byte) pieces of one contiguous region.
+template <bool ROWF>
 __device__ __forceinline__ void warp_expand_rows(const OcParams& p, const uint8_t* __restrict__ wrows,
                                                  float* __restrict__ out /* warp's first env row */,
                                                  int nvalid, int lane) {
-    if ((p.row_bytes & 3) == 0) {
-        const int r4 = p.row_bytes >> 2;             // float4 per env row
+    if (ROWF) {                                     // float rows, contiguous: plain copy
+        const int total = nvalid * (p.row_bytes >> 2);
+        const float4* i4 = reinterpret_cast<const float4*>(wrows);
+        float4* o4 = reinterpret_cast<float4*>(out);
+#pragma unroll 4
+        for (int idx = lane; idx < total; idx += 32) __stcs(o4 + idx, i4[idx]);   // streaming: written once, read later by the learner
+    } else if ((p.row_bytes & 3) == 0) {
+        const int r4 = p.row_bytes >> 2;            // float4 per env row
         const int total = nvalid * r4;
         float4* o4 = reinterpret_cast<float4*>(out);
         const bool contiguous = p.row_stride == p.row_bytes;
@@ -503,7 +559,7 @@ __device__ __forceinline__ void warp_expand_rows(const OcParams& p, const uint8_
             v.y = biased_byte_to_float(w, 1);
             v.z = biased_byte_to_float(w, 2);
             v.w = biased_byte_to_float(w, 3);
-            __stcs(o4 + idx, v);                                    // streaming: written once, read later by the learner
+            __stcs(o4 + idx, v);
         }
     } else {
         const int rf = p.row_bytes;
@@ -516,8 +572,8 @@ __device__ __forceinline__ void warp_expand_rows(const OcParams& p, const uint8_
     }
 }
 
-// after the expansion (and a __syncwarp): each thread stores the timestep feature of its own env
-// rows, timestep = float32(t / max_num_timesteps)  (overcooked_env.py:146)
+// byte rows only: after the expansion (and a __syncwarp) each thread stores the timestep feature
+// of its own env rows, timestep = float32(t / max_num_timesteps)  (overcooked_env.py:146)
 template <int A>
 __device__ __forceinline__ void store_timesteps(const OcParams& p, float* __restrict__ env_row, float ts) {
 #pragma unroll
@@ -525,27 +581,36 @@ __device__ __forceinline__ void store_timesteps(const OcParams& p, float* __rest
 }
 
 // a single thread expands its own row (rare path: terminal observations)
+template <bool ROWF>
 __device__ __forceinline__ void thread_expand_row(const OcParams& p, const uint8_t* __restrict__ row, float ts,
                                                   float* __restrict__ out) {
-    for (int j = 0; j < p.row_bytes; ++j) out[j] = (float)((int)row[j] - 128);
-    for (int k = 0; k < p.A; ++k) out[k * p.F + p.off_ts] = ts;
+    if (ROWF) {
+        for (int j = 0; j < p.row_bytes; ++j) out[j] = reinterpret_cast<const float*>(row)[j];
+    } else {
+        for (int j = 0; j < p.row_bytes; ++j) out[j] = (float)((int)row[j] - 128);
+        for (int k = 0; k < p.A; ++k) out[k * p.F + p.off_ts] = ts;
+    }
 }
 
-template <int A, int NOBJ>
+// observation of the env as it stands: fills this thread's row, returns the timestep float
+template <int A, int NOBJ, bool ROWF>
 __device__ __forceinline__ float finish_obs(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
-                                            uint8_t* myrow) {
-    env_build_rows<A, NOBJ>(e, p, tb, myrow);
-    return __ldg(p.ts_table + (e.w0 & 0xFFFFu));
+                                            const Info& in, uint8_t* myrow) {
+    const float ts = __ldg(p.ts_table + (e.w0 & 0xFFFFu));
+    if (ROWF) build_rows_f32<A, NOBJ>(e, p, tb, in, ts, reinterpret_cast<float*>(myrow));
+    else build_rows_u8<A, NOBJ>(e, p, tb, in, myrow);
+    return ts;
 }
 
 // terminal bookkeeping + in-place reset of one finished env (SB3 VecEnv auto-reset contract)
-template <int A, int NOBJ>
-__device__ __forceinline__ void finish_episode(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
+template <int A, int NOBJ, bool ROWF>
+__device__ __forceinline__ void finish_episode(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb, const Info& in,
                                                uint8_t* myrow, float* __restrict__ term_row, uint32_t env_id) {
     if (term_row != nullptr) {                       // infos["terminal_observation"]
-        env_build_rows<A, NOBJ>(e, p, tb, myrow);
-        thread_expand_row(p, myrow, __ldg(p.ts_table + (e.w0 & 0xFFFFu)), term_row);
-        for (int j = 0; j < (p.row_stride >> 2); ++j) reinterpret_cast<uint32_t*>(myrow)[j] = 0x80808080u;
+        const float ts = finish_obs<A, NOBJ, ROWF>(e, p, tb, in, myrow);
+        thread_expand_row<ROWF>(p, myrow, ts, term_row);
+        const uint32_t z = ROWF ? 0u : 0x80808080u;
+        for (int j = 0; j < (p.row_stride >> 2); ++j) reinterpret_cast<uint32_t*>(myrow)[j] = z;
     }
     e.w5 = (e.w5 & ~0xFFu) | (uint32_t)__popc(e.completed);    // episode_recorder.py:29
     e.episodes += 1;
@@ -553,18 +618,18 @@ __device__ __forceinline__ void finish_episode(Env<A, NOBJ>& e, const OcParams& 
 }
 
 // everything one thread does for its env in oc_step between loading and storing the state
-template <int A, int NOBJ>
+template <int A, int NOBJ, bool ROWF>
 __device__ __forceinline__ float step_one_env(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
                                               const int (&nav)[A], int comm0, int comm1, uint32_t env,
                                               uint8_t* myrow,
-                                             float* __restrict__ rew32, double* __restrict__ rew64,
-                                             uint8_t* __restrict__ done_out, float* __restrict__ term_obs,
-                                             uint32_t flags) {
+                                              float* __restrict__ rew32, double* __restrict__ rew64,
+                                              uint8_t* __restrict__ done_out, float* __restrict__ term_obs,
+                                              uint32_t flags) {
     double reward; bool done;
     // out-of-range message index -> zero vector (the reference raises IndexError)
     const int c0 = ((uint32_t)comm0 < (uint32_t)p.C) ? comm0 : (int)OCK_COMM_NONE;
     const int c1 = ((uint32_t)comm1 < (uint32_t)p.C) ? comm1 : (int)OCK_COMM_NONE;
-    env_step<A, NOBJ>(e, p, tb, nav, c0, c1, reward, done);
+    Info in = env_step<A, NOBJ>(e, p, tb, nav, c0, c1, reward, done);
     if (rew64 != nullptr) rew64[env] = reward;
     if (rew32 != nullptr) {
         const float r = (float)reward;
@@ -572,20 +637,22 @@ __device__ __forceinline__ float step_one_env(Env<A, NOBJ>& e, const OcParams& p
         for (int k = 0; k < A; ++k) rew32[(size_t)env * A + k] = r;
     }
     done_out[env] = done ? 1 : 0;
-    if (done && (flags & 1u /*OC_FLAG_AUTO_RESET*/))
-        finish_episode<A, NOBJ>(e, p, tb, myrow, term_obs ? term_obs + (size_t)env * p.row_bytes : nullptr, env);
-    return finish_obs<A, NOBJ>(e, p, tb, myrow);
+    if (done && (flags & 1u /*OC_FLAG_AUTO_RESET*/)) {
+        finish_episode<A, NOBJ, ROWF>(e, p, tb, in, myrow, term_obs ? term_obs + (size_t)env * p.row_bytes : nullptr, env);
+        in = gather_info<A, NOBJ>(e, p, tb);
+    }
+    return finish_obs<A, NOBJ, ROWF>(e, p, tb, in, myrow);
 }
 
 // one env, one step of the fused synthetic rollout: Philox actions (nav ~ U{0..3}, comm ~ U{0..C-1}),
 // auto-reset always on.  Draw layout (same in oracle/oc_oracle.c): counter (env, global step,
 // 'ACTS', 0); nav_k = bits [2k, 2k+2) of word 0; comm_0/1 = mulhi(word 1/2, C).
-template <int A, int NOBJ>
+template <int A, int NOBJ, bool ROWF>
 __device__ __forceinline__ float rollout_one_env(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
                                                  uint32_t env, uint32_t s, uint32_t step0,
                                                  uint8_t* myrow, bool want_obs,
-                                                float* __restrict__ rew32, uint8_t* __restrict__ done_out,
-                                                int32_t* __restrict__ actions_out) {
+                                                 float* __restrict__ rew32, uint8_t* __restrict__ done_out,
+                                                 int32_t* __restrict__ actions_out) {
     uint32_t r[4];
     philox4x32_10(env, step0 + s, 0x41435453u /*'ACTS'*/, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), r);
     int nav[A];
@@ -598,19 +665,22 @@ __device__ __forceinline__ float rollout_one_env(Env<A, NOBJ>& e, const OcParams
         for (int k = 0; k < A; ++k) { ao[2 * k] = nav[k]; ao[2 * k + 1] = (k == 0) ? c0 : (k == 1 ? c1 : 0); }
     }
     double reward; bool done;
-    env_step<A, NOBJ>(e, p, tb, nav, c0, c1, reward, done);
+    Info in = env_step<A, NOBJ>(e, p, tb, nav, c0, c1, reward, done);
     if (rew32 != nullptr) {
         const float rr = (float)reward;
 #pragma unroll
         for (int k = 0; k < A; ++k) rew32[((size_t)s * p.E + env) * A + k] = rr;
     }
     if (done_out != nullptr) done_out[(size_t)s * p.E + env] = done ? 1 : 0;
-    if (done) finish_episode<A, NOBJ>(e, p, tb, myrow, nullptr, env);
-    return want_obs ? finish_obs<A, NOBJ>(e, p, tb, myrow) : 0.0f;
+    if (done) {
+        finish_episode<A, NOBJ, ROWF>(e, p, tb, in, myrow, nullptr, env);
+        in = gather_info<A, NOBJ>(e, p, tb);
+    }
+    return want_obs ? finish_obs<A, NOBJ, ROWF>(e, p, tb, in, myrow) : 0.0f;
 }
 
 // oc_reset / initial bring-up of one env
-template <int A, int NOBJ>
+template <int A, int NOBJ, bool ROWF>
 __device__ __forceinline__ float reset_one_env(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb, uint32_t env,
                                                bool initial, const uint8_t* __restrict__ mask,
                                                const int32_t* __restrict__ placements, bool want_obs,
@@ -624,7 +694,9 @@ __device__ __forceinline__ float reset_one_env(Env<A, NOBJ>& e, const OcParams& 
         e.episodes += 1;
         env_reset<A, NOBJ>(e, p, tb, pl, env);
     }
-    return want_obs ? finish_obs<A, NOBJ>(e, p, tb, myrow) : 0.0f;
+    if (!want_obs) return 0.0f;
+    const Info in = gather_info<A, NOBJ>(e, p, tb);
+    return finish_obs<A, NOBJ, ROWF>(e, p, tb, in, myrow);
 }
 
 }  // namespace ock

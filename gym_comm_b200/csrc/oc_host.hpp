@@ -106,6 +106,10 @@ static inline int compile_config(const oc_config* c, HostImage& h, std::string& 
     // and the expansion needs no index arithmetic at all
     p.row_stride = (int)align_up(p.row_bytes, 4);
     if (((p.row_stride >> 2) & 1) == 0) p.row_stride += 4;
+    // float rows when a warp's 32 rows stay small (<= 24 KB) and rows are 16-byte multiples
+    p.rowf = ((p.row_bytes & 3) == 0 && 32 * p.row_bytes * 4 <= 24 * 1024) ? 1 : 0;
+    if (const char* f = getenv("OC_ROW_FORMAT")) p.rowf = (f[0] == 'f' && (p.row_bytes & 3) == 0) ? 1 : 0;
+    if (p.rowf) p.row_stride = p.row_bytes * 4;
     p.r4_magic = (p.row_bytes >= 4) ? (uint32_t)((1ull << 32) / (uint64_t)(p.row_bytes >> 2)) + 1u : 0u;
     p.rf_magic = (uint32_t)((1ull << 32) / (uint64_t)p.row_bytes) + 1u;
     for (int k = 0; k < OC_MAX_AGENTS; ++k) {
@@ -139,6 +143,7 @@ static inline int compile_config(const oc_config* c, HostImage& h, std::string& 
     // reset image: objects in world insertion order; stamp = insertion index + 1; key ranks in
     // first-insert order (world.py:236-237)
     uint64_t ranks = 0; uint32_t nkeys = 0; p.nrandom = 0;
+    for (int s = 0; s < OCK_MAX_OBJECTS; ++s) p.init_obj[s] = OCK_DEAD;
     for (int s = 0; s < c->num_objects; ++s) {
         const uint32_t b = c->object_contents[s];
         uint32_t cell = 0;
@@ -174,28 +179,33 @@ static inline int compile_config(const oc_config* c, HostImage& h, std::string& 
     if (p.ndeliver == 0) OC_BAD("no delivery subtask (overcooked_environment.py:251 asserts)");
     // items = ['Plate'] + Foods of recipes[0] (overcooked_environment.py:319-321)
     if (c->items[0] != 8) OC_BAD("items[0] must be Plate");
-    p.nfi = c->num_items - 1;
-    for (int i = 0; i < p.nfi; ++i) {
-        const int b = c->items[1 + i];
-        if (b != 1 && b != 2 && b != 4) OC_BAD("items[1..] must be single Food bits");
-        p.fi_bit[i] = (uint8_t)b;
+    p.item_foods = 0;
+    for (int i = 1; i < c->num_items; ++i) {
+        const int b = c->items[i];
+        if ((b != 1 && b != 2 && b != 4) || (p.item_foods & b)) OC_BAD("items[1..] must be distinct single Food bits");
+        p.item_foods |= (uint32_t)b;
     }
     p.npairs = c->num_items * (c->num_items - 1) / 2;
 
     // tables
     std::vector<uint8_t> pd;
     if (c->path_dist) pd.assign(c->path_dist, c->path_dist + (size_t)n * n); else bfs_path_dist(c, pd);
-    std::vector<uint8_t> mv(n * 4), xy(n * 2), dmin(n);
+    std::vector<uint16_t> mvt(n * 4), xy16(n);
+    std::vector<float> xyf(512, 0.0f);
+    std::vector<uint8_t> dmin(n), pdm((size_t)n * n);
     static const int dx[4] = {0, 0, -1, 1}, dy[4] = {1, -1, 0, 0};
     for (int i = 0; i < n; ++i) {
         const int x = i % W, y = i / W;
-        xy[2 * i] = (uint8_t)x; xy[2 * i + 1] = (uint8_t)y;
+        xy16[i] = (uint16_t)(x | (y << 8));
+        xyf[2 * i] = (float)x; xyf[2 * i + 1] = (float)y;
         for (int a = 0; a < 4; ++a) {
             const int vx = std::min(std::max(x + dx[a], 0), W - 1), vy = std::min(std::max(y + dy[a], 0), H - 1);
-            mv[4 * i + a] = (uint8_t)(vy * W + vx);
+            const int v = vy * W + vx;
+            mvt[4 * i + a] = (uint16_t)(v | (c->tiles[v] << 8));
         }
         int best = 1 << 20;
-        for (int d : deliveries) best = std::min(best, (int)pd[(size_t)i * n + d] + abs(x - d % W) + abs(y - d / W));
+        for (int j = 0; j < n; ++j) pdm[(size_t)i * n + j] = (uint8_t)((int)pd[(size_t)i * n + j] + abs(x - j % W) + abs(y - j / W));
+        for (int d : deliveries) best = std::min(best, (int)pdm[(size_t)i * n + d]);
         dmin[i] = (uint8_t)best;
     }
     const int nq = std::max(std::max(2 * M + std::max(nchop - 1, 0) * 2 * M, p.npairs * M), M + W + H) + 1;
@@ -207,23 +217,24 @@ static inline int compile_config(const oc_config* c, HostImage& h, std::string& 
     size_t off = 0;
     p.o_q = (int)off; off += align_up(q.size() * 8, 16);
     p.o_tmlut = (int)off; off += 128 * 4;
-    p.o_tile = (int)off; off += align_up(n, 16);
-    p.o_mv = (int)off; off += align_up(n * 4, 16);
-    p.o_xy = (int)off; off += align_up(n * 2, 16);
+    p.o_xyf = (int)off; off += 512 * 4;
+    p.o_mvt = (int)off; off += align_up((size_t)n * 8, 16);
+    p.o_xy16 = (int)off; off += align_up((size_t)n * 2, 16);
     p.o_dmin = (int)off; off += align_up(n, 16);
     p.o_counters = (int)off; off += align_up(std::max<size_t>(counters.size(), 1), 16);
     p.o_pd = (int)off; off += align_up((size_t)n * n, 16);
+    p.o_pdm = (int)off; off += align_up((size_t)n * n, 16);
     p.blob_bytes = (int)off;
     std::vector<uint8_t>& blob = h.blob; blob.assign(off, 0);
     memcpy(blob.data() + p.o_q, q.data(), q.size() * 8);
     memcpy(blob.data() + p.o_tmlut, tmlut.data(), 128 * 4);
-    memcpy(blob.data() + p.o_tile, c->tiles, n);
-    memcpy(blob.data() + p.o_mv, mv.data(), mv.size());
-    memcpy(blob.data() + p.o_xy, xy.data(), xy.size());
+    memcpy(blob.data() + p.o_xyf, xyf.data(), 512 * 4);
+    memcpy(blob.data() + p.o_mvt, mvt.data(), mvt.size() * 2);
+    memcpy(blob.data() + p.o_xy16, xy16.data(), xy16.size() * 2);
     memcpy(blob.data() + p.o_dmin, dmin.data(), dmin.size());
     if (!counters.empty()) memcpy(blob.data() + p.o_counters, counters.data(), counters.size());
     memcpy(blob.data() + p.o_pd, pd.data(), pd.size());
-
+    memcpy(blob.data() + p.o_pdm, pdm.data(), pdm.size());
     return OC_OK;
 #undef OC_BAD
 }

@@ -21,7 +21,7 @@ using namespace ock;
 // =============================================================================================
 
 // dynamic shared memory: [table blob][per warp: 32 byte-rows]
-template <int A, int NOBJ>
+template <int A, int NOBJ, bool ROWF>
 __global__ void __launch_bounds__(256)
 oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
                const int32_t* __restrict__ actions, float* __restrict__ obs,
@@ -43,27 +43,27 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
     }
     load_tables(p, smem);
     uint8_t* wrows = smem + p.blob_bytes + (size_t)warp * 32 * p.row_stride;
-    warp_zero_rows(wrows, 32 * p.row_stride, lane);
+    warp_clear_rows<ROWF>(wrows, 32 * p.row_stride, lane);
     __syncthreads();
     const Tables tb = make_tables(p, smem);
     uint8_t* myrow = wrows + lane * p.row_stride;
 
     float ts = 0.0f;
     if (valid) {
-        ts = step_one_env<A, NOBJ>(e, p, tb, nav, comm[0], comm[1], (uint32_t)env, myrow,
+        ts = step_one_env<A, NOBJ, ROWF>(e, p, tb, nav, comm[0], comm[1], (uint32_t)env, myrow,
                                    rew32, rew64, done_out, term_obs, flags);
         store_env<A, NOBJ>(e, state, p.E, env);
     }
     __syncwarp();
     const int env0 = blockIdx.x * blockDim.x + warp * 32;
     const int nvalid = min(32, p.E - env0);
-    if (nvalid > 0) warp_expand_rows(p, wrows, obs + (size_t)env0 * p.row_bytes, nvalid, lane);
+    if (nvalid > 0) warp_expand_rows<ROWF>(p, wrows, obs + (size_t)env0 * p.row_bytes, nvalid, lane);
     __syncwarp();                                   // order the float4 stores before the timestep patch
-    if (valid) store_timesteps<A>(p, obs + (size_t)env * p.row_bytes, ts);
+    if (!ROWF && valid) store_timesteps<A>(p, obs + (size_t)env * p.row_bytes, ts);
 }
 
 // n_steps steps per launch, state in registers, Philox actions (SURVEY section 8d synthetic inputs)
-template <int A, int NOBJ>
+template <int A, int NOBJ, bool ROWF>
 __global__ void __launch_bounds__(256)
 oc_rollout_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, int n_steps, uint32_t step0,
                   float* __restrict__ obs, float* __restrict__ rew32, uint8_t* __restrict__ done_out,
@@ -84,25 +84,25 @@ oc_rollout_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
     const size_t step_floats = (size_t)p.E * p.row_bytes;
 
     for (int s = 0; s < n_steps; ++s) {
-        if (obs != nullptr) { warp_zero_rows(wrows, 32 * p.row_stride, lane); __syncwarp(); }
+        if (obs != nullptr) { warp_clear_rows<ROWF>(wrows, 32 * p.row_stride, lane); __syncwarp(); }
         float ts = 0.0f;
         if (valid) {
-            ts = rollout_one_env<A, NOBJ>(e, p, tb, (uint32_t)env, (uint32_t)s, step0, myrow,
+            ts = rollout_one_env<A, NOBJ, ROWF>(e, p, tb, (uint32_t)env, (uint32_t)s, step0, myrow,
                                           obs != nullptr, rew32, done_out, actions_out);
         }
         if (obs != nullptr) {
             float* step_obs = obs + (size_t)s * step_floats;
             __syncwarp();
-            if (nvalid > 0) warp_expand_rows(p, wrows, step_obs + (size_t)env0 * p.row_bytes, nvalid, lane);
+            if (nvalid > 0) warp_expand_rows<ROWF>(p, wrows, step_obs + (size_t)env0 * p.row_bytes, nvalid, lane);
             __syncwarp();
-            if (valid) store_timesteps<A>(p, step_obs + (size_t)env * p.row_bytes, ts);
+            if (!ROWF && valid) store_timesteps<A>(p, step_obs + (size_t)env * p.row_bytes, ts);
         }
     }
     if (valid) store_env<A, NOBJ>(e, state, p.E, env);
 }
 
 // reset (masked) + observation of every env
-template <int A, int NOBJ>
+template <int A, int NOBJ, bool ROWF>
 __global__ void __launch_bounds__(256)
 oc_reset_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, const uint8_t* __restrict__ mask,
                 const int32_t* __restrict__ placements, float* __restrict__ obs, int initial) {
@@ -114,12 +114,12 @@ oc_reset_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, c
     if (valid && !initial) load_env<A, NOBJ>(e, state, p.E, env);
     load_tables(p, smem);
     uint8_t* wrows = smem + p.blob_bytes + (size_t)warp * 32 * p.row_stride;
-    warp_zero_rows(wrows, 32 * p.row_stride, lane);
+    warp_clear_rows<ROWF>(wrows, 32 * p.row_stride, lane);
     __syncthreads();
     const Tables tb = make_tables(p, smem);
     float ts = 0.0f;
     if (valid) {
-        ts = reset_one_env<A, NOBJ>(e, p, tb, (uint32_t)env, initial != 0, mask, placements, obs != nullptr,
+        ts = reset_one_env<A, NOBJ, ROWF>(e, p, tb, (uint32_t)env, initial != 0, mask, placements, obs != nullptr,
                                     wrows + lane * p.row_stride);
         store_env<A, NOBJ>(e, state, p.E, env);
     }
@@ -127,9 +127,9 @@ oc_reset_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, c
     const int env0 = blockIdx.x * blockDim.x + warp * 32;
     const int nvalid = min(32, p.E - env0);
     if (obs != nullptr) {
-        if (nvalid > 0) warp_expand_rows(p, wrows, obs + (size_t)env0 * p.row_bytes, nvalid, lane);
+        if (nvalid > 0) warp_expand_rows<ROWF>(p, wrows, obs + (size_t)env0 * p.row_bytes, nvalid, lane);
         __syncwarp();
-        if (valid) store_timesteps<A>(p, obs + (size_t)env * p.row_bytes, ts);
+        if (!ROWF && valid) store_timesteps<A>(p, obs + (size_t)env * p.row_bytes, ts);
     }
 }
 
@@ -180,8 +180,12 @@ struct oc_env {
 };
 
 template <typename F>
-static int dispatch(int A, int NOBJ, F&& f) {
-#define OC_CASE(a, n) if (A == a && NOBJ == n) return f(std::integral_constant<int, a>(), std::integral_constant<int, n>());
+static int dispatch(int A, int NOBJ, int rowf, F&& f) {
+#define OC_CASE(a, n)                                                                                              \
+    if (A == a && NOBJ == n) {                                                                                     \
+        if (rowf) return f(std::integral_constant<int, a>(), std::integral_constant<int, n>(), std::true_type());  \
+        return f(std::integral_constant<int, a>(), std::integral_constant<int, n>(), std::false_type());           \
+    }
     OC_CASE(2, 4) OC_CASE(3, 4) OC_CASE(4, 4) OC_CASE(2, 6) OC_CASE(3, 6) OC_CASE(4, 6)
 #undef OC_CASE
     return fail(OC_ERR_INVALID, "unsupported (num_agents, num_objects)");
@@ -232,13 +236,14 @@ extern "C" int oc_create(const oc_config* c, oc_env** out) {
     p.blob = h->blob; p.ts_table = h->ts;
 
     // opt in to large dynamic shared memory for every instantiation we may launch
-    int rc = dispatch(p.A, p.NOBJ, [&](auto a, auto nobj) -> int {
+    int rc = dispatch(p.A, p.NOBJ, p.rowf, [&](auto a, auto nobj, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
-        CUDA_TRY(cudaFuncSetAttribute(oc_step_kernel<AA, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-        CUDA_TRY(cudaFuncSetAttribute(oc_rollout_kernel<AA, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-        CUDA_TRY(cudaFuncSetAttribute(oc_reset_kernel<AA, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        constexpr bool RF = decltype(rf)::value;
+        CUDA_TRY(cudaFuncSetAttribute(oc_step_kernel<AA, NN, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        CUDA_TRY(cudaFuncSetAttribute(oc_rollout_kernel<AA, NN, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        CUDA_TRY(cudaFuncSetAttribute(oc_reset_kernel<AA, NN, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
         const int grid = (p.E + h->threads - 1) / h->threads;
-        oc_reset_kernel<AA, NN><<<grid, h->threads, h->smem_bytes, 0>>>(p, h->state, nullptr, nullptr, nullptr, 1);
+        oc_reset_kernel<AA, NN, RF><<<grid, h->threads, h->smem_bytes, 0>>>(p, h->state, nullptr, nullptr, nullptr, 1);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaDeviceSynchronize());
         return OC_OK;
@@ -272,10 +277,11 @@ extern "C" int oc_reset(oc_env* h, const uint8_t* mask, const int32_t* placement
     if (!h) return fail(OC_ERR_INVALID, "null handle");
     if (obs && misaligned16(obs)) return fail(OC_ERR_INVALID, "obs must be 16-byte aligned");
     const OcParams& p = h->p;
-    int rc = dispatch(p.A, p.NOBJ, [&](auto a, auto nobj) -> int {
+    int rc = dispatch(p.A, p.NOBJ, p.rowf, [&](auto a, auto nobj, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
+        constexpr bool RF = decltype(rf)::value;
         const int grid = (p.E + h->threads - 1) / h->threads;
-        oc_reset_kernel<AA, NN><<<grid, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(p, h->state, mask, placements, obs, 0);
+        oc_reset_kernel<AA, NN, RF><<<grid, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(p, h->state, mask, placements, obs, 0);
         CUDA_TRY(cudaGetLastError());
         return OC_OK;
     });
@@ -288,10 +294,11 @@ extern "C" int oc_step(oc_env* h, const int32_t* actions, float* obs, float* rew
     if (!h || !actions || !obs || !done) return fail(OC_ERR_INVALID, "null argument");
     if (misaligned16(obs) || (reinterpret_cast<uintptr_t>(actions) & 7)) return fail(OC_ERR_INVALID, "obs must be 16-byte and actions 8-byte aligned");
     const OcParams& p = h->p;
-    int rc = dispatch(p.A, p.NOBJ, [&](auto a, auto nobj) -> int {
+    int rc = dispatch(p.A, p.NOBJ, p.rowf, [&](auto a, auto nobj, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
+        constexpr bool RF = decltype(rf)::value;
         const int grid = (p.E + h->threads - 1) / h->threads;
-        oc_step_kernel<AA, NN><<<grid, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(
+        oc_step_kernel<AA, NN, RF><<<grid, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(
             p, h->state, actions, obs, rew_f32, rew_f64, done, term_obs, flags);
         CUDA_TRY(cudaGetLastError());
         return OC_OK;
@@ -305,10 +312,11 @@ extern "C" int oc_rollout(oc_env* h, int32_t n_steps, float* obs, float* rew_f32
     if (!h || n_steps <= 0) return fail(OC_ERR_INVALID, "bad argument");
     if (obs && misaligned16(obs)) return fail(OC_ERR_INVALID, "obs must be 16-byte aligned");
     const OcParams& p = h->p;
-    int rc = dispatch(p.A, p.NOBJ, [&](auto a, auto nobj) -> int {
+    int rc = dispatch(p.A, p.NOBJ, p.rowf, [&](auto a, auto nobj, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
+        constexpr bool RF = decltype(rf)::value;
         const int grid = (p.E + h->threads - 1) / h->threads;
-        oc_rollout_kernel<AA, NN><<<grid, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(
+        oc_rollout_kernel<AA, NN, RF><<<grid, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(
             p, h->state, n_steps, h->rollout_step, obs, rew_f32, done, actions_out);
         CUDA_TRY(cudaGetLastError());
         return OC_OK;

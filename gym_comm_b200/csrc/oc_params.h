@@ -19,10 +19,11 @@
 // w5  last_completed[0:8] (popcount of completed at the end of the last episode)
 // w6,w7  world.objects key ranks: 16 x 4 bit, index = contents mask, 0 = key absent, else rank+1
 // w8..w13 objects: contents[0:4] | chopped[4:7] | holder[8:11] (7 = not held) | cell[16:24] | stamp[24:32]
-//         (word 0 = dead slot)
+//         (OCK_DEAD = empty slot: no contents, nobody holds it, cell 0xFF -- matches no holder / cell test)
 // w14 comm index agent0 [0:16] | agent1 [16:32]   (0xFFFF = all-zero vector)
 // w15 reserved
 #define OCK_HOLDER_NONE 7u
+#define OCK_DEAD 0x00FF0700u
 #define OCK_COMM_NONE 0xFFFFu
 
 struct OcParams {
@@ -30,9 +31,10 @@ struct OcParams {
     int32_t W, H, ncell;
     int32_t T, C, S, F;
     int32_t fow, M;
-    int32_t row_bytes;        // A * F
-    int32_t row_stride;       // smem byte-row stride per env: == row_bytes when that is an odd number of
-                              // words (rows contiguous AND conflict-free), else padded to one
+    int32_t row_bytes;        // A * F = features (floats) of one env row in global memory
+    int32_t rowf;             // 1: float32 rows in shared memory (row_stride = 4 * row_bytes), 0: biased-byte rows
+    int32_t row_stride;       // shared-memory bytes per env row.  Byte rows: == row_bytes when that is an odd
+                              // number of words (contiguous AND conflict-free), else padded to one
     uint8_t can_move[OCK_MAX_AGENTS];
     uint8_t allergic[OCK_MAX_AGENTS];
     uint8_t blind[OCK_MAX_AGENTS];
@@ -51,8 +53,7 @@ struct OcParams {
     uint8_t  deliver_sig[OCK_MAX_DELIVER];  // in table order
     uint8_t  deliver_idx[OCK_MAX_DELIVER];
     int32_t  npairs;                        // C(num_items, 2) item pairs of calculate_reward_shaping
-    int32_t  nfi;                           // number of Food items (items[1..]); items[0] is Plate
-    uint8_t  fi_bit[4];                     // their content bits, in item order
+    uint32_t item_foods;                    // Food bits among the shaping items (items[0] is always Plate)
     uint32_t r4_magic, rf_magic;            // floor(2^32 / d) + 1 for d = row_bytes / 4 and row_bytes
     // observation layout (float offsets inside one observer row)
     int32_t off_a1comm, off_a1loc, off_a2comm, off_a2loc, off_hold, off_completed,
@@ -61,6 +62,6 @@ struct OcParams {
     // table blob (device pointer) and the byte offsets of its sections; copied to smem per CTA
     const uint8_t* blob;
     int32_t blob_bytes;        // multiple of 16
-    int32_t o_q, o_tmlut, o_tile, o_mv, o_xy, o_dmin, o_counters, o_pd;
+    int32_t o_q, o_tmlut, o_xyf, o_mvt, o_xy16, o_dmin, o_counters, o_pd, o_pdm;
     const float* ts_table;     // [T+1] float32(t / T)   (overcooked_env.py:146)
 };

@@ -25,14 +25,18 @@ struct emu_env {
 static std::string g_err;
 
 template <typename F>
-static int dispatch(int A, int NOBJ, F&& f) {
-#define OC_CASE(a, n) if (A == a && NOBJ == n) return f(std::integral_constant<int, a>(), std::integral_constant<int, n>());
+static int dispatch(int A, int NOBJ, int rowf, F&& f) {
+#define OC_CASE(a, n)                                                                                              \
+    if (A == a && NOBJ == n) {                                                                                     \
+        if (rowf) return f(std::integral_constant<int, a>(), std::integral_constant<int, n>(), std::true_type());  \
+        return f(std::integral_constant<int, a>(), std::integral_constant<int, n>(), std::false_type());           \
+    }
     OC_CASE(2, 4) OC_CASE(3, 4) OC_CASE(4, 4) OC_CASE(2, 6) OC_CASE(3, 6) OC_CASE(4, 6)
 #undef OC_CASE
     return OC_ERR_INVALID;
 }
 
-template <int A, int NOBJ, typename Body>
+template <int A, int NOBJ, bool ROWF, typename Body>
 static void for_each_warp(emu_env* h, float* obs, Body&& body) {
     const OcParams& p = h->p;
     const Tables tb = make_tables(p, h->blob.data());
@@ -40,13 +44,14 @@ static void for_each_warp(emu_env* h, float* obs, Body&& body) {
     float wts[32];
     for (int env0 = 0; env0 < p.E; env0 += 32) {
         const int nvalid = std::min(32, p.E - env0);
-        for (int lane = 0; lane < 32; ++lane) warp_zero_rows(rows.data(), 32 * p.row_stride, lane);
+        for (int lane = 0; lane < 32; ++lane) warp_clear_rows<ROWF>(rows.data(), 32 * p.row_stride, lane);
         for (int lane = 0; lane < nvalid; ++lane) wts[lane] = body(tb, env0 + lane, rows.data() + (size_t)lane * p.row_stride);
         if (obs) {
             for (int lane = 0; lane < 32; ++lane)
-                warp_expand_rows(p, rows.data(), obs + (size_t)env0 * p.row_bytes, nvalid, lane);
-            for (int lane = 0; lane < nvalid; ++lane)
-                store_timesteps<A>(p, obs + (size_t)(env0 + lane) * p.row_bytes, wts[lane]);
+                warp_expand_rows<ROWF>(p, rows.data(), obs + (size_t)env0 * p.row_bytes, nvalid, lane);
+            if (!ROWF)
+                for (int lane = 0; lane < nvalid; ++lane)
+                    store_timesteps<A>(p, obs + (size_t)(env0 + lane) * p.row_bytes, wts[lane]);
         }
     }
 }
@@ -64,11 +69,12 @@ int emu_create(const oc_config* c, emu_env** out) {
     memcpy(h->obs_size, img.obs_size, sizeof(h->obs_size));
     h->p.blob = h->blob.data(); h->p.ts_table = h->ts.data();
     h->state.assign((size_t)h->p.E * 4, uint4{0, 0, 0, 0});
-    dispatch(h->p.A, h->p.NOBJ, [&](auto a, auto n) -> int {
+    dispatch(h->p.A, h->p.NOBJ, h->p.rowf, [&](auto a, auto n, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = decltype(n)::value;
-        for_each_warp<AA, NN>(h, nullptr, [&](const Tables& tb, int env, uint8_t* row) -> float {
+        constexpr bool RF = decltype(rf)::value;
+        for_each_warp<AA, NN, RF>(h, nullptr, [&](const Tables& tb, int env, uint8_t* row) -> float {
             Env<AA, NN> e;
-            const float ts = reset_one_env<AA, NN>(e, h->p, tb, (uint32_t)env, true, nullptr, nullptr, false, row);
+            const float ts = reset_one_env<AA, NN, RF>(e, h->p, tb, (uint32_t)env, true, nullptr, nullptr, false, row);
             store_env<AA, NN>(e, h->state.data(), h->p.E, env);
             return ts;
         });
@@ -85,12 +91,13 @@ int emu_obs_layout(const emu_env* h, int32_t* off, int32_t* sz) {
 }
 
 int emu_reset(emu_env* h, const uint8_t* mask, const int32_t* placements, float* obs, void*) {
-    return dispatch(h->p.A, h->p.NOBJ, [&](auto a, auto n) -> int {
+    return dispatch(h->p.A, h->p.NOBJ, h->p.rowf, [&](auto a, auto n, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = decltype(n)::value;
-        for_each_warp<AA, NN>(h, obs, [&](const Tables& tb, int env, uint8_t* row) -> float {
+        constexpr bool RF = decltype(rf)::value;
+        for_each_warp<AA, NN, RF>(h, obs, [&](const Tables& tb, int env, uint8_t* row) -> float {
             Env<AA, NN> e;
             load_env<AA, NN>(e, h->state.data(), h->p.E, env);
-            const float ts = reset_one_env<AA, NN>(e, h->p, tb, (uint32_t)env, false, mask, placements, obs != nullptr, row);
+            const float ts = reset_one_env<AA, NN, RF>(e, h->p, tb, (uint32_t)env, false, mask, placements, obs != nullptr, row);
             store_env<AA, NN>(e, h->state.data(), h->p.E, env);
             return ts;
         });
@@ -100,14 +107,15 @@ int emu_reset(emu_env* h, const uint8_t* mask, const int32_t* placements, float*
 
 int emu_step(emu_env* h, const int32_t* actions, float* obs, float* rew32, double* rew64, uint8_t* done,
              float* term_obs, uint32_t flags, void*) {
-    return dispatch(h->p.A, h->p.NOBJ, [&](auto a, auto n) -> int {
+    return dispatch(h->p.A, h->p.NOBJ, h->p.rowf, [&](auto a, auto n, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = decltype(n)::value;
-        for_each_warp<AA, NN>(h, obs, [&](const Tables& tb, int env, uint8_t* row) -> float {
+        constexpr bool RF = decltype(rf)::value;
+        for_each_warp<AA, NN, RF>(h, obs, [&](const Tables& tb, int env, uint8_t* row) -> float {
             Env<AA, NN> e;
             load_env<AA, NN>(e, h->state.data(), h->p.E, env);
             int nav[AA], comm[AA];
             for (int k = 0; k < AA; ++k) { nav[k] = actions[((size_t)env * AA + k) * 2] & 3; comm[k] = actions[((size_t)env * AA + k) * 2 + 1]; }
-            const float ts = step_one_env<AA, NN>(e, h->p, tb, nav, comm[0], comm[1], (uint32_t)env, row, rew32, rew64, done, term_obs, flags);
+            const float ts = step_one_env<AA, NN, RF>(e, h->p, tb, nav, comm[0], comm[1], (uint32_t)env, row, rew32, rew64, done, term_obs, flags);
             store_env<AA, NN>(e, h->state.data(), h->p.E, env);
             return ts;
         });
@@ -117,14 +125,15 @@ int emu_step(emu_env* h, const int32_t* actions, float* obs, float* rew32, doubl
 
 int emu_rollout(emu_env* h, int32_t n_steps, float* obs, float* rew32, uint8_t* done, int32_t* actions_out, void*) {
     const size_t step_floats = (size_t)h->p.E * h->p.row_bytes;
-    int rc = dispatch(h->p.A, h->p.NOBJ, [&](auto a, auto n) -> int {
+    int rc = dispatch(h->p.A, h->p.NOBJ, h->p.rowf, [&](auto a, auto n, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = decltype(n)::value;
+        constexpr bool RF = decltype(rf)::value;
         for (int s = 0; s < n_steps; ++s)
-            for_each_warp<AA, NN>(h, obs ? obs + (size_t)s * step_floats : nullptr,
+            for_each_warp<AA, NN, RF>(h, obs ? obs + (size_t)s * step_floats : nullptr,
                                   [&](const Tables& tb, int env, uint8_t* row) -> float {
                 Env<AA, NN> e;
                 load_env<AA, NN>(e, h->state.data(), h->p.E, env);
-                const float ts = rollout_one_env<AA, NN>(e, h->p, tb, (uint32_t)env, (uint32_t)s, h->rollout_step, row,
+                const float ts = rollout_one_env<AA, NN, RF>(e, h->p, tb, (uint32_t)env, (uint32_t)s, h->rollout_step, row,
                                                          obs != nullptr, rew32, done, actions_out);
                 store_env<AA, NN>(e, h->state.data(), h->p.E, env);
                 return ts;

@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 #include <algorithm>
 #define __device__
 #define __forceinline__ inline
@@ -16,6 +17,7 @@ using std::max;
 struct uint4 { uint32_t x, y, z, w; };
 struct float4 { float x, y, z, w; };
 struct int2 { int x, y; };
+struct float2 { float x, y; };
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
@@ -27,6 +29,8 @@ static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t s) {
     return r;
 }
 static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline float __saturatef(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
+static inline float __fmaf_rn(float a, float b, float c) { return __builtin_fmaf(a, b, c); }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
