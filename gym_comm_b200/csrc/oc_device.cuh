@@ -28,7 +28,7 @@ enum : uint32_t { TILE_FLOOR = 0, TILE_COUNTER = 1, TILE_CUTBOARD = 2, TILE_DELI
 struct Tables {
     const double*   q;        // q[n] = n / MAX_PATH as the reference's Python float (f64)
     const uint32_t* tmlut;    // [128] object signature -> bitmask of subtasks whose goal template it equals
-    const float2*   xyf;      // [256] (x, y) of a cell as floats (index 0xFF = dead slot, harmless)
+    const float2*   xyf;      // [ncell] (x, y) of a cell as floats (only ever indexed with live cells)
     const uint16_t* mvt;      // [ncell*4] inbounds(cell + NAV[a]) | tile(target) << 8     world.py:317-320
     const uint16_t* xy16;     // [ncell] x | y << 8
     const uint8_t*  dmin;     // [ncell] min over Delivery tiles of pd + manhattan   overcooked_environment.py:383-388

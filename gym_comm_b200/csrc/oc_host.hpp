@@ -191,7 +191,7 @@ static inline int compile_config(const oc_config* c, HostImage& h, std::string& 
     std::vector<uint8_t> pd;
     if (c->path_dist) pd.assign(c->path_dist, c->path_dist + (size_t)n * n); else bfs_path_dist(c, pd);
     std::vector<uint16_t> mvt(n * 4), xy16(n);
-    std::vector<float> xyf(512, 0.0f);
+    std::vector<float> xyf((size_t)2 * n, 0.0f);
     std::vector<uint8_t> dmin(n), pdm((size_t)n * n);
     static const int dx[4] = {0, 0, -1, 1}, dy[4] = {1, -1, 0, 0};
     for (int i = 0; i < n; ++i) {
@@ -217,7 +217,7 @@ static inline int compile_config(const oc_config* c, HostImage& h, std::string& 
     size_t off = 0;
     p.o_q = (int)off; off += align_up(q.size() * 8, 16);
     p.o_tmlut = (int)off; off += 128 * 4;
-    p.o_xyf = (int)off; off += 512 * 4;
+    p.o_xyf = (int)off; off += align_up((size_t)n * 8, 16);
     p.o_mvt = (int)off; off += align_up((size_t)n * 8, 16);
     p.o_xy16 = (int)off; off += align_up((size_t)n * 2, 16);
     p.o_dmin = (int)off; off += align_up(n, 16);
@@ -228,7 +228,7 @@ static inline int compile_config(const oc_config* c, HostImage& h, std::string& 
     std::vector<uint8_t>& blob = h.blob; blob.assign(off, 0);
     memcpy(blob.data() + p.o_q, q.data(), q.size() * 8);
     memcpy(blob.data() + p.o_tmlut, tmlut.data(), 128 * 4);
-    memcpy(blob.data() + p.o_xyf, xyf.data(), 512 * 4);
+    memcpy(blob.data() + p.o_xyf, xyf.data(), xyf.size() * 4);
     memcpy(blob.data() + p.o_mvt, mvt.data(), mvt.size() * 2);
     memcpy(blob.data() + p.o_xy16, xy16.data(), xy16.size() * 2);
     memcpy(blob.data() + p.o_dmin, dmin.data(), dmin.size());

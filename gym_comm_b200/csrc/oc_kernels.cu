@@ -32,7 +32,16 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = env < p.E;
 
-    // global loads first so their latency overlaps the table copy
+    // Programmatic dependent launch: let the NEXT launch in the stream start its own prologue as
+    // soon as every CTA of this grid is running; do our prologue (tables, row clear) before
+    // waiting for the previous grid -- only what follows the wait touches its outputs (state,
+    // actions).  Both instructions are no-ops when the launch carries no PDL attribute.
+    asm volatile("griddepcontrol.launch_dependents;");
+    load_tables(p, smem);
+    uint8_t* wrows = smem + p.blob_bytes + (size_t)warp * 32 * p.row_stride;
+    warp_clear_rows<ROWF>(wrows, 32 * p.row_stride, lane);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
     Env<A, NOBJ> e;
     int nav[A], comm[A];
     if (valid) {
@@ -41,9 +50,6 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
 #pragma unroll
         for (int k = 0; k < A; ++k) { const int2 v = __ldg(a2 + k); nav[k] = v.x & 3; comm[k] = v.y; }
     }
-    load_tables(p, smem);
-    uint8_t* wrows = smem + p.blob_bytes + (size_t)warp * 32 * p.row_stride;
-    warp_clear_rows<ROWF>(wrows, 32 * p.row_stride, lane);
     __syncthreads();
     const Tables tb = make_tables(p, smem);
     uint8_t* myrow = wrows + lane * p.row_stride;
@@ -176,6 +182,7 @@ struct oc_env {
     float* ts = nullptr;
     uint64_t launches = 0;
     uint32_t rollout_step = 0;
+    int pdl = 1;
     int obs_off[OC_NUM_OBS_KEYS], obs_size[OC_NUM_OBS_KEYS];
 };
 
@@ -215,6 +222,7 @@ extern "C" int oc_create(const oc_config* c, oc_env** out) {
     }
     h->device = dev;
 
+    if (const char* pe = getenv("OC_PDL")) h->pdl = atoi(pe) != 0;
     const char* tenv = getenv("OC_BLOCK_THREADS");
     h->threads = tenv ? atoi(tenv) : 64;
     if (h->threads < 32 || h->threads > 256 || (h->threads & 31)) h->threads = 64;
@@ -298,9 +306,16 @@ extern "C" int oc_step(oc_env* h, const int32_t* actions, float* obs, float* rew
         constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
         constexpr bool RF = decltype(rf)::value;
         const int grid = (p.E + h->threads - 1) / h->threads;
-        oc_step_kernel<AA, NN, RF><<<grid, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(
-            p, h->state, actions, obs, rew_f32, rew_f64, done, term_obs, flags);
-        CUDA_TRY(cudaGetLastError());
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(h->threads);
+        cfg.dynamicSmemBytes = h->smem_bytes; cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = h->pdl ? 1 : 0;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, oc_step_kernel<AA, NN, RF>, p, h->state, actions, obs, rew_f32, rew_f64,
+                                    done, term_obs, flags));
         return OC_OK;
     });
     if (rc == OC_OK) h->launches += 1;
