@@ -28,9 +28,7 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
                float* __restrict__ rew32, double* __restrict__ rew64, uint8_t* __restrict__ done_out,
                float* __restrict__ term_obs, uint32_t flags) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = env < p.E;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     // Programmatic dependent launch: let the NEXT launch in the stream start its own prologue as
     // soon as every CTA of this grid is running; do our prologue (tables, row clear) before
@@ -39,33 +37,37 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
     asm volatile("griddepcontrol.launch_dependents;");
     load_tables(p, smem);
     uint8_t* wrows = smem + p.blob_bytes + (size_t)warp * 32 * p.row_stride;
+    uint8_t* myrow = wrows + lane * p.row_stride;
     warp_clear_rows<ROWF>(wrows, 32 * p.row_stride, lane);
     asm volatile("griddepcontrol.wait;" ::: "memory");
-
-    Env<A, NOBJ> e;
-    int nav[A], comm[A];
-    if (valid) {
-        load_env<A, NOBJ>(e, state, p.E, env);
-        const int2* a2 = reinterpret_cast<const int2*>(actions) + (size_t)env * A;
-#pragma unroll
-        for (int k = 0; k < A; ++k) { const int2 v = __ldg(a2 + k); nav[k] = v.x & 3; comm[k] = v.y; }
-    }
     __syncthreads();
     const Tables tb = make_tables(p, smem);
-    uint8_t* myrow = wrows + lane * p.row_stride;
 
-    float ts = 0.0f;
-    if (valid) {
-        ts = step_one_env<A, NOBJ, ROWF>(e, p, tb, nav, comm[0], comm[1], (uint32_t)env, myrow,
-                                   rew32, rew64, done_out, term_obs, flags);
-        store_env<A, NOBJ>(e, state, p.E, env);
+    // the grid is sized to ONE resident wave (148 SMs x CTAs that fit); with more envs than that
+    // each CTA walks several chunks so the tables are loaded once per CTA, not once per chunk
+    for (int base = blockIdx.x * blockDim.x; base < p.E; base += gridDim.x * blockDim.x) {
+        const int env = base + threadIdx.x;
+        const bool valid = env < p.E;
+        float ts = 0.0f;
+        if (valid) {
+            Env<A, NOBJ> e;
+            int nav[A], comm[A];
+            load_env<A, NOBJ>(e, state, p.E, env);
+            const int2* a2 = reinterpret_cast<const int2*>(actions) + (size_t)env * A;
+#pragma unroll
+            for (int k = 0; k < A; ++k) { const int2 v = __ldg(a2 + k); nav[k] = v.x & 3; comm[k] = v.y; }
+            ts = step_one_env<A, NOBJ, ROWF>(e, p, tb, nav, comm[0], comm[1], (uint32_t)env, myrow,
+                                             rew32, rew64, done_out, term_obs, flags);
+            store_env<A, NOBJ>(e, state, p.E, env);
+        }
+        __syncwarp();
+        const int env0 = base + warp * 32;
+        const int nvalid = min(32, p.E - env0);
+        if (nvalid > 0) warp_expand_rows<ROWF>(p, wrows, obs + (size_t)env0 * p.row_bytes, nvalid, lane);
+        __syncwarp();                               // order the float4 stores before the timestep patch
+        if (!ROWF && valid) store_timesteps<A>(p, obs + (size_t)env * p.row_bytes, ts);
+        if (base + gridDim.x * blockDim.x < p.E) { warp_clear_rows<ROWF>(wrows, 32 * p.row_stride, lane); __syncwarp(); }
     }
-    __syncwarp();
-    const int env0 = blockIdx.x * blockDim.x + warp * 32;
-    const int nvalid = min(32, p.E - env0);
-    if (nvalid > 0) warp_expand_rows<ROWF>(p, wrows, obs + (size_t)env0 * p.row_bytes, nvalid, lane);
-    __syncwarp();                                   // order the float4 stores before the timestep patch
-    if (!ROWF && valid) store_timesteps<A>(p, obs + (size_t)env * p.row_bytes, ts);
 }
 
 // n_steps steps per launch, state in registers, Philox actions (SURVEY section 8d synthetic inputs)
@@ -183,6 +185,7 @@ struct oc_env {
     uint64_t launches = 0;
     uint32_t rollout_step = 0;
     int pdl = 1;
+    int step_grid = 1;
     int obs_off[OC_NUM_OBS_KEYS], obs_size[OC_NUM_OBS_KEYS];
 };
 
@@ -223,13 +226,33 @@ extern "C" int oc_create(const oc_config* c, oc_env** out) {
     h->device = dev;
 
     if (const char* pe = getenv("OC_PDL")) h->pdl = atoi(pe) != 0;
-    const char* tenv = getenv("OC_BLOCK_THREADS");
-    h->threads = tenv ? atoi(tenv) : 64;
-    if (h->threads < 32 || h->threads > 256 || (h->threads & 31)) h->threads = 64;
+    // CTA shape: the work is one warp per 32 envs; pick the CTA size whose resident wave
+    // (limited by shared memory: table blob + 32 rows per warp, by 2048 threads and 32 CTAs per
+    // SM) covers the envs with the smallest makespan, preferring fewer table copies on ties.
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    const int num_sm = prop.multiProcessorCount;
+    const size_t smem_sm = prop.sharedMemPerMultiprocessor, smem_cta_max = prop.sharedMemPerBlockOptin;
     auto smem_for = [&](int threads) { return (size_t)p.blob_bytes + (size_t)(threads / 32) * (32 * (size_t)p.row_stride); };
-    while (h->threads > 32 && smem_for(h->threads) > 200 * 1024) h->threads -= 32;
-    h->smem_bytes = smem_for(h->threads);
-    if (h->smem_bytes > 227 * 1024) { delete h; return fail(OC_ERR_INVALID, "observation row too wide for shared memory"); }
+    const char* tenv = getenv("OC_BLOCK_THREADS");
+    int best_t = 0, best_cap = 1; double best_cost = 1e30;
+    for (int t = 32; t <= 256; t += 32) {
+        if (tenv && atoi(tenv) != t) continue;
+        const size_t sm = smem_for(t);
+        if (sm > smem_cta_max) continue;
+        int cap = (int)std::min<size_t>(smem_sm / (sm + 1024), (size_t)std::min(2048 / t, 32));
+        if (cap < 1) continue;
+        const long long ctas = ((long long)p.E + t - 1) / t;
+        const long long per_sm = (ctas + num_sm - 1) / num_sm;              // CTAs of work on the busiest SM
+        const double conc = (double)std::min<long long>(per_sm, cap) * (t / 32); // warps resident together
+        const double eff = std::min(1.0, conc / 14.0);                      // ~14 warps/SM hide the ALU/LDS latency
+        const double cost = (double)per_sm * (t / 32) / eff + 1e-3 * (double)(256 - t) / 256.0;
+        if (cost < best_cost) { best_cost = cost; best_t = t; best_cap = cap; }
+    }
+    if (best_t == 0) { delete h; return fail(OC_ERR_INVALID, "observation row too wide for shared memory"); }
+    h->threads = best_t;
+    h->smem_bytes = smem_for(best_t);
+    h->step_grid = (int)std::min<long long>(((long long)p.E + best_t - 1) / best_t, (long long)num_sm * best_cap);
 
     cudaError_t ce;
     if ((ce = cudaMalloc(&h->state, (size_t)p.E * 64)) != cudaSuccess ||
@@ -305,7 +328,7 @@ extern "C" int oc_step(oc_env* h, const int32_t* actions, float* obs, float* rew
     int rc = dispatch(p.A, p.NOBJ, p.rowf, [&](auto a, auto nobj, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
         constexpr bool RF = decltype(rf)::value;
-        const int grid = (p.E + h->threads - 1) / h->threads;
+        const int grid = h->step_grid;
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(h->threads);
