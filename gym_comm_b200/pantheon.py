@@ -1,0 +1,149 @@
+"""Batched PantheonRL layer: the ego-centric view of the 2-player env with the partner learner
+living INSIDE `step`, re-expressed over [E] tensors.
+
+Reference semantics mirrored (pantheonrl/common/multiagentenv.py:149-243, agents.py:112-213):
+* `step(ego_action)`: the partner's action comes from `partner.get_action(partner_obs)` on the
+  observation the partner saw after the previous step; both act simultaneously
+  (`SimultaneousEnv.n_step`, :395-404); the partner then receives `update(reward, done)`.
+* the ego's reward is the env reward of this step; on `done` the reference returns the PREVIOUS
+  ego observation (:206-208) -- which SB3's DummyVecEnv turns into
+  `infos["terminal_observation"]` before resetting.  Here: `terminal_obs` holds that previous
+  observation for the envs that finished, and the returned observation is the first one of the
+  new episode (VecEnv auto-reset contract).
+* `OnPolicyAgent`: records (obs, action, value, log_prob, episode_start) at `get_action`, adds
+  the reward to the last recorded transition at `update`, and trains when its buffer is full --
+  inside the env step, exactly where the reference does it.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .ppo import PPO
+from .vec_env import OvercookedVecEnv
+
+
+class BatchedOnPolicyAgent:
+    """`OnPolicyAgent` (pantheonrl/common/agents.py:84-213) over E envs at once."""
+
+    def __init__(self, model: PPO, name: str = "partner"):
+        self.model = model
+        self.name = name
+        self._last_episode_starts = torch.ones(model.buffer.num_envs, device=model.device)
+        self._values = torch.zeros(model.buffer.num_envs, device=model.device)
+        self.num_timesteps = 0
+        self.iteration = 0
+        self.last_train_stats = None
+
+    def get_action(self, obs: torch.Tensor, record: bool = True) -> torch.Tensor:
+        buf = self.model.buffer
+        if record and buf.full:                         # train the model if the buffer is full (:127-160)
+            buf.compute_returns_and_advantage(self._values, self._last_episode_starts)
+            self.last_train_stats = self.model.train()
+            self.iteration += 1
+            buf.reset()
+        actions, values, log_probs = self.model.policy.act(obs)
+        if record:
+            buf.add(obs, actions, self._last_episode_starts, values, log_probs)
+        self.num_timesteps += obs.shape[0]
+        self._values = values
+        return actions
+
+    def update(self, reward: torch.Tensor, done: torch.Tensor) -> None:
+        self._last_episode_starts = done.to(torch.float32)
+        self.model.buffer.add_reward(reward)
+
+
+class PantheonVecEnv:
+    """Ego-centric batched env: `reset() -> ego_obs [E, F]`, `step(ego_actions [E, 2]) ->
+    (ego_obs, reward [E], done [E] u8)`; the partner acts and learns inside `step`."""
+
+    def __init__(self, env: OvercookedVecEnv, partner: Optional[BatchedOnPolicyAgent] = None, ego_ind: int = 0):
+        if env.num_agents != 2:
+            raise ValueError("the PantheonRL layer is 2-player (SimultaneousEnv, multiagentenv.py:390-393)")
+        if ego_ind != 0:
+            raise ValueError("ego_ind must be 0 (as in the reference trainer)")
+        if not env.auto_reset:
+            raise ValueError("PantheonVecEnv needs an auto-resetting OvercookedVecEnv")
+        self.env = env
+        self.partner = partner
+        self.num_envs = env.num_envs
+        self.obs_dim = env.obs_width
+        self.device = env.device
+        E, F = self.num_envs, self.obs_dim
+        self._actions = torch.zeros((E, 2, 2), dtype=torch.int32, device=self.device)
+        self._obs = torch.zeros((E, 2, F), device=self.device)
+        self._old_ego_obs = torch.zeros((E, F), device=self.device)
+        self.terminal_obs = torch.zeros((E, F), device=self.device)
+        self.ep_return = torch.zeros(E, device=self.device)
+        self.ep_length = torch.zeros(E, device=self.device)
+        # running episode statistics (device-side, read by the trainer when it logs)
+        self.finished_episodes = torch.zeros((), device=self.device)
+        self.finished_return_sum = torch.zeros((), device=self.device)
+        self.finished_length_sum = torch.zeros((), device=self.device)
+        self.finished_success = torch.zeros((), device=self.device)
+
+    def add_partner_agent(self, agent: BatchedOnPolicyAgent):
+        self.partner = agent
+
+    def reset(self) -> torch.Tensor:
+        self._obs.copy_(self.env.reset())
+        self._old_ego_obs.copy_(self._obs[:, 0])
+        self.ep_return.zero_()
+        self.ep_length.zero_()
+        return self._obs[:, 0]
+
+    def step(self, ego_actions: torch.Tensor):
+        assert self.partner is not None, "add_partner_agent first (multiagentenv.py:92-101)"
+        partner_actions = self.partner.get_action(self._obs[:, 1])           # _get_actions (:149-161)
+        self._actions[:, 0].copy_(ego_actions)
+        self._actions[:, 1].copy_(partner_actions)
+        prev_ego = self._obs[:, 0].clone()
+        obs, rew, done = self.env.step(self._actions)                        # n_step -> multi_step
+        self._obs.copy_(obs)
+        self.partner.update(rew[:, 1], done)                                 # _update_players (:163-170)
+        d = done.bool()
+        self.terminal_obs = torch.where(d[:, None], prev_ego, self.terminal_obs)   # "old ego obs" (:206-208)
+        # episode bookkeeping
+        self.ep_return += rew[:, 0]
+        self.ep_length += 1
+        T = float(self.env.arglist.max_num_timesteps)
+        self.finished_episodes += d.sum()
+        self.finished_return_sum += (self.ep_return * d).sum()
+        self.finished_length_sum += (self.ep_length * d).sum()
+        self.finished_success += (d & (self.ep_length < T)).sum()             # ended by delivery, not by the clock
+        self.ep_return = torch.where(d, torch.zeros_like(self.ep_return), self.ep_return)
+        self.ep_length = torch.where(d, torch.zeros_like(self.ep_length), self.ep_length)
+        return self._obs[:, 0], rew[:, 0], done
+
+    def pop_episode_stats(self):
+        """Host read (one sync) of the episode statistics accumulated since the last call."""
+        n = float(self.finished_episodes.item())
+        out = dict(episodes=n,
+                   ep_rew_mean=float(self.finished_return_sum.item()) / max(n, 1.0),
+                   ep_len_mean=float(self.finished_length_sum.item()) / max(n, 1.0),
+                   delivered_frac=float(self.finished_success.item()) / max(n, 1.0))
+        for t in (self.finished_episodes, self.finished_return_sum, self.finished_length_sum, self.finished_success):
+            t.zero_()
+        return out
+
+
+def collect_and_train(penv: PantheonVecEnv, ego: PPO, obs: torch.Tensor, episode_starts: torch.Tensor):
+    """One ego iteration: fill the ego buffer with n_steps of experience (the partner records and
+    trains on its own schedule inside penv.step), then one PPO update.  Mirrors
+    `collect_rollouts` + `train` of `OnPolicyAlgorithm.learn`
+    (sb3_contrib/ppo_recurrent/ppo_recurrent.py:195-312) without the per-step host syncs."""
+    buf = ego.buffer
+    buf.reset()
+    for _ in range(buf.n_steps):
+        actions, values, log_probs = ego.policy.act(obs)
+        buf.add(obs, actions, episode_starts, values, log_probs)
+        obs, rew, done = penv.step(actions.to(torch.int32))
+        buf.add_reward(rew)
+        episode_starts = done.to(torch.float32)
+    with torch.no_grad():
+        last_values = ego.policy.value(obs)
+    buf.compute_returns_and_advantage(last_values, episode_starts)
+    stats = ego.train()
+    return obs, episode_starts, stats

@@ -1,0 +1,194 @@
+"""A small batched PPO (torch) for the MultiDiscrete([4, C]) action space of the Overcooked env.
+
+The reference trains with SB3 / sb3_contrib (`trainer.py:92-121`), which is not installed here
+and is out of scope to rebuild; this module is the minimum learner needed to show the GPU env
+training end to end.  It follows SB3's PPO where that matters for
+comparability: MlpPolicy-style separate pi / vf towers (2 x 64, tanh, orthogonal init), GAE with
+episode-start masks (`RolloutBuffer.compute_returns_and_advantage`), per-minibatch advantage
+normalisation, clipped surrogate, unclipped value loss, entropy bonus, grad-norm clipping.
+Observations are the flat float32 rows the kernel writes == what `FlattenedDictExtractor`
+(gym_comm/extractors/CustomExtractor.py:119-128) would concatenate.  Everything stays on the
+env's device; nothing syncs to the host inside a rollout.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Tuple
+
+import torch
+import torch.nn as nn
+
+
+def _mlp(inp: int, hidden: Tuple[int, ...]) -> nn.Sequential:
+    layers, d = [], inp
+    for h in hidden:
+        lin = nn.Linear(d, h)
+        nn.init.orthogonal_(lin.weight, gain=math.sqrt(2))
+        nn.init.zeros_(lin.bias)
+        layers += [lin, nn.Tanh()]
+        d = h
+    return nn.Sequential(*layers)
+
+
+class ActorCritic(nn.Module):
+    """obs [.., F] -> logits over nav (4) and message (C), value."""
+
+    def __init__(self, obs_dim: int, num_nav: int, num_comm: int, hidden=(64, 64)):
+        super().__init__()
+        self.num_nav, self.num_comm = num_nav, num_comm
+        self.pi = _mlp(obs_dim, hidden)
+        self.vf = _mlp(obs_dim, hidden)
+        self.action_head = nn.Linear(hidden[-1], num_nav + num_comm)
+        self.value_head = nn.Linear(hidden[-1], 1)
+        nn.init.orthogonal_(self.action_head.weight, gain=0.01)
+        nn.init.zeros_(self.action_head.bias)
+        nn.init.orthogonal_(self.value_head.weight, gain=1.0)
+        nn.init.zeros_(self.value_head.bias)
+
+    def _dists(self, obs):
+        logits = self.action_head(self.pi(obs))
+        return (torch.distributions.Categorical(logits=logits[..., :self.num_nav]),
+                torch.distributions.Categorical(logits=logits[..., self.num_nav:]))
+
+    def value(self, obs):
+        return self.value_head(self.vf(obs)).squeeze(-1)
+
+    @torch.no_grad()
+    def act(self, obs, deterministic: bool = False):
+        """-> actions int64 [.., 2], values [..], log_probs [..]   (SB3 `policy.forward`)."""
+        dn, dc = self._dists(obs)
+        nav = dn.probs.argmax(-1) if deterministic else dn.sample()
+        com = dc.probs.argmax(-1) if deterministic else dc.sample()
+        return torch.stack([nav, com], -1), self.value(obs), dn.log_prob(nav) + dc.log_prob(com)
+
+    def evaluate(self, obs, actions):
+        """-> values, log_probs, entropy   (SB3 `policy.evaluate_actions`)."""
+        dn, dc = self._dists(obs)
+        logp = dn.log_prob(actions[..., 0]) + dc.log_prob(actions[..., 1])
+        return self.value(obs), logp, dn.entropy() + dc.entropy()
+
+
+class RolloutBuffer:
+    """[n_steps, E, ...] tensors on the device; SB3 `RolloutBuffer` semantics."""
+
+    def __init__(self, n_steps: int, num_envs: int, obs_dim: int, device, gamma=0.99, gae_lambda=0.95):
+        self.n_steps, self.num_envs, self.gamma, self.gae_lambda = n_steps, num_envs, gamma, gae_lambda
+        kw = dict(device=device)
+        self.obs = torch.zeros((n_steps, num_envs, obs_dim), **kw)
+        self.actions = torch.zeros((n_steps, num_envs, 2), dtype=torch.int64, **kw)
+        self.rewards = torch.zeros((n_steps, num_envs), **kw)
+        self.episode_starts = torch.zeros((n_steps, num_envs), **kw)
+        self.values = torch.zeros((n_steps, num_envs), **kw)
+        self.log_probs = torch.zeros((n_steps, num_envs), **kw)
+        self.advantages = torch.zeros((n_steps, num_envs), **kw)
+        self.returns = torch.zeros((n_steps, num_envs), **kw)
+        self.pos = 0
+
+    @property
+    def full(self) -> bool:
+        return self.pos >= self.n_steps
+
+    def reset(self):
+        self.pos = 0
+        self.rewards.zero_()
+
+    def add(self, obs, actions, episode_starts, values, log_probs):
+        p = self.pos
+        self.obs[p].copy_(obs)
+        self.actions[p].copy_(actions)
+        self.episode_starts[p].copy_(episode_starts)
+        self.values[p].copy_(values)
+        self.log_probs[p].copy_(log_probs)
+        self.pos += 1
+
+    def add_reward(self, reward):
+        """Reward of the most recently recorded action (OnPolicyAgent.update, agents.py:196-213)."""
+        self.rewards[self.pos - 1] += reward
+
+    def compute_returns_and_advantage(self, last_values, dones):
+        last_gae = torch.zeros_like(last_values)
+        for step in reversed(range(self.n_steps)):
+            if step == self.n_steps - 1:
+                next_non_terminal, next_values = 1.0 - dones, last_values
+            else:
+                next_non_terminal, next_values = 1.0 - self.episode_starts[step + 1], self.values[step + 1]
+            delta = self.rewards[step] + self.gamma * next_values * next_non_terminal - self.values[step]
+            last_gae = delta + self.gamma * self.gae_lambda * next_non_terminal * last_gae
+            self.advantages[step] = last_gae
+        self.returns = self.advantages + self.values
+
+
+@dataclass
+class PPOConfig:
+    """Defaults = the reference's (`trainer.py:92-112`) except n_steps, which there is per single env
+    (5000) and here is per env of a large batch."""
+    n_steps: int = 128
+    batch_size: int = 16384
+    n_epochs: int = 4
+    learning_rate: float = 3e-4
+    gamma: float = 0.99
+    gae_lambda: float = 0.95
+    clip_range: float = 0.05
+    ent_coef: float = 0.01
+    vf_coef: float = 0.5
+    max_grad_norm: float = 0.5
+
+    @staticmethod
+    def from_hyperparams(h: dict, **over):
+        """`hyperparams` block of the reference's JSON configs (n_steps, batch_size, learning_rate,
+        entrop_coef, clip_range)."""
+        c = PPOConfig()
+        c.learning_rate = float(h.get("learning_rate", c.learning_rate))
+        c.ent_coef = float(h.get("entrop_coef", c.ent_coef))
+        c.clip_range = float(h.get("clip_range", c.clip_range))
+        for k, v in over.items():
+            setattr(c, k, v)
+        return c
+
+
+class PPO:
+    def __init__(self, obs_dim: int, num_nav: int, num_comm: int, num_envs: int, device, cfg: PPOConfig = None,
+                 seed: int = 0):
+        self.cfg = cfg or PPOConfig()
+        self.device = torch.device(device)
+        gen = torch.Generator().manual_seed(seed)
+        with torch.random.fork_rng(devices=[]):
+            torch.manual_seed(int(torch.randint(0, 2 ** 31 - 1, (1,), generator=gen)))
+            self.policy = ActorCritic(obs_dim, num_nav, num_comm).to(self.device)
+        self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.learning_rate, eps=1e-5)
+        self.buffer = RolloutBuffer(self.cfg.n_steps, num_envs, obs_dim, self.device, self.cfg.gamma, self.cfg.gae_lambda)
+        self.n_updates = 0
+
+    def train(self):
+        """One PPO update over the (full) rollout buffer.  Returns a dict of float stats."""
+        c, b = self.cfg, self.buffer
+        n = b.n_steps * b.num_envs
+        obs = b.obs.reshape(n, -1)
+        actions = b.actions.reshape(n, 2)
+        old_logp, adv_all, ret = b.log_probs.reshape(n), b.advantages.reshape(n), b.returns.reshape(n)
+        bs = min(c.batch_size, n)
+        stats = dict(pg=0.0, vf=0.0, ent=0.0, clipfrac=0.0, kl=0.0, n=0)
+        for _ in range(c.n_epochs):
+            perm = torch.randperm(n, device=self.device)
+            for i in range(0, n - bs + 1, bs):
+                idx = perm[i:i + bs]
+                values, logp, ent = self.policy.evaluate(obs[idx], actions[idx])
+                adv = adv_all[idx]
+                adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+                ratio = torch.exp(logp - old_logp[idx])
+                pg = -torch.min(adv * ratio, adv * torch.clamp(ratio, 1 - c.clip_range, 1 + c.clip_range)).mean()
+                vf = torch.nn.functional.mse_loss(values, ret[idx])
+                loss = pg + c.vf_coef * vf - c.ent_coef * ent.mean()
+                self.optimizer.zero_grad(set_to_none=True)
+                loss.backward()
+                nn.utils.clip_grad_norm_(self.policy.parameters(), c.max_grad_norm)
+                self.optimizer.step()
+                with torch.no_grad():
+                    stats["pg"] += float(pg); stats["vf"] += float(vf); stats["ent"] += float(ent.mean())
+                    stats["clipfrac"] += float(((ratio - 1).abs() > c.clip_range).float().mean())
+                    stats["kl"] += float((old_logp[idx] - logp).mean())
+                    stats["n"] += 1
+        self.n_updates += 1
+        k = max(stats.pop("n"), 1)
+        return {a: v / k for a, v in stats.items()}

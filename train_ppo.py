@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""End-to-end PantheonRL-style PPO training off the GPU env.
+
+    python train_ppo.py --json-path cfg.json            # same JSON schema as the reference trainer
+    python train_ppo.py --level open-divider_tomato --envs 4096 --iters 200
+
+Ego PPO + partner PPO (the partner records and trains inside `env.step`, like PantheonRL's
+OnPolicyAgent), both on the device; the Overcooked env is `OvercookedVecEnv` (one CUDA launch per
+step, no host sync inside a rollout).  Prints one JSON line per log interval.
+"""
+import argparse
+import json
+import sys
+import time
+
+import torch
+
+from gym_comm_b200 import OvercookedVecEnv, create_arglist, namespace_from_dict
+from gym_comm_b200.pantheon import BatchedOnPolicyAgent, PantheonVecEnv, collect_and_train
+from gym_comm_b200.ppo import PPO, PPOConfig
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--json-path", default=None, help="env config JSON (reference trainer.py --json-path)")
+    ap.add_argument("--level", default="open-divider_tomato")
+    ap.add_argument("--max-num-timesteps", type=int, default=500)
+    ap.add_argument("--num-communication", type=int, default=10)
+    ap.add_argument("--envs", type=int, default=4096)
+    ap.add_argument("--n-steps", type=int, default=128)
+    ap.add_argument("--iters", type=int, default=100)
+    ap.add_argument("--batch-size", type=int, default=32768)
+    ap.add_argument("--epochs", type=int, default=4)
+    ap.add_argument("--clip-range", type=float, default=0.2)
+    ap.add_argument("--ent-coef", type=float, default=0.01)
+    ap.add_argument("--lr", type=float, default=3e-4)
+    ap.add_argument("--log-every", type=int, default=10)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--device", default="cuda:0")
+    ap.add_argument("--save", default=None, help="path to save the two policies (torch.save)")
+    args = ap.parse_args(argv)
+
+    if args.json_path:
+        ns = create_arglist(args.json_path)
+    else:
+        ns = namespace_from_dict(dict(level=args.level, num_agents=2, max_num_timesteps=args.max_num_timesteps,
+                                      communication_on=True, num_communication=args.num_communication))
+    torch.manual_seed(args.seed)
+    env = OvercookedVecEnv(ns, num_envs=args.envs, device=args.device, seed=args.seed, auto_reset=True)
+    h = getattr(ns, "hyperparams", {}) or {}
+    cfg = PPOConfig.from_hyperparams(h, n_steps=args.n_steps, batch_size=args.batch_size, n_epochs=args.epochs)
+    if "clip_range" not in h:
+        cfg.clip_range = args.clip_range
+    if "entrop_coef" not in h:
+        cfg.ent_coef = args.ent_coef
+    if "learning_rate" not in h:
+        cfg.learning_rate = args.lr
+    C = ns.num_communication
+    ego = PPO(env.obs_width, 4, C, args.envs, env.device, cfg, seed=args.seed)
+    partner = BatchedOnPolicyAgent(PPO(env.obs_width, 4, C, args.envs, env.device, cfg, seed=args.seed + 1))
+    penv = PantheonVecEnv(env, partner)
+
+    obs = penv.reset()
+    starts = torch.ones(args.envs, device=env.device)
+    t0 = time.time()
+    steps = 0
+    history = []
+    for it in range(1, args.iters + 1):
+        obs, starts, stats = collect_and_train(penv, ego, obs, starts)
+        steps += args.n_steps * args.envs
+        if it % args.log_every == 0 or it == args.iters:
+            ep = penv.pop_episode_stats()
+            dt = time.time() - t0
+            line = dict(iter=it, env_steps=steps, agent_steps_per_s=2 * steps / dt, wall_s=dt, **ep,
+                        ego_loss=stats, partner_updates=partner.iteration)
+            history.append(line)
+            print(json.dumps(line), flush=True)
+    if args.save:
+        torch.save({"ego": ego.policy.state_dict(), "partner": partner.model.policy.state_dict(),
+                    "config": vars(ns)}, args.save)
+    env.close()
+    return history
+
+
+if __name__ == "__main__":
+    sys.exit(0 if main() else 1)
