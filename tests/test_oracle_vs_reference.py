@@ -11,9 +11,25 @@ from oracle import ref_harness
 from oracle.drivers import GoalChaser
 from oracle.spec_model import BIT, SpecEnv
 
-pytestmark = pytest.mark.skipif(
-    not (ref_harness.reference_available() and ref_harness.hashseed_is_canonical()),
-    reason="needs /root/reference and PYTHONHASHSEED=0")
+pytestmark = pytest.mark.skipif(not ref_harness.reference_available(), reason="needs /root/reference")
+
+if ref_harness.reference_available() and not ref_harness.hashseed_is_canonical():
+    # the hash seed is fixed at interpreter start: re-run this module in a child with PYTHONHASHSEED=0
+    import os
+    import subprocess
+    import sys
+
+    def test_lockstep_in_child_with_canonical_hashseed():
+        env = dict(os.environ, PYTHONHASHSEED="0")
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", os.path.abspath(__file__)], env=env, cwd=root,
+                           capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+        assert "4 passed" in r.stdout, r.stdout[-500:]
+
+    CASES_ENABLED = False
+else:
+    CASES_ENABLED = True
 
 CASES = [
     ("open-divider_tomato", 250, dict(max_num_timesteps=60)),
@@ -26,6 +42,7 @@ CASES = [
 ]
 
 
+@pytest.mark.skipif(not CASES_ENABLED, reason="runs in the PYTHONHASHSEED=0 child")
 @pytest.mark.parametrize("level,steps,kw", CASES)
 def test_lockstep(level, steps, kw):
     n = kw.get("num_agents", 2)
