@@ -10,6 +10,11 @@ open-divider_tomato, 2 agents, comm on (C=10), T=500, 65,536 lock-step envs per 
 random actions, auto-reset.  N GPUs = N independent shards (weak scaling, no collective on the
 step path; torch.distributed only for the barrier and the max-over-ranks of the device time).
 
+Headline `value`: the fused synthetic rollout (`oc_rollout`: 64 steps per launch, actions drawn on
+the device by Philox -- the "synthetic random-action rollout" BASELINE.json names).  The same JSON
+line carries `step_api` (the per-step C-ABI call `oc_step`, actions read from HBM, CUDA graphs),
+`e2e` (the public VecEnv API with HOST buffers), `roofline`, `cpu_baseline`, `clocks`.
+
 Only the ``cpu_baseline`` leg and ``--impl reference`` touch ``oracle/`` (as the thing timed
 beside us, never as our result).
 """
@@ -50,6 +55,21 @@ def workload_namespace(w):
     from gym_comm_b200.arglist import namespace_from_dict
     d = {k: v for k, v in w.items() if k != "envs"}
     return namespace_from_dict(d)
+
+
+def workload_config(wname, E, mode):
+    """The `config` object both arms print (no env needed: F = 23 + S + 2C)."""
+    from gym_comm_b200 import levels_data
+    w = WORKLOADS[wname]
+    text = levels_data.LEVELS[w["level"]]
+    S = len(levels_data.SUBTASKS[tuple(text.split("\n\n")[1].split("\n"))])
+    A, C = w["num_agents"], w["num_communication"]
+    F = 23 + S + 2 * C
+    return {"workload": "%s: %s, %d envs/GPU, uniform random (nav, comm) actions, auto-reset, obs f32 [E,%d,%d]" %
+                        (wname, w["level"], E, A, F),
+            "mode": mode, "envs_per_gpu": E, "num_agents": A, "obs_width": F,
+            "max_num_timesteps": w["max_num_timesteps"], "num_communication": C,
+            "fow_radius": w["fow_radius"]}, A, F
 
 
 def bytes_per_env_step(A, F):
@@ -158,7 +178,7 @@ def main():
                 "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32+f64", "data": "synthetic",
-                "config": {"workload": "%s: %s" % (args.workload, json.dumps({k: v for k, v in w.items()}, sort_keys=True))},
+                "config": workload_config(args.workload, args.envs or w["envs"], args.mode)[0],
                 "cpu_baseline": res,
                 "e2e": {"value": res["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "wall_s": time.time() - t0}
@@ -385,12 +405,10 @@ def main():
             "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": primary["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32+f64", "data": "synthetic",
-            "config": {"workload": "%s: %s, %d envs/GPU, uniform random (nav, comm) actions, auto-reset, obs f32 [E,%d,%d]" %
-                                   (args.workload, ns.level, E, A, F),
-                       "mode": args.mode, "mode_desc": desc[args.mode], "cuda_graphs": primary["cuda_graphs"],
-                       "envs_per_gpu": E, "num_agents": A, "obs_width": F, "rollout_ring_slots": R,
-                       "l2": "inputs/outputs larger than L2: the obs ring (%d x %.1f MB) is rewritten round-robin and the action pool is %.1f GB; only the %.1f MB packed state stays L2-resident (by design)"
-                             % (R, E * A * F * 4 / 1e6, P * E * A * 8 / 1e9, E * 64 / 1e6)},
+            "config": dict(workload_config(args.workload, E, args.mode)[0],
+                           mode_desc=desc[args.mode], cuda_graphs=primary["cuda_graphs"], rollout_ring_slots=R,
+                           l2="inputs/outputs larger than L2: the obs ring (%d x %.1f MB) is rewritten round-robin and the action pool is %.1f GB; only the %.1f MB packed state stays L2-resident (by design)"
+                              % (R, E * A * F * 4 / 1e6, P * E * A * 8 / 1e9, E * 64 / 1e6)),
             "roofline": primary["roofline"], "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": primary["gpu_launches"], "clocks": primary["clocks"],
         }
