@@ -218,6 +218,34 @@ class OvercookedVecEnv:
             comm0=w[:, 14] & 0xFFFF, comm1=w[:, 14] >> 16)
         return out
 
+    def render(self, index: int = 0, state=None) -> str:
+        """ASCII picture of env `index` in the reference's `str(OvercookedEnvironment)` format
+        (overcooked_environment.py:62-65, world.py:36-46, core.py:277-279): one character cell + a
+        space per tile; objects print as `1t` (fresh) / `2t` (chopped) / `p`, merged ones joined
+        by '-' in name order; agents print their index and hide what is under them."""
+        d = self.decode_state(state)
+        lv = self.level
+        tile_rep = {0: " ", 1: "-", 2: "/", 3: "*"}
+        grid = [[tile_rep[int(lv.tiles[lv.cell(x, y)])] for x in range(lv.width)] for y in range(lv.height)]
+        names = [(2, "l"), (4, "o"), (8, "p"), (1, "t")]                 # alphabetical: Lettuce Onion Plate Tomato
+        ranks = int(d["ranks"][index])
+        objs = []
+        for s in range(6):
+            c = int(d["obj_contents"][index, s])
+            if c:
+                ch = int(d["obj_chopped"][index, s])
+                txt = "-".join(("p" if b == 8 else "%d%s" % (2 if ch & b else 1, r)) for b, r in names if c & b)
+                objs.append((((ranks >> (4 * c)) & 15, int(d["obj_stamp"][index, s])), int(d["obj_cell"][index, s]), txt, c))
+        objs.sort(key=lambda o: o[0])                                    # world.objects iteration order
+        for _, cell, txt, c in objs:
+            grid[cell // lv.width][cell % lv.width] = txt
+        for _, cell, txt, c in objs:                                     # Tomato objects are drawn again last (world.py:44-45)
+            if c == 1:
+                grid[cell // lv.width][cell % lv.width] = txt
+        for k in range(self.num_agents):
+            grid[int(d["agent_y"][index, k])][int(d["agent_x"][index, k])] = str(k)
+        return "\n".join("".join(c + " " for c in row) for row in grid)
+
     def close(self):
         if not self._closed and self._handle:
             self.lib.destroy(self._handle)
