@@ -535,12 +535,22 @@ template <bool ROWF>
 __device__ __forceinline__ void warp_expand_rows(const OcParams& p, const uint8_t* __restrict__ wrows,
                                                  float* __restrict__ out /* warp's first env row */,
                                                  int nvalid, int lane) {
-    if (ROWF) {                                     // float rows, contiguous: plain copy
-        const int total = nvalid * (p.row_bytes >> 2);
+    if (ROWF) {                                     // float rows: plain 16-byte copy
+        const int r4 = p.row_bytes >> 2;
+        const int total = nvalid * r4;
         const float4* i4 = reinterpret_cast<const float4*>(wrows);
         float4* o4 = reinterpret_cast<float4*>(out);
+        if (p.row_stride == p.row_bytes * 4) {      // contiguous rows
 #pragma unroll 4
-        for (int idx = lane; idx < total; idx += 32) __stcs(o4 + idx, i4[idx]);   // streaming: written once, read later by the learner
+            for (int idx = lane; idx < total; idx += 32) __stcs(o4 + idx, i4[idx]);   // streaming: written once, read later by the learner
+        } else {                                    // padded rows: env = idx / r4 by magic multiply
+            const int s4 = p.row_stride >> 4;
+#pragma unroll 4
+            for (int idx = lane; idx < total; idx += 32) {
+                const int env = (int)__umulhi((uint32_t)idx, p.r4_magic);
+                __stcs(o4 + idx, i4[env * s4 + (idx - env * r4)]);
+            }
+        }
     } else if ((p.row_bytes & 3) == 0) {
         const int r4 = p.row_bytes >> 2;            // float4 per env row
         const int total = nvalid * r4;

@@ -109,7 +109,10 @@ static inline int compile_config(const oc_config* c, HostImage& h, std::string& 
     // float rows when a warp's 32 rows stay small (<= 24 KB) and rows are 16-byte multiples
     p.rowf = ((p.row_bytes & 3) == 0 && 32 * p.row_bytes * 4 <= 24 * 1024) ? 1 : 0;
     if (const char* f = getenv("OC_ROW_FORMAT")) p.rowf = (f[0] == 'f' && (p.row_bytes & 3) == 0) ? 1 : 0;
-    if (p.rowf) p.row_stride = p.row_bytes * 4;
+    // float rows stay 16-byte aligned, so the best the per-thread scatter can do is a stride of
+    // 4 (mod 8) words (8 distinct banks, 4-way conflict); a multiple of 8 words would put all 32 lanes
+    // on 1-4 banks (cfg4: 96 floats -> 32-way), so such rows get 4 floats of padding
+    if (p.rowf) p.row_stride = (p.row_bytes + ((p.row_bytes & 7) == 0 ? 4 : 0)) * 4;
     p.r4_magic = (p.row_bytes >= 4) ? (uint32_t)((1ull << 32) / (uint64_t)(p.row_bytes >> 2)) + 1u : 0u;
     p.rf_magic = (uint32_t)((1ull << 32) / (uint64_t)p.row_bytes) + 1u;
     for (int k = 0; k < OC_MAX_AGENTS; ++k) {
