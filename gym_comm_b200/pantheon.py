@@ -59,7 +59,8 @@ class PantheonVecEnv:
     """Ego-centric batched env: `reset() -> ego_obs [E, F]`, `step(ego_actions [E, 2]) ->
     (ego_obs, reward [E], done [E] u8)`; the partner acts and learns inside `step`."""
 
-    def __init__(self, env: OvercookedVecEnv, partner: Optional[BatchedOnPolicyAgent] = None, ego_ind: int = 0):
+    def __init__(self, env: OvercookedVecEnv, partner: Optional[BatchedOnPolicyAgent] = None, ego_ind: int = 0,
+                 reward_scale: float = 1.0):
         if env.num_agents != 2:
             raise ValueError("the PantheonRL layer is 2-player (SimultaneousEnv, multiagentenv.py:390-393)")
         if ego_ind != 0:
@@ -68,6 +69,7 @@ class PantheonVecEnv:
             raise ValueError("PantheonVecEnv needs an auto-resetting OvercookedVecEnv")
         self.env = env
         self.partner = partner
+        self.reward_scale = float(reward_scale)      # learner-side scaling; episode statistics stay in env units
         self.num_envs = env.num_envs
         self.obs_dim = env.obs_width
         self.device = env.device
@@ -102,7 +104,7 @@ class PantheonVecEnv:
         prev_ego = self._obs[:, 0].clone()
         obs, rew, done = self.env.step(self._actions)                        # n_step -> multi_step
         self._obs.copy_(obs)
-        self.partner.update(rew[:, 1], done)                                 # _update_players (:163-170)
+        self.partner.update(rew[:, 1] * self.reward_scale, done)             # _update_players (:163-170)
         d = done.bool()
         self.terminal_obs = torch.where(d[:, None], prev_ego, self.terminal_obs)   # "old ego obs" (:206-208)
         # episode bookkeeping
@@ -115,7 +117,7 @@ class PantheonVecEnv:
         self.finished_success += (d & (self.ep_length < T)).sum()             # ended by delivery, not by the clock
         self.ep_return = torch.where(d, torch.zeros_like(self.ep_return), self.ep_return)
         self.ep_length = torch.where(d, torch.zeros_like(self.ep_length), self.ep_length)
-        return self._obs[:, 0], rew[:, 0], done
+        return self._obs[:, 0], rew[:, 0] * self.reward_scale, done
 
     def pop_episode_stats(self):
         """Host read (one sync) of the episode statistics accumulated since the last call."""

@@ -29,11 +29,12 @@ def main(argv=None):
     ap.add_argument("--envs", type=int, default=4096)
     ap.add_argument("--n-steps", type=int, default=128)
     ap.add_argument("--iters", type=int, default=100)
-    ap.add_argument("--batch-size", type=int, default=32768)
+    ap.add_argument("--batch-size", type=int, default=4096)
     ap.add_argument("--epochs", type=int, default=4)
     ap.add_argument("--clip-range", type=float, default=0.2)
     ap.add_argument("--ent-coef", type=float, default=0.01)
-    ap.add_argument("--lr", type=float, default=3e-4)
+    ap.add_argument("--lr", type=float, default=1e-3)
+    ap.add_argument("--reward-scale", type=float, default=0.1, help="learner-side reward scaling (1.0 = the reference's raw reward)")
     ap.add_argument("--log-every", type=int, default=10)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--device", default="cuda:0")
@@ -58,7 +59,7 @@ def main(argv=None):
     C = ns.num_communication
     ego = PPO(env.obs_width, 4, C, args.envs, env.device, cfg, seed=args.seed)
     partner = BatchedOnPolicyAgent(PPO(env.obs_width, 4, C, args.envs, env.device, cfg, seed=args.seed + 1))
-    penv = PantheonVecEnv(env, partner)
+    penv = PantheonVecEnv(env, partner, reward_scale=args.reward_scale)
 
     obs = penv.reset()
     starts = torch.ones(args.envs, device=env.device)
