@@ -25,6 +25,7 @@ import sys
 import numpy as np
 
 from .drivers import GoalChaser
+from .level_fuzz import random_level
 from .ref_harness import LiveReference, hashseed_is_canonical, make_namespace
 from .spec_model import BIT, SpecEnv
 
@@ -71,6 +72,15 @@ SCENARIOS = [
     ("wide_big_blind_ego", "random-open-divider_salad_small_wide_big", 400,
      dict(max_num_timesteps=120, ego_config=dict(BLIND=True))),
     ("custom_level", "custom-two-deliveries", 700, dict(max_num_timesteps=200, level_text=CUSTOM_LEVEL)),
+    # rows whose width is not a multiple of 4 floats (3 observers x 49 features)
+    ("open_tl_3a_c5", "open-divider_tl", 500, dict(num_agents=3, max_num_timesteps=150, num_communication=5, fow_radius=3)),
+    # random kitchens (oracle/level_fuzz.py): geometry the shipped levels never exercise
+    ("fuzz_kitchen_a", "fuzz-a", 400, dict(max_num_timesteps=90, num_communication=4, fow_radius=1,
+                                            level_text=random_level(1003))),
+    ("fuzz_kitchen_b", "fuzz-b", 400, dict(num_agents=3, max_num_timesteps=80, num_communication=6, fow_radius=2,
+                                            level_text=random_level(1008, 3))),
+    ("fuzz_kitchen_c", "fuzz-c", 400, dict(max_num_timesteps=100, num_communication=7, fow_radius=3, ego_led=True,
+                                            level_text=random_level(1011))),
 ]
 
 A9_PARTNER = [3, 1, 0, 2, 2, 2, 2, 2, 0, 0, 0, 3, 3, 3, 3, 3, 1, 1, 2, 2, 2, 2, 2]
