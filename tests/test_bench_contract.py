@@ -1,0 +1,27 @@
+"""bench.py's CPU arm (`--impl reference`) runs without a GPU and prints the contract's JSON line."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_contract_line():
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1",
+                                   "--steps", "5", "--warmup", "3", "--cpu-seconds", "2"], cwd=ROOT, timeout=300).decode()
+    line = json.loads(out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "agent-steps/s" and line["higher_is_better"] is True
+    assert line["metric"] == "env agent-steps/sec incl. obs" and line["value"] > 0
+    assert line["e2e"] == {"value": line["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
+    assert cb["c_port"]["value"] > cb["value"]          # the C port is reported beside the Python port
+    assert line["config"]["workload"].startswith("cfg2: open-divider_tomato, 65536 envs/GPU")
+
+
+def test_nonzero_rank_of_reference_arm_exits_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                                  cwd=ROOT, env=env, timeout=120).decode()
+    assert out.strip() == ""
