@@ -35,7 +35,6 @@ struct Tables {
     const uint8_t*  counters; // [ncounters] Counter cells, reading order            overcooked_environment.py:164
     const uint8_t*  pd;       // [ncell*ncell] World.get_path_distance_between       world.py:114-131
     const uint8_t*  pdm;      // [ncell*ncell] pd + manhattan distance               overcooked_environment.py:380
-    const uint16_t* remq;     // [nrem] float4 indices of an env row outside the zero runs (wide byte rows)
 };
 
 __device__ __forceinline__ Tables make_tables(const OcParams& p, const uint8_t* smem) {
@@ -49,7 +48,6 @@ __device__ __forceinline__ Tables make_tables(const OcParams& p, const uint8_t* 
     t.counters = smem + p.o_counters;
     t.pd = smem + p.o_pd;
     t.pdm = smem + p.o_pdm;
-    t.remq = reinterpret_cast<const uint16_t*>(smem + p.o_remq);
     return t;
 }
 
@@ -534,7 +532,7 @@ __device__ __forceinline__ float biased_byte_to_float(uint32_t w, int k) {
 // warp-cooperative expansion: the warp's 32 rows in shared memory -> float32 rows in global
 // memory, consecutive lanes writing consecutive 16-byte (or 4-byte) pieces of one contiguous region.
 template <bool ROWF>
-__device__ __forceinline__ void warp_expand_rows(const OcParams& p, const Tables& tb, const uint8_t* __restrict__ wrows,
+__device__ __forceinline__ void warp_expand_rows(const OcParams& p, const uint8_t* __restrict__ wrows,
                                                  float* __restrict__ out /* warp's first env row */,
                                                  int nvalid, int lane) {
     if (ROWF) {                                     // float rows: plain 16-byte copy
@@ -552,30 +550,6 @@ __device__ __forceinline__ void warp_expand_rows(const OcParams& p, const Tables
                 const int env = (int)__umulhi((uint32_t)idx, p.r4_magic);
                 __stcs(o4 + idx, i4[env * s4 + (idx - env * r4)]);
             }
-        }
-    } else if (p.nzr > 0) {                         // wide byte rows: zero runs + the rest through the bytes
-        const int r4 = p.row_bytes >> 2;
-        float4* o4 = reinterpret_cast<float4*>(out);
-        const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        for (int r = 0; r < p.nzr; ++r) {
-            if (lane < (int)p.zr_w[r]) {
-                float4* dst = o4 + p.zr_q0[r] + lane;
-#pragma unroll 4
-                for (int e = 0; e < nvalid; ++e) __stcs(dst + (size_t)e * r4, z);
-            }
-        }
-        const int total = nvalid * p.nrem, s4 = p.row_stride >> 2;
-#pragma unroll 2
-        for (int idx = lane; idx < total; idx += 32) {
-            const int env = (int)__umulhi((uint32_t)idx, p.nrem_magic);
-            const int q = tb.remq[idx - env * p.nrem];
-            const uint32_t w = reinterpret_cast<const uint32_t*>(wrows)[env * s4 + q];
-            float4 v;
-            v.x = biased_byte_to_float(w, 0);
-            v.y = biased_byte_to_float(w, 1);
-            v.z = biased_byte_to_float(w, 2);
-            v.w = biased_byte_to_float(w, 3);
-            __stcs(o4 + (size_t)env * r4 + q, v);
         }
     } else if ((p.row_bytes & 3) == 0) {
         const int r4 = p.row_bytes >> 2;            // float4 per env row
@@ -611,17 +585,9 @@ __device__ __forceinline__ void warp_expand_rows(const OcParams& p, const Tables
 // byte rows only: after the expansion (and a __syncwarp) each thread stores the timestep feature
 // of its own env rows, timestep = float32(t / max_num_timesteps)  (overcooked_env.py:146)
 template <int A>
-__device__ __forceinline__ void store_timesteps(const OcParams& p, float* __restrict__ env_row, float ts, uint32_t comm) {
+__device__ __forceinline__ void store_timesteps(const OcParams& p, float* __restrict__ env_row, float ts) {
 #pragma unroll
     for (int k = 0; k < A; ++k) env_row[k * p.F + p.off_ts] = ts;
-    if (p.nzr > 0) {                                // zero runs wiped the message one-hots: set the ones
-        const uint32_t c0 = comm & 0xFFFFu, c1 = comm >> 16;
-#pragma unroll
-        for (int k = 0; k < A; ++k) {
-            if (c0 != OCK_COMM_NONE) env_row[k * p.F + p.off_a1comm + c0] = 1.0f;
-            if (c1 != OCK_COMM_NONE) env_row[k * p.F + p.off_a2comm + c1] = 1.0f;
-        }
-    }
 }
 
 // a single thread expands its own row (rare path: terminal observations)

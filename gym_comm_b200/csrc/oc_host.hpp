@@ -227,33 +227,6 @@ static inline int compile_config(const oc_config* c, HostImage& h, std::string& 
     p.o_counters = (int)off; off += align_up(std::max<size_t>(counters.size(), 1), 16);
     p.o_pd = (int)off; off += align_up((size_t)n * n, 16);
     p.o_pdm = (int)off; off += align_up((size_t)n * n, 16);
-    // zero runs for wide byte rows
-    std::vector<uint16_t> remq;
-    p.nzr = 0; p.nrem = 0; p.nrem_magic = 0;
-    if (!p.rowf && (p.row_bytes & 3) == 0 && C >= 16 && !getenv("OC_NO_ZERO_RUNS")) {
-        const int r4 = p.row_bytes >> 2;
-        std::vector<uint8_t> inside(r4, 0);
-        bool ok = true;
-        for (int k = 0; k < A && ok; ++k)
-            for (int reg = 0; reg < 2 && ok; ++reg) {
-                const int s = k * p.F + (reg == 0 ? p.off_a1comm : p.off_a2comm), e = s + C;
-                int q0 = (s + 3) / 4, q1 = e / 4;
-                while (q0 < q1) {
-                    const int w = std::min(32, q1 - q0);
-                    if (p.nzr >= OCK_MAX_ZERO_RUNS) { ok = false; break; }
-                    p.zr_q0[p.nzr] = (uint16_t)q0; p.zr_w[p.nzr] = (uint16_t)w; ++p.nzr;
-                    for (int q = q0; q < q0 + w; ++q) inside[q] = 1;
-                    q0 += w;
-                }
-            }
-        if (!ok) p.nzr = 0;
-        else {
-            for (int q = 0; q < r4; ++q) if (!inside[q]) remq.push_back((uint16_t)q);
-            p.nrem = (int)remq.size();
-            p.nrem_magic = p.nrem ? (uint32_t)((1ull << 32) / (uint64_t)p.nrem) + 1u : 0u;
-        }
-    }
-    p.o_remq = (int)off; off += align_up(std::max<size_t>(remq.size(), 1) * 2, 16);
     p.blob_bytes = (int)off;
     std::vector<uint8_t>& blob = h.blob; blob.assign(off, 0);
     memcpy(blob.data() + p.o_q, q.data(), q.size() * 8);
@@ -265,7 +238,6 @@ static inline int compile_config(const oc_config* c, HostImage& h, std::string& 
     if (!counters.empty()) memcpy(blob.data() + p.o_counters, counters.data(), counters.size());
     memcpy(blob.data() + p.o_pd, pd.data(), pd.size());
     memcpy(blob.data() + p.o_pdm, pdm.data(), pdm.size());
-    if (!remq.empty()) memcpy(blob.data() + p.o_remq, remq.data(), remq.size() * 2);
     return OC_OK;
 #undef OC_BAD
 }

@@ -49,7 +49,6 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
         const int env = base + threadIdx.x;
         const bool valid = env < p.E;
         float ts = 0.0f;
-        uint32_t commw = 0;
         if (valid) {
             Env<A, NOBJ> e;
             int nav[A], comm[A];
@@ -60,14 +59,13 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
             ts = step_one_env<A, NOBJ, ROWF>(e, p, tb, nav, comm[0], comm[1], (uint32_t)env, myrow,
                                              rew32, rew64, done_out, term_obs, flags);
             store_env<A, NOBJ>(e, state, p.E, env);
-            commw = e.comm;
         }
         __syncwarp();
         const int env0 = base + warp * 32;
         const int nvalid = min(32, p.E - env0);
-        if (nvalid > 0) warp_expand_rows<ROWF>(p, tb, wrows, obs + (size_t)env0 * p.row_bytes, nvalid, lane);
+        if (nvalid > 0) warp_expand_rows<ROWF>(p, wrows, obs + (size_t)env0 * p.row_bytes, nvalid, lane);
         __syncwarp();                               // order the float4 stores before the timestep patch
-        if (!ROWF && valid) store_timesteps<A>(p, obs + (size_t)env * p.row_bytes, ts, commw);
+        if (!ROWF && valid) store_timesteps<A>(p, obs + (size_t)env * p.row_bytes, ts);
         if (base + gridDim.x * blockDim.x < p.E) { warp_clear_rows<ROWF>(wrows, 32 * p.row_stride, lane); __syncwarp(); }
     }
 }
@@ -103,9 +101,9 @@ oc_rollout_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
         if (obs != nullptr) {
             float* step_obs = obs + (size_t)s * step_floats;
             __syncwarp();
-            if (nvalid > 0) warp_expand_rows<ROWF>(p, tb, wrows, step_obs + (size_t)env0 * p.row_bytes, nvalid, lane);
+            if (nvalid > 0) warp_expand_rows<ROWF>(p, wrows, step_obs + (size_t)env0 * p.row_bytes, nvalid, lane);
             __syncwarp();
-            if (!ROWF && valid) store_timesteps<A>(p, step_obs + (size_t)env * p.row_bytes, ts, e.comm);
+            if (!ROWF && valid) store_timesteps<A>(p, step_obs + (size_t)env * p.row_bytes, ts);
         }
     }
     if (valid) store_env<A, NOBJ>(e, state, p.E, env);
@@ -137,9 +135,9 @@ oc_reset_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, c
     const int env0 = blockIdx.x * blockDim.x + warp * 32;
     const int nvalid = min(32, p.E - env0);
     if (obs != nullptr) {
-        if (nvalid > 0) warp_expand_rows<ROWF>(p, tb, wrows, obs + (size_t)env0 * p.row_bytes, nvalid, lane);
+        if (nvalid > 0) warp_expand_rows<ROWF>(p, wrows, obs + (size_t)env0 * p.row_bytes, nvalid, lane);
         __syncwarp();
-        if (!ROWF && valid) store_timesteps<A>(p, obs + (size_t)env * p.row_bytes, ts, e.comm);
+        if (!ROWF && valid) store_timesteps<A>(p, obs + (size_t)env * p.row_bytes, ts);
     }
 }
 

@@ -8,7 +8,6 @@
 #define OCK_MAX_OBJECTS 6
 #define OCK_MAX_PAIRS 6
 #define OCK_MAX_DELIVER 4
-#define OCK_MAX_ZERO_RUNS 32
 
 // ---- packed per-env state: 16 x u32, stored as 4 SoA planes of uint4 (plane p, env e at
 //      state[p * E + e]) so a warp's 32 envs load/store 512 contiguous bytes per plane.
@@ -56,12 +55,6 @@ struct OcParams {
     int32_t  npairs;                        // C(num_items, 2) item pairs of calculate_reward_shaping
     uint32_t item_foods;                    // Food bits among the shaping items (items[0] is always Plate)
     uint32_t r4_magic, rf_magic;            // floor(2^32 / d) + 1 for d = row_bytes / 4 and row_bytes
-    // wide byte rows (large C): float4 runs of an env row that lie entirely inside a message
-    // one-hot region are stored as zeros without touching shared memory; the rest goes through
-    // the byte rows; the ones of the one-hots are patched by the owning thread afterwards
-    int32_t  nzr;                           // number of zero runs (0 = feature off), each <= 32 float4 wide
-    uint16_t zr_q0[OCK_MAX_ZERO_RUNS], zr_w[OCK_MAX_ZERO_RUNS];
-    int32_t  nrem; uint32_t nrem_magic;     // float4s of an env row outside the runs (indices in the blob at o_remq)
     // observation layout (float offsets inside one observer row)
     int32_t off_a1comm, off_a1loc, off_a2comm, off_a2loc, off_hold, off_completed,
             off_hidden, off_encx, off_ency, off_state, off_ts;
@@ -69,6 +62,6 @@ struct OcParams {
     // table blob (device pointer) and the byte offsets of its sections; copied to smem per CTA
     const uint8_t* blob;
     int32_t blob_bytes;        // multiple of 16
-    int32_t o_q, o_tmlut, o_xyf, o_mvt, o_xy16, o_dmin, o_counters, o_pd, o_pdm, o_remq;
+    int32_t o_q, o_tmlut, o_xyf, o_mvt, o_xy16, o_dmin, o_counters, o_pd, o_pdm;
     const float* ts_table;     // [T+1] float32(t / T)   (overcooked_env.py:146)
 };

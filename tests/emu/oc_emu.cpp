@@ -48,10 +48,10 @@ static void for_each_warp(emu_env* h, float* obs, Body&& body) {
         for (int lane = 0; lane < nvalid; ++lane) wts[lane] = body(tb, env0 + lane, rows.data() + (size_t)lane * p.row_stride);
         if (obs) {
             for (int lane = 0; lane < 32; ++lane)
-                warp_expand_rows<ROWF>(p, tb, rows.data(), obs + (size_t)env0 * p.row_bytes, nvalid, lane);
+                warp_expand_rows<ROWF>(p, rows.data(), obs + (size_t)env0 * p.row_bytes, nvalid, lane);
             if (!ROWF)
                 for (int lane = 0; lane < nvalid; ++lane)
-                    store_timesteps<A>(p, obs + (size_t)(env0 + lane) * p.row_bytes, wts[lane], h->state[(size_t)3 * p.E + env0 + lane].z);
+                    store_timesteps<A>(p, obs + (size_t)(env0 + lane) * p.row_bytes, wts[lane]);
         }
     }
 }
