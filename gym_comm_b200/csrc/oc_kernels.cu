@@ -230,7 +230,10 @@ extern "C" int oc_create(const oc_config* c, oc_env** out) {
     // (limited by shared memory: table blob + 32 rows per warp, by 2048 threads and 32 CTAs per
     // SM) covers the envs with the smallest makespan, preferring fewer table copies on ties.
     cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    {
+        cudaError_t cep = cudaGetDeviceProperties(&prop, dev);
+        if (cep != cudaSuccess) { delete h; return fail(OC_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(cep)); }
+    }
     const int num_sm = prop.multiProcessorCount;
     const size_t smem_sm = prop.sharedMemPerMultiprocessor, smem_cta_max = prop.sharedMemPerBlockOptin;
     auto smem_for = [&](int threads) { return (size_t)p.blob_bytes + (size_t)(threads / 32) * (32 * (size_t)p.row_stride); };
