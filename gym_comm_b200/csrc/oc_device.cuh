@@ -529,6 +529,29 @@ __device__ __forceinline__ float biased_byte_to_float(uint32_t w, int k) {
     return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + (uint32_t)k)) - 8388736.0f;
 }
 
+#ifndef OCK_HOST_EMU
+// TMA bulk store (cp.async.bulk, SASS UBLKCP): the copy engine streams a contiguous shared-memory
+// region to global memory while the warp goes on with the next step; no LDS/STG instructions.
+__device__ __forceinline__ void tma_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(s), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+#endif
+// rows may be overwritten again once the copy engine has READ them
+__device__ __forceinline__ void rows_wait_read(const OcParams& p) {
+#ifndef OCK_HOST_EMU
+    if (p.use_tma) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
+    __syncwarp();
+}
+// before the kernel exits: all bulk stores complete
+__device__ __forceinline__ void rows_wait_done(const OcParams& p) {
+#ifndef OCK_HOST_EMU
+    if (p.use_tma) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
+}
+
 // warp-cooperative expansion: the warp's 32 rows in shared memory -> float32 rows in global
 // memory, consecutive lanes writing consecutive 16-byte (or 4-byte) pieces of one contiguous region.
 template <bool ROWF>
@@ -540,6 +563,16 @@ __device__ __forceinline__ void warp_expand_rows(const OcParams& p, const uint8_
         const int total = nvalid * r4;
         const float4* i4 = reinterpret_cast<const float4*>(wrows);
         float4* o4 = reinterpret_cast<float4*>(out);
+#ifndef OCK_HOST_EMU
+        if (p.use_tma) {
+            // generic-proxy writes of every lane -> visible to the async proxy, then ONE bulk store
+            // of the warp's 32 contiguous rows (11.8 KB for cfg2) by one lane
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) tma_store(out, wrows, (uint32_t)(total * 16));
+            return;
+        }
+#endif
         if (p.row_stride == p.row_bytes * 4) {      // contiguous rows
 #pragma unroll 4
             for (int idx = lane; idx < total; idx += 32) __stcs(o4 + idx, i4[idx]);   // streaming: written once, read later by the learner

@@ -66,8 +66,13 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
         if (nvalid > 0) warp_expand_rows<ROWF>(p, wrows, obs + (size_t)env0 * p.row_bytes, nvalid, lane);
         __syncwarp();                               // order the float4 stores before the timestep patch
         if (!ROWF && valid) store_timesteps<A>(p, obs + (size_t)env * p.row_bytes, ts);
-        if (base + gridDim.x * blockDim.x < p.E) { warp_clear_rows<ROWF>(wrows, 32 * p.row_stride, lane); __syncwarp(); }
+        if (base + gridDim.x * blockDim.x < p.E) {
+            rows_wait_read(p);
+            warp_clear_rows<ROWF>(wrows, 32 * p.row_stride, lane);
+            __syncwarp();
+        }
     }
+    rows_wait_done(p);
 }
 
 // n_steps steps per launch, state in registers, Philox actions (SURVEY section 8d synthetic inputs)
@@ -92,7 +97,11 @@ oc_rollout_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
     const size_t step_floats = (size_t)p.E * p.row_bytes;
 
     for (int s = 0; s < n_steps; ++s) {
-        if (obs != nullptr) { warp_clear_rows<ROWF>(wrows, 32 * p.row_stride, lane); __syncwarp(); }
+        if (obs != nullptr) {
+            if (s > 0) rows_wait_read(p);
+            warp_clear_rows<ROWF>(wrows, 32 * p.row_stride, lane);
+            __syncwarp();
+        }
         float ts = 0.0f;
         if (valid) {
             ts = rollout_one_env<A, NOBJ, ROWF>(e, p, tb, (uint32_t)env, (uint32_t)s, step0, myrow,
@@ -107,6 +116,7 @@ oc_rollout_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
         }
     }
     if (valid) store_env<A, NOBJ>(e, state, p.E, env);
+    rows_wait_done(p);
 }
 
 // reset (masked) + observation of every env
@@ -139,6 +149,7 @@ oc_reset_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, c
         __syncwarp();
         if (!ROWF && valid) store_timesteps<A>(p, obs + (size_t)env * p.row_bytes, ts);
     }
+    rows_wait_done(p);
 }
 
 // packed state <-> [E, 16] u32 rows

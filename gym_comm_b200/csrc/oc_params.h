@@ -32,6 +32,7 @@ struct OcParams {
     int32_t T, C, S, F;
     int32_t fow, M;
     int32_t row_bytes;        // A * F = features (floats) of one env row in global memory
+    int32_t use_tma;          // float rows leave shared memory through cp.async.bulk (TMA) instead of LDS/STG
     int32_t rowf;             // 1: float32 rows in shared memory (row_stride = 4 * row_bytes), 0: biased-byte rows
     int32_t row_stride;       // shared-memory bytes per env row.  Byte rows: == row_bytes when that is an odd
                               // number of words (contiguous AND conflict-free), else padded to one

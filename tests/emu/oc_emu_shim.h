@@ -35,5 +35,6 @@ static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline void __stcs(float4* p, float4 v) { *p = v; }
+static inline void __syncwarp() {}
 struct EmuDim { int x; };
 static thread_local EmuDim threadIdx{0}, blockDim{1};
