@@ -149,3 +149,74 @@ def collect_and_train(penv: PantheonVecEnv, ego: PPO, obs: torch.Tensor, episode
     buf.compute_returns_and_advantage(last_values, episode_starts)
     stats = ego.train()
     return obs, episode_starts, stats
+
+
+class SB3VecEnvAdapter:
+    """Stable-Baselines3 `VecEnv` duck type over `PantheonVecEnv` (interface 2):
+    numpy in / numpy out, `step_async` / `step_wait`, auto-reset with
+    `infos[i]["terminal_observation"]`, `get_attr` / `set_attr` / `env_method` / `env_is_wrapped` /
+    `seed` / `close`.  This is what replaces the `DummyVecEnv` of ONE env that
+    `collect_rollouts` steps (sb3_contrib/ppo_recurrent/ppo_recurrent.py:233-252) for a learner that
+    keeps its rollout buffers on the host; a learner living on the GPU should use
+    `PantheonVecEnv` / `OvercookedVecEnv` directly and never leave the device.
+    SB3 itself is not imported (it is not installed in this image)."""
+
+    def __init__(self, penv: PantheonVecEnv, dict_obs: bool = False):
+        self.penv = penv
+        self.num_envs = penv.num_envs
+        self.observation_space = penv.env.observation_space
+        self.action_space = penv.env.action_space
+        self.dict_obs = dict_obs
+        self._actions = None
+        self.render_mode = None
+
+    def _obs(self, t: torch.Tensor):
+        a = t.cpu().numpy()
+        if not self.dict_obs:
+            return a
+        return {k: a[:, s] for k, s in self.penv.env.obs_layout.items()}
+
+    def reset(self):
+        return self._obs(self.penv.reset())
+
+    def step_async(self, actions):
+        self._actions = torch.as_tensor(actions, dtype=torch.int32, device=self.penv.device).reshape(self.num_envs, 2)
+
+    def step_wait(self):
+        obs, rew, done = self.penv.step(self._actions)
+        d = done.bool().cpu().numpy()
+        infos = [{} for _ in range(self.num_envs)]
+        if d.any():
+            term = self.penv.terminal_obs.cpu().numpy()
+            for i in d.nonzero()[0]:
+                infos[i]["terminal_observation"] = (term[i] if not self.dict_obs else
+                                                    {k: term[i, s] for k, s in self.penv.env.obs_layout.items()})
+                infos[i]["TimeLimit.truncated"] = False
+        return self._obs(obs), rew.cpu().numpy().astype("float32"), d, infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def close(self):
+        self.penv.env.close()
+
+    def seed(self, seed=None):
+        return [None] * self.num_envs          # placements / actions are seeded at construction (oc_config.seed)
+
+    def get_attr(self, attr_name, indices=None):
+        n = self.num_envs if indices is None else len(list(indices) if not isinstance(indices, int) else [indices])
+        return [getattr(self.penv.env, attr_name)] * n
+
+    def set_attr(self, attr_name, value, indices=None):
+        raise AttributeError("the batched env shares one configuration; rebuild it to change %r" % attr_name)
+
+    def env_method(self, method_name, *args, indices=None, **kwargs):
+        if method_name == "render":
+            idx = range(self.num_envs) if indices is None else ([indices] if isinstance(indices, int) else indices)
+            return [self.penv.env.render(i) for i in idx]
+        raise AttributeError("no per-env method %r" % method_name)
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        n = self.num_envs if indices is None else len(list(indices) if not isinstance(indices, int) else [indices])
+        return [False] * n

@@ -73,3 +73,36 @@ def test_short_training_run_improves_return():
     assert hist[-1]["partner_updates"] >= 50
     # dense shaping makes the return move quickly once the agents walk towards the tomato
     assert hist[-1]["ep_rew_mean"] > hist[0]["ep_rew_mean"], (hist[0]["ep_rew_mean"], hist[-1]["ep_rew_mean"])
+
+
+def test_sb3_vecenv_adapter():
+    from gym_comm_b200.pantheon import SB3VecEnvAdapter
+    E, T = 16, 12
+    rng = np.random.default_rng(0)
+    table = torch.zeros((64, E, 2), dtype=torch.int32, device=DEV)
+    table[..., 0] = torch.from_numpy(rng.integers(0, 4, (64, E))).to(DEV)
+    venv = SB3VecEnvAdapter(PantheonVecEnv(OvercookedVecEnv(_ns(T), num_envs=E, device=DEV, seed=2), ScriptedPartner(table)),
+                            dict_obs=True)
+    obs = venv.reset()
+    assert set(obs.keys()) == set(venv.observation_space.spaces.keys()) and obs["timestep"].shape == (E, 1)
+    assert venv.action_space.nvec.tolist() == [4, 10] and venv.num_envs == E
+    seen_terminal = 0
+    prev = obs
+    for t in range(30):
+        acts = np.stack([rng.integers(0, 4, E), rng.integers(0, 10, E)], -1)
+        venv.step_async(acts)
+        obs, rew, done, infos = venv.step_wait()
+        assert rew.dtype == np.float32 and rew.shape == (E,) and done.dtype == bool and len(infos) == E
+        if (t + 1) % T == 0:
+            assert done.all()
+            for i in range(E):
+                to = infos[i]["terminal_observation"]
+                assert np.array_equal(to["agent1_location"], prev["agent1_location"][i])   # previous ego obs
+                seen_terminal += 1
+            assert np.all(obs["timestep"] == 0)                    # first obs of the new episode
+        else:
+            assert not done.any() and all(info == {} for info in infos)
+        prev = obs
+    assert seen_terminal == 2 * E
+    assert venv.env_is_wrapped(object) == [False] * E and len(venv.env_method("render", indices=[0, 1])) == 2
+    venv.close()
