@@ -255,3 +255,30 @@ def test_out_of_range_and_errors():
     bad = dict(cfg, max_num_timesteps=0)
     with pytest.raises(RuntimeError):
         make_gpu(bad, 4, False)
+
+
+def test_masked_reset_draws_same_placements_as_c_oracle():
+    """Random level, auto-reset OFF: explicit masked resets with device-drawn placements (Philox keyed
+    by env and episode) must land the objects on the same counters as the C oracle's twin."""
+    cfg = dict(CONFIGS["cfg4"], max_num_timesteps=25)
+    text, subtasks = level_and_subtasks(cfg)
+    E = 3000
+    env = make_gpu(cfg, E, auto_reset=False, seed=11)
+    ora = COracle(text, subtasks, E, seed=11, **oracle_kwargs(cfg))
+    assert np.array_equal(env.reset().cpu().numpy(), ora.reset().astype(np.float32))
+    rng = np.random.default_rng(2)
+    for t in range(80):
+        a = np.stack([rng.integers(0, 4, (E, 2)), rng.integers(0, 8, (E, 2))], -1).astype(np.int32)
+        obs, rew, done = env.step(torch.from_numpy(a).to(DEV), want_f64=True)
+        oo, orr, od = ora.step(a, auto_reset=False)
+        assert np.array_equal(done.cpu().numpy(), od) and np.array_equal(env.rewards64.cpu().numpy(), orr)
+        # reset a random subset of the finished envs plus a few unfinished ones
+        mask = ((od == 1) | (rng.random(E) < 0.01)).astype(np.uint8)
+        if mask.any():
+            og = env.reset(mask=torch.from_numpy(mask).to(DEV))
+            oc = ora.reset(mask=mask)
+            assert np.array_equal(og.cpu().numpy(), oc.astype(np.float32)), t
+    st, os_ = env.decode_state(), ora.state()
+    assert np.array_equal(st["episodes"], os_["episodes"]) and np.array_equal(st["t"], os_["t"])
+    env.close()
+    ora.close()
