@@ -280,13 +280,16 @@ extern "C" int oc_create(const oc_config* c, oc_env** out) {
     }
     p.blob = h->blob; p.ts_table = h->ts;
 
-    // opt in to large dynamic shared memory for every instantiation we may launch
+    // opt in to large dynamic shared memory for the instantiations we launch.  The attribute is per
+    // function, not per handle, so it is always set to the device maximum: a second handle with a
+    // smaller footprint must not lower it under the first one's feet.
+    const int smem_optin = (int)smem_cta_max;
     int rc = dispatch(p.A, p.NOBJ, p.rowf, [&](auto a, auto nobj, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
         constexpr bool RF = decltype(rf)::value;
-        CUDA_TRY(cudaFuncSetAttribute(oc_step_kernel<AA, NN, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-        CUDA_TRY(cudaFuncSetAttribute(oc_rollout_kernel<AA, NN, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-        CUDA_TRY(cudaFuncSetAttribute(oc_reset_kernel<AA, NN, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        CUDA_TRY(cudaFuncSetAttribute(oc_step_kernel<AA, NN, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(oc_rollout_kernel<AA, NN, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(oc_reset_kernel<AA, NN, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
         const int grid = (p.E + h->threads - 1) / h->threads;
         oc_reset_kernel<AA, NN, RF><<<grid, h->threads, h->smem_bytes, 0>>>(p, h->state, nullptr, nullptr, nullptr, 1);
         CUDA_TRY(cudaGetLastError());
@@ -318,9 +321,19 @@ extern "C" int oc_obs_layout(const oc_env* h, int32_t* offsets, int32_t* sizes) 
 
 static bool misaligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) != 0; }
 
+// a handle is bound to the device that was current at oc_create
+static int check_device(const oc_env* h) {
+    int cur = -1;
+    CUDA_TRY(cudaGetDevice(&cur));
+    if (cur != h->device) return fail(OC_ERR_INVALID, "handle was created on device " + std::to_string(h->device) +
+                                                      " but device " + std::to_string(cur) + " is current");
+    return OC_OK;
+}
+
 extern "C" int oc_reset(oc_env* h, const uint8_t* mask, const int32_t* placements, float* obs, void* stream) {
     if (!h) return fail(OC_ERR_INVALID, "null handle");
     if (obs && misaligned16(obs)) return fail(OC_ERR_INVALID, "obs must be 16-byte aligned");
+    if (int dc = check_device(h)) return dc;
     const OcParams& p = h->p;
     int rc = dispatch(p.A, p.NOBJ, p.rowf, [&](auto a, auto nobj, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
@@ -338,6 +351,7 @@ extern "C" int oc_step(oc_env* h, const int32_t* actions, float* obs, float* rew
                        uint8_t* done, float* term_obs, uint32_t flags, void* stream) {
     if (!h || !actions || !obs || !done) return fail(OC_ERR_INVALID, "null argument");
     if (misaligned16(obs) || (reinterpret_cast<uintptr_t>(actions) & 7)) return fail(OC_ERR_INVALID, "obs must be 16-byte and actions 8-byte aligned");
+    if (int dc = check_device(h)) return dc;
     const OcParams& p = h->p;
     int rc = dispatch(p.A, p.NOBJ, p.rowf, [&](auto a, auto nobj, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
@@ -363,6 +377,7 @@ extern "C" int oc_rollout(oc_env* h, int32_t n_steps, float* obs, float* rew_f32
                           int32_t* actions_out, void* stream) {
     if (!h || n_steps <= 0) return fail(OC_ERR_INVALID, "bad argument");
     if (obs && misaligned16(obs)) return fail(OC_ERR_INVALID, "obs must be 16-byte aligned");
+    if (int dc = check_device(h)) return dc;
     const OcParams& p = h->p;
     int rc = dispatch(p.A, p.NOBJ, p.rowf, [&](auto a, auto nobj, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
@@ -380,6 +395,7 @@ extern "C" int oc_rollout(oc_env* h, int32_t n_steps, float* obs, float* rew_f32
 extern "C" int oc_get_state(oc_env* h, uint32_t* state, void* stream) {
     if (!h || !state) return fail(OC_ERR_INVALID, "null argument");
     if (misaligned16(state)) return fail(OC_ERR_INVALID, "state must be 16-byte aligned");
+    if (int dc = check_device(h)) return dc;
     const int n = h->p.E * 4;
     oc_state_export_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->state, state, h->p.E);
     CUDA_TRY(cudaGetLastError());
@@ -390,6 +406,7 @@ extern "C" int oc_get_state(oc_env* h, uint32_t* state, void* stream) {
 extern "C" int oc_set_state(oc_env* h, const uint32_t* state, void* stream) {
     if (!h || !state) return fail(OC_ERR_INVALID, "null argument");
     if (misaligned16(state)) return fail(OC_ERR_INVALID, "state must be 16-byte aligned");
+    if (int dc = check_device(h)) return dc;
     const int n = h->p.E * 4;
     oc_state_import_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->state, state, h->p.E);
     CUDA_TRY(cudaGetLastError());
@@ -399,6 +416,7 @@ extern "C" int oc_set_state(oc_env* h, const uint32_t* state, void* stream) {
 
 extern "C" int oc_get_stats(oc_env* h, uint32_t* episodes, uint32_t* last_completed, void* stream) {
     if (!h) return fail(OC_ERR_INVALID, "null handle");
+    if (int dc = check_device(h)) return dc;
     oc_stats_kernel<<<(h->p.E + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->state, episodes, last_completed, h->p.E);
     CUDA_TRY(cudaGetLastError());
     h->launches += 1;

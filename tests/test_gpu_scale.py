@@ -282,3 +282,28 @@ def test_masked_reset_draws_same_placements_as_c_oracle():
     assert np.array_equal(st["episodes"], os_["episodes"]) and np.array_equal(st["t"], os_["t"])
     env.close()
     ora.close()
+
+
+def test_two_handles_with_different_levels_coexist():
+    """No global state: handles with different levels / widths / CTA shapes interleave their steps."""
+    names = ["cfg5", "cfg2", "cfg3_full"]
+    sizes = [4096, 100, 1000]
+    envs, oras = [], []
+    for nm, E in zip(names, sizes):
+        cfg = CONFIGS[nm]
+        text, subtasks = level_and_subtasks(cfg)
+        envs.append(make_gpu(cfg, E, auto_reset=True, seed=21))
+        oras.append(COracle(text, subtasks, E, seed=21, **oracle_kwargs(cfg)))
+    rng = np.random.default_rng(8)
+    for t in range(60):
+        for nm, E, env, ora in zip(names, sizes, envs, oras):
+            cfg = CONFIGS[nm]
+            n = cfg["num_agents"]
+            a = np.stack([rng.integers(0, 4, (E, n)), rng.integers(0, cfg["num_communication"], (E, n))], -1).astype(np.int32)
+            obs, rew, done = env.step(torch.from_numpy(a).to(DEV), want_f64=True)
+            oo, orr, od = ora.step(a, auto_reset=True)
+            assert np.array_equal(obs.cpu().numpy(), oo.astype(np.float32)), (nm, t)
+            assert np.array_equal(env.rewards64.cpu().numpy(), orr), (nm, t)
+    for env, ora in zip(envs, oras):
+        env.close()
+        ora.close()
