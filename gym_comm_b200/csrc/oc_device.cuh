@@ -691,11 +691,10 @@ __device__ __forceinline__ float step_one_env(Env<A, NOBJ>& e, const OcParams& p
 // auto-reset always on.  Draw layout (same in oracle/oc_oracle.c): counter (env, global step,
 // 'ACTS', 0); nav_k = bits [2k, 2k+2) of word 0; comm_0/1 = mulhi(word 1/2, C).
 template <int A, int NOBJ, bool ROWF>
-__device__ __forceinline__ float rollout_one_env(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
-                                                 uint32_t env, uint32_t s, uint32_t step0,
-                                                 uint8_t* myrow, bool want_obs,
-                                                 float* __restrict__ rew32, uint8_t* __restrict__ done_out,
-                                                 int32_t* __restrict__ actions_out) {
+__device__ __forceinline__ Info rollout_logic(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
+                                              uint32_t env, uint32_t s, uint32_t step0,
+                                              float* __restrict__ rew32, uint8_t* __restrict__ done_out,
+                                              int32_t* __restrict__ actions_out) {
     uint32_t r[4];
     philox4x32_10(env, step0 + s, 0x41435453u /*'ACTS'*/, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), r);
     int nav[A];
@@ -715,10 +714,21 @@ __device__ __forceinline__ float rollout_one_env(Env<A, NOBJ>& e, const OcParams
         for (int k = 0; k < A; ++k) rew32[((size_t)s * p.E + env) * A + k] = rr;
     }
     if (done_out != nullptr) done_out[(size_t)s * p.E + env] = done ? 1 : 0;
-    if (done) {
-        finish_episode<A, NOBJ, ROWF>(e, p, tb, in, myrow, nullptr, env);
+    if (done) {                                      // no terminal observation in the fused rollout: rows untouched
+        finish_episode<A, NOBJ, ROWF>(e, p, tb, in, nullptr, nullptr, env);
         in = gather_info<A, NOBJ>(e, p, tb);
     }
+    return in;
+}
+
+// logic + observation rows in one call (the CPU emulation harness drives this form)
+template <int A, int NOBJ, bool ROWF>
+__device__ __forceinline__ float rollout_one_env(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
+                                                 uint32_t env, uint32_t s, uint32_t step0,
+                                                 uint8_t* myrow, bool want_obs,
+                                                 float* __restrict__ rew32, uint8_t* __restrict__ done_out,
+                                                 int32_t* __restrict__ actions_out) {
+    const Info in = rollout_logic<A, NOBJ, ROWF>(e, p, tb, env, s, step0, rew32, done_out, actions_out);
     return want_obs ? finish_obs<A, NOBJ, ROWF>(e, p, tb, in, myrow) : 0.0f;
 }
 

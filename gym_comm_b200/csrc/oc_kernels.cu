@@ -97,17 +97,16 @@ oc_rollout_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
     const size_t step_floats = (size_t)p.E * p.row_bytes;
 
     for (int s = 0; s < n_steps; ++s) {
+        // dynamics first: they do not touch the rows, so the copy engine may still be reading the
+        // previous step's rows out of shared memory while this runs
+        Info in;
+        if (valid) in = rollout_logic<A, NOBJ, ROWF>(e, p, tb, (uint32_t)env, (uint32_t)s, step0, rew32, done_out, actions_out);
         if (obs != nullptr) {
             if (s > 0) rows_wait_read(p);
             warp_clear_rows<ROWF>(wrows, 32 * p.row_stride, lane);
             __syncwarp();
-        }
-        float ts = 0.0f;
-        if (valid) {
-            ts = rollout_one_env<A, NOBJ, ROWF>(e, p, tb, (uint32_t)env, (uint32_t)s, step0, myrow,
-                                          obs != nullptr, rew32, done_out, actions_out);
-        }
-        if (obs != nullptr) {
+            float ts = 0.0f;
+            if (valid) ts = finish_obs<A, NOBJ, ROWF>(e, p, tb, in, myrow);
             float* step_obs = obs + (size_t)s * step_floats;
             __syncwarp();
             if (nvalid > 0) warp_expand_rows<ROWF>(p, wrows, step_obs + (size_t)env0 * p.row_bytes, nvalid, lane);
