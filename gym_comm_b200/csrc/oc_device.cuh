@@ -660,19 +660,17 @@ __device__ __forceinline__ void finish_episode(Env<A, NOBJ>& e, const OcParams& 
     env_reset<A, NOBJ>(e, p, tb, nullptr, env_id);
 }
 
-// everything one thread does for its env in oc_step between loading and storing the state
-template <int A, int NOBJ, bool ROWF>
-__device__ __forceinline__ float step_one_env(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
-                                              const int (&nav)[A], int comm0, int comm1, uint32_t env,
-                                              uint8_t* myrow,
-                                              float* __restrict__ rew32, double* __restrict__ rew64,
-                                              uint8_t* __restrict__ done_out, float* __restrict__ term_obs,
-                                              uint32_t flags) {
-    double reward; bool done;
+// oc_step, part 1: dynamics + reward / done outputs (does not touch the observation rows)
+template <int A, int NOBJ>
+__device__ __forceinline__ Info step_logic(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
+                                           const int (&nav)[A], int comm0, int comm1, uint32_t env,
+                                           float* __restrict__ rew32, double* __restrict__ rew64,
+                                           uint8_t* __restrict__ done_out, bool& done) {
+    double reward;
     // out-of-range message index -> zero vector (the reference raises IndexError)
     const int c0 = ((uint32_t)comm0 < (uint32_t)p.C) ? comm0 : (int)OCK_COMM_NONE;
     const int c1 = ((uint32_t)comm1 < (uint32_t)p.C) ? comm1 : (int)OCK_COMM_NONE;
-    Info in = env_step<A, NOBJ>(e, p, tb, nav, c0, c1, reward, done);
+    const Info in = env_step<A, NOBJ>(e, p, tb, nav, c0, c1, reward, done);
     if (rew64 != nullptr) rew64[env] = reward;
     if (rew32 != nullptr) {
         const float r = (float)reward;
@@ -680,11 +678,31 @@ __device__ __forceinline__ float step_one_env(Env<A, NOBJ>& e, const OcParams& p
         for (int k = 0; k < A; ++k) rew32[(size_t)env * A + k] = r;
     }
     done_out[env] = done ? 1 : 0;
+    return in;
+}
+
+// oc_step, part 2: auto-reset (with the optional terminal observation) and the observation rows
+template <int A, int NOBJ, bool ROWF>
+__device__ __forceinline__ float step_finish(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb, Info in, bool done,
+                                             uint32_t env, uint8_t* myrow, float* __restrict__ term_obs, uint32_t flags) {
     if (done && (flags & 1u /*OC_FLAG_AUTO_RESET*/)) {
         finish_episode<A, NOBJ, ROWF>(e, p, tb, in, myrow, term_obs ? term_obs + (size_t)env * p.row_bytes : nullptr, env);
         in = gather_info<A, NOBJ>(e, p, tb);
     }
     return finish_obs<A, NOBJ, ROWF>(e, p, tb, in, myrow);
+}
+
+// both parts in one call (the CPU emulation harness drives this form)
+template <int A, int NOBJ, bool ROWF>
+__device__ __forceinline__ float step_one_env(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
+                                              const int (&nav)[A], int comm0, int comm1, uint32_t env,
+                                              uint8_t* myrow,
+                                              float* __restrict__ rew32, double* __restrict__ rew64,
+                                              uint8_t* __restrict__ done_out, float* __restrict__ term_obs,
+                                              uint32_t flags) {
+    bool done;
+    const Info in = step_logic<A, NOBJ>(e, p, tb, nav, comm0, comm1, env, rew32, rew64, done_out, done);
+    return step_finish<A, NOBJ, ROWF>(e, p, tb, in, done, env, myrow, term_obs, flags);
 }
 
 // one env, one step of the fused synthetic rollout: Philox actions (nav ~ U{0..3}, comm ~ U{0..C-1}),

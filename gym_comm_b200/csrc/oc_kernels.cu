@@ -45,19 +45,30 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
 
     // the grid is sized to ONE resident wave (148 SMs x CTAs that fit); with more envs than that
     // each CTA walks several chunks so the tables are loaded once per CTA, not once per chunk
+    bool first = true;
     for (int base = blockIdx.x * blockDim.x; base < p.E; base += gridDim.x * blockDim.x) {
         const int env = base + threadIdx.x;
         const bool valid = env < p.E;
-        float ts = 0.0f;
-        if (valid) {
-            Env<A, NOBJ> e;
+        Env<A, NOBJ> e;
+        Info in;
+        bool done = false;
+        if (valid) {                                    // dynamics: no row access, may overlap the previous chunk's TMA read
             int nav[A], comm[A];
             load_env<A, NOBJ>(e, state, p.E, env);
             const int2* a2 = reinterpret_cast<const int2*>(actions) + (size_t)env * A;
 #pragma unroll
             for (int k = 0; k < A; ++k) { const int2 v = __ldg(a2 + k); nav[k] = v.x & 3; comm[k] = v.y; }
-            ts = step_one_env<A, NOBJ, ROWF>(e, p, tb, nav, comm[0], comm[1], (uint32_t)env, myrow,
-                                             rew32, rew64, done_out, term_obs, flags);
+            in = step_logic<A, NOBJ>(e, p, tb, nav, comm[0], comm[1], (uint32_t)env, rew32, rew64, done_out, done);
+        }
+        if (!first) {                                   // rows of the previous chunk: read out, then clear
+            rows_wait_read(p);
+            warp_clear_rows<ROWF>(wrows, 32 * p.row_stride, lane);
+            __syncwarp();
+        }
+        first = false;
+        float ts = 0.0f;
+        if (valid) {
+            ts = step_finish<A, NOBJ, ROWF>(e, p, tb, in, done, (uint32_t)env, myrow, term_obs, flags);
             store_env<A, NOBJ>(e, state, p.E, env);
         }
         __syncwarp();
@@ -66,11 +77,6 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
         if (nvalid > 0) warp_expand_rows<ROWF>(p, wrows, obs + (size_t)env0 * p.row_bytes, nvalid, lane);
         __syncwarp();                               // order the float4 stores before the timestep patch
         if (!ROWF && valid) store_timesteps<A>(p, obs + (size_t)env * p.row_bytes, ts);
-        if (base + gridDim.x * blockDim.x < p.E) {
-            rows_wait_read(p);
-            warp_clear_rows<ROWF>(wrows, 32 * p.row_stride, lane);
-            __syncwarp();
-        }
     }
     rows_wait_done(p);
 }

@@ -307,3 +307,25 @@ def test_two_handles_with_different_levels_coexist():
     for env, ora in zip(envs, oras):
         env.close()
         ora.close()
+
+
+def test_rollout_without_observations():
+    """oc_rollout with obs = NULL (state-only fast-forward): rewards/dones/state still match the oracle,
+    and a following observed step sees the same world."""
+    cfg = CONFIGS["cfg2"]
+    text, subtasks = level_and_subtasks(cfg)
+    E = 5000
+    env = make_gpu(cfg, E, auto_reset=True, seed=31)
+    ora = COracle(text, subtasks, E, seed=31, **oracle_kwargs(cfg))
+    rew = torch.zeros((700, E, 2), device=DEV)
+    done = torch.zeros((700, E), dtype=torch.uint8, device=DEV)
+    env.rollout(700, rew_out=rew, done_out=done)
+    _, orr, od, _ = ora.rollout(700, want_obs=False)
+    assert torch.equal(done.cpu(), torch.from_numpy(od))
+    assert torch.equal(rew.cpu()[:, :, 0], torch.from_numpy(orr.astype(np.float32)))
+    a = torch.zeros((E, 2, 2), dtype=torch.int32, device=DEV)
+    obs, _, _ = env.step(a)
+    oo, _, _ = ora.step(a.cpu().numpy(), auto_reset=True)
+    assert torch.equal(obs.cpu(), torch.from_numpy(oo.astype(np.float32)))
+    env.close()
+    ora.close()
