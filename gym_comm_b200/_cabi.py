@@ -19,7 +19,7 @@ OBS_KEYS = ("agent1_comm", "agent1_location", "agent2_comm", "agent2_location", 
             "state_encodings", "timestep")
 
 EXPORTS = ("oc_abi_version", "oc_last_error", "oc_create", "oc_destroy", "oc_obs_width", "oc_obs_layout",
-           "oc_reset", "oc_step", "oc_rollout", "oc_get_state", "oc_set_state", "oc_get_stats",
+           "oc_reset", "oc_step", "oc_rollout", "oc_replay", "oc_get_state", "oc_set_state", "oc_get_stats",
            "oc_launch_count")
 
 
@@ -86,6 +86,8 @@ class OcLibrary:
         self.reset = fn("reset", C.c_int, [vp, vp, vp, vp, vp])
         self.step = fn("step", C.c_int, [vp, vp, vp, vp, vp, vp, vp, u32, vp])
         self.rollout = fn("rollout", C.c_int, [vp, i32, vp, vp, vp, vp, vp])
+        if prefix == "oc_":
+            self.replay = fn("replay", C.c_int, [vp, i32, vp, vp, vp, vp, vp])
         self.get_state = fn("get_state", C.c_int, [vp, vp, vp])
         self.set_state = fn("set_state", C.c_int, [vp, vp, vp])
         self.get_stats = fn("get_stats", C.c_int, [vp, vp, vp, vp])

@@ -712,13 +712,24 @@ template <int A, int NOBJ, bool ROWF>
 __device__ __forceinline__ Info rollout_logic(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
                                               uint32_t env, uint32_t s, uint32_t step0,
                                               float* __restrict__ rew32, uint8_t* __restrict__ done_out,
-                                              int32_t* __restrict__ actions_out) {
-    uint32_t r[4];
-    philox4x32_10(env, step0 + s, 0x41435453u /*'ACTS'*/, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), r);
+                                              int32_t* __restrict__ actions_out,
+                                              const int32_t* __restrict__ actions_in = nullptr) {
     int nav[A];
+    int c0, c1;
+    if (actions_in != nullptr) {                     // oc_replay: open-loop action sequence from HBM
+        const int2* a2 = reinterpret_cast<const int2*>(actions_in) + ((size_t)s * p.E + env) * A;
+        int cm[A];
 #pragma unroll
-    for (int k = 0; k < A; ++k) nav[k] = (r[0] >> (2 * k)) & 3;
-    const int c0 = (int)__umulhi(r[1], (uint32_t)p.C), c1 = (int)__umulhi(r[2], (uint32_t)p.C);
+        for (int k = 0; k < A; ++k) { const int2 v = __ldg(a2 + k); nav[k] = v.x & 3; cm[k] = v.y; }
+        c0 = ((uint32_t)cm[0] < (uint32_t)p.C) ? cm[0] : (int)OCK_COMM_NONE;
+        c1 = ((uint32_t)cm[1] < (uint32_t)p.C) ? cm[1] : (int)OCK_COMM_NONE;
+    } else {
+        uint32_t r[4];
+        philox4x32_10(env, step0 + s, 0x41435453u /*'ACTS'*/, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), r);
+#pragma unroll
+        for (int k = 0; k < A; ++k) nav[k] = (r[0] >> (2 * k)) & 3;
+        c0 = (int)__umulhi(r[1], (uint32_t)p.C); c1 = (int)__umulhi(r[2], (uint32_t)p.C);
+    }
     if (actions_out != nullptr) {
         int32_t* ao = actions_out + ((size_t)s * p.E + env) * A * 2;
 #pragma unroll

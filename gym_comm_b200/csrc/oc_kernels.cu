@@ -86,7 +86,7 @@ template <int A, int NOBJ, bool ROWF>
 __global__ void __launch_bounds__(256)
 oc_rollout_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, int n_steps, uint32_t step0,
                   float* __restrict__ obs, float* __restrict__ rew32, uint8_t* __restrict__ done_out,
-                  int32_t* __restrict__ actions_out) {
+                  int32_t* __restrict__ actions_out, const int32_t* __restrict__ actions_in) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
@@ -106,7 +106,7 @@ oc_rollout_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
         // dynamics first: they do not touch the rows, so the copy engine may still be reading the
         // previous step's rows out of shared memory while this runs
         Info in;
-        if (valid) in = rollout_logic<A, NOBJ, ROWF>(e, p, tb, (uint32_t)env, (uint32_t)s, step0, rew32, done_out, actions_out);
+        if (valid) in = rollout_logic<A, NOBJ, ROWF>(e, p, tb, (uint32_t)env, (uint32_t)s, step0, rew32, done_out, actions_out, actions_in);
         if (obs != nullptr) {
             if (s > 0) rows_wait_read(p);
             warp_clear_rows<ROWF>(wrows, 32 * p.row_stride, lane);
@@ -378,8 +378,23 @@ extern "C" int oc_step(oc_env* h, const int32_t* actions, float* obs, float* rew
     return rc;
 }
 
+static int launch_rollout(oc_env* h, int32_t n_steps, float* obs, float* rew_f32, uint8_t* done,
+                          int32_t* actions_out, const int32_t* actions_in, void* stream);
+
 extern "C" int oc_rollout(oc_env* h, int32_t n_steps, float* obs, float* rew_f32, uint8_t* done,
                           int32_t* actions_out, void* stream) {
+    return launch_rollout(h, n_steps, obs, rew_f32, done, actions_out, nullptr, stream);
+}
+
+extern "C" int oc_replay(oc_env* h, int32_t n_steps, const int32_t* actions, float* obs, float* rew_f32,
+                         uint8_t* done, void* stream) {
+    if (!actions) return fail(OC_ERR_INVALID, "null actions");
+    if (reinterpret_cast<uintptr_t>(actions) & 7) return fail(OC_ERR_INVALID, "actions must be 8-byte aligned");
+    return launch_rollout(h, n_steps, obs, rew_f32, done, nullptr, actions, stream);
+}
+
+static int launch_rollout(oc_env* h, int32_t n_steps, float* obs, float* rew_f32, uint8_t* done,
+                          int32_t* actions_out, const int32_t* actions_in, void* stream) {
     if (!h || n_steps <= 0) return fail(OC_ERR_INVALID, "bad argument");
     if (obs && misaligned16(obs)) return fail(OC_ERR_INVALID, "obs must be 16-byte aligned");
     if (int dc = check_device(h)) return dc;
@@ -389,11 +404,11 @@ extern "C" int oc_rollout(oc_env* h, int32_t n_steps, float* obs, float* rew_f32
         constexpr bool RF = decltype(rf)::value;
         const int grid = (p.E + h->threads - 1) / h->threads;
         oc_rollout_kernel<AA, NN, RF><<<grid, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(
-            p, h->state, n_steps, h->rollout_step, obs, rew_f32, done, actions_out);
+            p, h->state, n_steps, h->rollout_step, obs, rew_f32, done, actions_out, actions_in);
         CUDA_TRY(cudaGetLastError());
         return OC_OK;
     });
-    if (rc == OC_OK) { h->launches += 1; h->rollout_step += (uint32_t)n_steps; }
+    if (rc == OC_OK) { h->launches += 1; if (!actions_in) h->rollout_step += (uint32_t)n_steps; }
     return rc;
 }
 

@@ -174,6 +174,22 @@ class OvercookedVecEnv:
             self.lib.check(self.lib.rollout(self._handle, int(n_steps), self._ptr(obs_out), self._ptr(rew_out),
                                             self._ptr(done_out), self._ptr(actions_out), self._stream()), "oc_rollout")
 
+    def replay(self, actions: torch.Tensor, obs_out=None, rew_out=None, done_out=None):
+        """Open-loop replay of an action sequence int32 [n_steps, E, A, 2] in ONE launch (auto-reset
+        on); outputs as for `rollout`."""
+        n_steps = int(actions.shape[0])
+        E, A, F = self.num_envs, self.num_agents, self.obs_width
+        self._check_tensor(actions, (n_steps, E, A, 2), torch.int32, "actions")
+        if obs_out is not None:
+            self._check_tensor(obs_out, (n_steps, E, A, F), torch.float32, "obs_out")
+        if rew_out is not None:
+            self._check_tensor(rew_out, (n_steps, E, A), torch.float32, "rew_out")
+        if done_out is not None:
+            self._check_tensor(done_out, (n_steps, E), torch.uint8, "done_out")
+        with self._device_guard():
+            self.lib.check(self.lib.replay(self._handle, n_steps, self._ptr(actions), self._ptr(obs_out), self._ptr(rew_out),
+                                           self._ptr(done_out), self._stream()), "oc_replay")
+
     # ------------------------------------------------------------------ state / stats
     def get_state(self) -> torch.Tensor:
         st = torch.zeros((self.num_envs, _cabi.OC_STATE_WORDS), dtype=torch.int32, device=self.device)

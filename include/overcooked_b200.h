@@ -158,6 +158,13 @@ int oc_step(oc_env* env, const int32_t* actions, float* obs, float* rew_f32, dou
 int oc_rollout(oc_env* env, int32_t n_steps, float* obs, float* rew_f32, uint8_t* done,
                int32_t* actions_out, void* stream);
 
+/* Open-loop replay: like oc_rollout, but step s applies the caller's actions[s] (int32
+ * [n_steps, E, A, 2], device) instead of drawing them -- n_steps env steps in ONE launch with the
+ * state kept on chip, auto-reset on.  For evaluating recorded / scripted / planned action sequences
+ * (the reference's tester.py:72-106 loop with a fixed action list). */
+int oc_replay(oc_env* env, int32_t n_steps, const int32_t* actions, float* obs, float* rew_f32,
+              uint8_t* done, void* stream);
+
 /* Packed state export / injection (parity tests; checkpointing).  state: u32[E, OC_STATE_WORDS]
  * device, layout in DESIGN.md.  Replaces OvercookedEnvironment.__copy__/get_repr
  * (overcooked_environment.py:59-84). */

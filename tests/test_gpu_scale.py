@@ -329,3 +329,33 @@ def test_rollout_without_observations():
     assert torch.equal(obs.cpu(), torch.from_numpy(oo.astype(np.float32)))
     env.close()
     ora.close()
+
+
+def test_replay_of_an_action_sequence_matches_stepping():
+    """oc_replay (n steps of caller-given actions in one launch) == n oc_step calls == the C oracle."""
+    cfg = CONFIGS["cfg3_full"]
+    text, subtasks = level_and_subtasks(cfg)
+    E, n, T = 3001, 3, 350
+    env_a = make_gpu(cfg, E, auto_reset=True, seed=41)
+    env_b = make_gpu(cfg, E, auto_reset=True, seed=41)
+    ora = COracle(text, subtasks, E, seed=41, **oracle_kwargs(cfg))
+    gen = torch.Generator(device=DEV).manual_seed(41)
+    acts = torch.stack([torch.randint(0, 4, (T, E, n), generator=gen, device=DEV, dtype=torch.int32),
+                        torch.randint(0, 10, (T, E, n), generator=gen, device=DEV, dtype=torch.int32)], -1).contiguous()
+    F = env_a.obs_width
+    obs = torch.zeros((T, E, n, F), device=DEV)
+    rew = torch.zeros((T, E, n), device=DEV)
+    done = torch.zeros((T, E), dtype=torch.uint8, device=DEV)
+    env_a.replay(acts, obs_out=obs, rew_out=rew, done_out=done)
+    a_cpu = acts.cpu().numpy()
+    for t in range(T):
+        o_b, r_b, d_b = env_b.step(acts[t])
+        assert torch.equal(o_b, obs[t]) and torch.equal(r_b, rew[t]) and torch.equal(d_b, done[t]), t
+        oo, orr, od = ora.step(a_cpu[t], auto_reset=True)
+        if t % 25 == 0 or t == T - 1:
+            assert torch.equal(obs[t].cpu(), torch.from_numpy(oo.astype(np.float32))), t
+        assert torch.equal(done[t].cpu(), torch.from_numpy(od)), t
+    assert torch.equal(env_a.get_state(), env_b.get_state())
+    for e in (env_a, env_b):
+        e.close()
+    ora.close()
