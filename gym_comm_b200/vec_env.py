@@ -313,8 +313,12 @@ class OvercookedMultiEnv:
 
     def _split(self, obs_row: np.ndarray):
         out = {}
+        t = int(self.vec.decode_state()["t"][0])
         for k, s in self.vec.obs_layout.items():
             v = obs_row[s]
+            if k == "timestep":       # the reference returns the f64 quotient (overcooked_env.py:146), not its f32 rounding
+                out[k] = np.array((t / self.arglist.max_num_timesteps,))
+                continue
             if k in ("object_encodings_x", "object_encodings_y", "state_encodings", "is_hidden",
                      "completed_subtasks"):
                 v = v.astype(np.int64)

@@ -39,8 +39,7 @@ def test_multi_step_matches_reference_trace(name):
             assert set(obs_pair[k].keys()) == set(KEYS)
             for key in KEYS:
                 got = np.asarray(obs_pair[k][key], dtype=np.float64)
-                exp = np.float32(want[key]).astype(np.float64) if key == "timestep" else want[key]
-                assert np.array_equal(got, exp), (name, key, got, exp)
+                assert np.array_equal(got, want[key]), (name, key, got, want[key])      # timestep too: exact f64
 
     ep = 0
     check(env.multi_reset(placements(0)), g["reset_obs"][0])
@@ -72,5 +71,5 @@ def test_known_answer_survey_a7():
     assert o0["agent1_location"].tolist() == [3, 1] and o0["agent2_location"].tolist() == [4, 2]
     assert o0["agent1_comm"].tolist() == [0, 0, 1, 0, 0] and o0["agent2_comm"].tolist() == [0, 0, 0, 0, 1]
     assert o0["completed_subtasks"].tolist() == [0, 0, 0] and o0["agent_is_holding"].tolist() == [False, False]
-    assert abs(float(o0["timestep"][0]) - 0.002) < 1e-9
+    assert float(o0["timestep"][0]) == 0.002
     env.close()
