@@ -352,5 +352,58 @@ class OvercookedMultiEnv:
         o = self.vec.reset(placements=pl)[0].cpu().numpy()
         return (self._split(o[0]), self._split(o[1]))
 
+    # ---- MultiAgentEnv surface (pantheonrl/common/multiagentenv.py:72-243), single env, ego index 0
+    class Observation:
+        """pantheonrl.common.observation.Observation: what a partner's `get_action` receives."""
+
+        def __init__(self, obs):
+            self.obs, self.state, self.action_mask = obs, obs, None
+
+    def add_partner_agent(self, agent, player_num: int = 1) -> None:
+        if player_num != 1:
+            raise ValueError("Ego agent is not set by the environment")      # PlayerException (:86-87)
+        self.__dict__.setdefault("partners", []).append(agent)
+        self.__dict__.setdefault("partnerid", 0)
+
+    def getDummyEnv(self, player_num: int):
+        return self
+
+    def set_ego_extractor(self, ego_extractor) -> None:
+        self.ego_extractor = ego_extractor
+
+    def reset(self, placements=None):
+        """MultiAgentEnv.reset (:217-243): round-robin partner resampling, first ego observation."""
+        partners = self.__dict__.get("partners", [])
+        if partners:
+            self.partnerid = (self.partnerid + 1) % len(partners)                # resample_round_robin (:124-131)
+        self._obs = self.multi_reset(placements)
+        self._should_update, self._total_rews = False, [0.0, 0.0]
+        self._old_ego_obs = self._obs[0]
+        return self.__dict__.get("ego_extractor", lambda o: o)(self._obs[0])
+
+    def step(self, action):
+        """MultiAgentEnv.step (:172-215): the partner acts inside the step on the observation it saw
+        last, gets `update(reward, done)`; on done the PREVIOUS ego observation is returned."""
+        partners = self.__dict__.get("partners", [])
+        if not partners:
+            raise RuntimeError("add_partner_agent first")
+        if "_obs" not in self.__dict__:
+            self.reset()
+        agent = partners[self.partnerid]
+        alt = agent.get_action(self.Observation(self._obs[1]))
+        if not self._should_update:
+            agent.update(self._total_rews[1], False)                             # _get_actions (:157-159)
+        self._should_update = True
+        obs, rews, done, info = self.multi_step(action, alt)
+        info["_partnerid"] = [self.partnerid]
+        agent.update(rews[1], done)                                              # _update_players (:163-170)
+        self._total_rews = [self._total_rews[0] + rews[0], self._total_rews[1] + rews[1]]
+        extract = self.__dict__.get("ego_extractor", lambda o: o)
+        if done:
+            return extract(self._old_ego_obs), rews[0], done, info               # (:204-208)
+        self._obs = obs
+        self._old_ego_obs = obs[0]
+        return extract(obs[0]), rews[0], done, info
+
     def close(self):
         self.vec.close()

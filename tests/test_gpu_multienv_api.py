@@ -73,3 +73,45 @@ def test_known_answer_survey_a7():
     assert o0["completed_subtasks"].tolist() == [0, 0, 0] and o0["agent_is_holding"].tolist() == [False, False]
     assert float(o0["timestep"][0]) == 0.002
     env.close()
+
+
+def test_multiagentenv_step_reset_with_partner():
+    """`step(action)` / `reset()` with an embedded partner, as trainer.py drives the env
+    (pantheonrl/common/multiagentenv.py:172-243)."""
+    import argparse
+
+    class Partner:
+        def __init__(self):
+            self.seen, self.updates = [], []
+
+        def get_action(self, obs):
+            self.seen.append(obs.obs)
+            return (0, 3)
+
+        def update(self, reward, done):
+            self.updates.append((reward, done))
+
+    d = dict(CAN_MOVE=True, ALLERGIC=False, BLIND=False)
+    ns = argparse.Namespace(level="open-divider_tomato", num_agents=2, max_num_timesteps=5, communication_on=True,
+                            num_communication=5, ego_led=False, fow_radius=2, ego_config=d, partner_config=d)
+    env = OvercookedMultiEnv(ns)
+    twin = OvercookedMultiEnv(ns)
+    p = Partner()
+    env.add_partner_agent(p)
+    ego_obs = env.reset()
+    o_twin = twin.multi_reset()
+    assert all(np.array_equal(ego_obs[k], o_twin[0][k]) for k in KEYS)
+    prev = ego_obs
+    for t in range(5):
+        obs, r, done, info = env.step((3, 1))
+        (t0, t1), (tr, _), tdone, _ = twin.multi_step((3, 1), (0, 3))
+        assert r == tr and done is tdone and info["_partnerid"] == [0]
+        if not done:
+            assert all(np.array_equal(obs[k], t0[k]) for k in KEYS)
+            prev = obs
+        else:
+            assert all(np.array_equal(obs[k], prev[k]) for k in KEYS)     # previous ego obs on done
+    assert done and len(p.seen) == 5
+    assert p.updates[0] == (0.0, False) and len(p.updates) == 6 and p.updates[-1][1] is True
+    env.close()
+    twin.close()
