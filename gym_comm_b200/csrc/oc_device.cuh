@@ -164,7 +164,8 @@ __device__ __forceinline__ void env_reset(Env<A, NOBJ>& e, const OcParams& p, co
     if (p.nrandom > 0) {
         uint32_t cell[OCK_MAX_OBJECTS] = {0, 0, 0, 0, 0, 0};
         if (placements != nullptr) {
-            for (int j = 0; j < p.nrandom; ++j) cell[j] = (uint32_t)placements[j];
+            for (int j = 0; j < p.nrandom; ++j)          // clamped: a bad index must not run the table look-ups out of bounds
+                cell[j] = min((uint32_t)placements[j], (uint32_t)(p.ncell - 1));
         } else {
             draw_random_cells(p, tb.counters, env_id, e.episodes, cell);
         }
