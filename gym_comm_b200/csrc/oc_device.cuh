@@ -570,7 +570,11 @@ __device__ __forceinline__ void warp_expand_rows(const OcParams& p, const uint8_
             // of the warp's 32 contiguous rows (11.8 KB for cfg2) by one lane
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) tma_store(out, wrows, (uint32_t)(total * 16));
+            if (p.use_tma == 1) {                    // contiguous rows: one copy for the warp
+                if (lane == 0) tma_store(out, wrows, (uint32_t)(total * 16));
+            } else if (lane < nvalid) {              // padded rows (use_tma == 2): one copy per env row
+                tma_store(out + (size_t)lane * p.row_bytes, wrows + (size_t)lane * p.row_stride, (uint32_t)(p.row_bytes * 4));
+            }
             return;
         }
 #endif

@@ -113,8 +113,10 @@ static inline int compile_config(const oc_config* c, HostImage& h, std::string& 
     // 4 (mod 8) words (8 distinct banks, 4-way conflict); a multiple of 8 words would put all 32 lanes
     // on 1-4 banks (cfg4: 96 floats -> 32-way), so such rows get 4 floats of padding
     if (p.rowf) p.row_stride = (p.row_bytes + ((p.row_bytes & 7) == 0 ? 4 : 0)) * 4;
-    p.use_tma = p.rowf && p.row_stride == p.row_bytes * 4;   // padded rows (32 small copies per warp) measured slower
-    if (const char* t = getenv("OC_TMA")) p.use_tma = p.use_tma && atoi(t) != 0;
+    // 1: one bulk copy per warp (contiguous rows).  Padded rows would need 32 small copies per warp: that
+    // measured slower in the fused rollout but faster in the single-step kernel, which sets 2 itself.
+    p.use_tma = (p.rowf && p.row_stride == p.row_bytes * 4) ? 1 : 0;
+    if (const char* t = getenv("OC_TMA")) p.use_tma = (p.use_tma && atoi(t) != 0) ? 1 : 0;
     p.r4_magic = (p.row_bytes >= 4) ? (uint32_t)((1ull << 32) / (uint64_t)(p.row_bytes >> 2)) + 1u : 0u;
     p.rf_magic = (uint32_t)((1ull << 32) / (uint64_t)p.row_bytes) + 1u;
     for (int k = 0; k < OC_MAX_AGENTS; ++k) {

@@ -201,6 +201,7 @@ struct oc_env {
     uint64_t launches = 0;
     uint32_t rollout_step = 0;
     int pdl = 1;
+    int tma_rows_in_step = 1;
     int step_grid = 1;
     int obs_off[OC_NUM_OBS_KEYS], obs_size[OC_NUM_OBS_KEYS];
 };
@@ -242,6 +243,7 @@ extern "C" int oc_create(const oc_config* c, oc_env** out) {
     h->device = dev;
 
     if (const char* pe = getenv("OC_PDL")) h->pdl = atoi(pe) != 0;
+    if (const char* te = getenv("OC_TMA")) h->tma_rows_in_step = atoi(te) != 0;
     // CTA shape: the work is one warp per 32 envs; pick the CTA size whose resident wave
     // (limited by shared memory: table blob + 32 rows per warp, by 2048 threads and 32 CTAs per
     // SM) covers the envs with the smallest makespan, preferring fewer table copies on ties.
@@ -370,7 +372,9 @@ extern "C" int oc_step(oc_env* h, const int32_t* actions, float* obs, float* rew
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = h->pdl ? 1 : 0;
-        CUDA_TRY(cudaLaunchKernelEx(&cfg, oc_step_kernel<AA, NN, RF>, p, h->state, actions, obs, rew_f32, rew_f64,
+        OcParams ps = p;
+        if (ps.rowf && !ps.use_tma && h->tma_rows_in_step) ps.use_tma = 2;      // padded float rows: per-row bulk copies
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, oc_step_kernel<AA, NN, RF>, ps, h->state, actions, obs, rew_f32, rew_f64,
                                     done, term_obs, flags));
         return OC_OK;
     });
