@@ -452,8 +452,6 @@ __device__ __forceinline__ void build_rows_f32(const Env<A, NOBJ>& e, const OcPa
             r[p.off_a2loc] = a1.x; r[p.off_a2loc + 1] = a1.y;
         }
         if (!p.ego_blind && ((in.holdmask >> k) & 1u)) r[p.off_hold] = 1.0f;   // :154
-        for (int i = 0; i < p.S; ++i)
-            if ((e.completed >> i) & 1u) r[p.off_completed + i] = 1.0f;
         if (blind) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) r[p.off_hidden + c] = 1.0f;            // :109
@@ -474,6 +472,12 @@ __device__ __forceinline__ void build_rows_f32(const Env<A, NOBJ>& e, const OcPa
         }
         r[p.off_ts] = ts;                                                      // :146
     }
+    // completed_subtasks: the same bits for every observer -- walk the set bits once
+    for (uint32_t m = e.completed; m != 0; m &= m - 1) {
+        float* r = row + p.off_completed + (__ffs((int)m) - 1);
+#pragma unroll
+        for (int k = 0; k < A; ++k) r[k * p.F] = 1.0f;
+    }
 }
 
 template <int A, int NOBJ>
@@ -493,8 +497,6 @@ __device__ __forceinline__ void build_rows_u8(const Env<A, NOBJ>& e, const OcPar
             r[p.off_a2loc] = OCK_BIAS + (xy1 & 0xFF);  r[p.off_a2loc + 1] = OCK_BIAS + (xy1 >> 8);
         }
         if (!p.ego_blind && ((in.holdmask >> k) & 1u)) r[p.off_hold] = OCK_BIAS + 1;
-        for (int i = 0; i < p.S; ++i)
-            if ((e.completed >> i) & 1u) r[p.off_completed + i] = OCK_BIAS + 1;
         if (blind) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) r[p.off_hidden + c] = OCK_BIAS + 1;
@@ -513,6 +515,11 @@ __device__ __forceinline__ void build_rows_u8(const Env<A, NOBJ>& e, const OcPar
                 }
             }
         }
+    }
+    for (uint32_t m = e.completed; m != 0; m &= m - 1) {
+        uint8_t* r = row + p.off_completed + (__ffs((int)m) - 1);
+#pragma unroll
+        for (int k = 0; k < A; ++k) r[k * p.F] = OCK_BIAS + 1;
     }
 }
 
