@@ -1,0 +1,32 @@
+import sys, argparse
+sys.path.insert(0, '/root/repo')
+import numpy as np, torch
+from gym_comm_b200 import _cabi
+from gym_comm_b200.vec_env import OvercookedVecEnv
+from tests.golden_util import golden_names, load_golden
+from tests.parity_util import replay_golden
+lib = _cabi.OcLibrary(sys.argv[1], prefix='emu_')
+for name in golden_names():
+    meta, g = load_golden(name)
+    replay_golden(meta, g, lib, 'cpu', num_envs=33)
+    print(name, 'ok', flush=True)
+# auto-reset + term obs + rollout on random levels
+d = dict(CAN_MOVE=True, ALLERGIC=False, BLIND=False)
+for c in [dict(level="random-open-divider_salad_small_cramped", num_agents=2, max_num_timesteps=12, num_communication=8, fow_radius=10),
+          dict(level="random-salad-superwide", num_agents=2, max_num_timesteps=10, num_communication=100, fow_radius=2),
+          dict(level="open-divider_tl", num_agents=3, max_num_timesteps=10, num_communication=5, fow_radius=3),
+          dict(level="open-divider_salad", num_agents=4, max_num_timesteps=10, num_communication=7, fow_radius=1)]:
+    ns = argparse.Namespace(communication_on=True, ego_led=False, ego_config=d, partner_config=d, **c)
+    for E in (1, 33, 70):
+        env = OvercookedVecEnv(ns, num_envs=E, device='cpu', seed=3, lib=lib)
+        A, F = env.num_agents, env.obs_width
+        rng = np.random.default_rng(0)
+        term = torch.zeros((E, A, F))
+        for t in range(40):
+            a = torch.from_numpy(np.stack([rng.integers(0,4,(E,A)), rng.integers(0,c['num_communication'],(E,A))],-1).astype(np.int32))
+            env.step(a, term_obs_out=term, want_f64=True)
+        obs = torch.zeros((8, E, A, F)); rew = torch.zeros((8, E, A)); done = torch.zeros((8, E), dtype=torch.uint8); acts = torch.zeros((8,E,A,2), dtype=torch.int32)
+        env.rollout(8, obs_out=obs, rew_out=rew, done_out=done, actions_out=acts)
+        env.reset(mask=done[-1].contiguous()); env.set_state(env.get_state()); env.close()
+    print(c['level'], 'ok', flush=True)
+print('ASAN RUN CLEAN')
