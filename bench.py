@@ -326,10 +326,15 @@ def main():
         avg_launch_ms = total_ms / nlaunch
         steps_per_launch = K / nlaunch
         achieved = float(bpes) * E * steps_per_launch / (avg_launch_ms / 1e3) / 1e9
+        moved = bpes if mode == "step" else A * 4 * F + A * 4 + 1
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic.get(args.workload + ":" + mode), "peak_source": peak_src,
                 "kernel": "oc_step_kernel" if mode == "step" else "oc_rollout_kernel",
                 "bytes_per_env_step": bpes, "envs_per_launch": E, "steps_per_launch": steps_per_launch,
+                # what this kernel really moves per env-step: the fused rollout keeps state and actions
+                # on chip, so only obs + reward + done cross HBM (that is why its algorithmic frac can exceed 1)
+                "bytes_moved_per_env_step": moved, "achieved_moved": float(moved) * E * steps_per_launch / (avg_launch_ms / 1e3) / 1e9,
+                "frac_moved": float(moved) * E * steps_per_launch / (avg_launch_ms / 1e3) / 1e9 / peak,
                 "launches_in_timed_region": nlaunch, "avg_launch_us": avg_launch_ms * 1e3,
                 "event_bracketed_launch_us": {"mean": mean_ms * 1e3 * (steps_per_launch / spl),
                                               "median": statistics.median(kernel_ms) * 1e3, "n": nk, "steps_per_launch": spl},
