@@ -12,6 +12,7 @@ env logic on the host, and nothing falls back to a CPU implementation.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -61,6 +62,9 @@ class OvercookedVecEnv:
         a = self.arglist
         self.lib = lib if lib is not None else _cabi.default_library()
         self.device = torch.device(device)
+        if self.lib.prefix != "oc_" and os.environ.get("OC_TEST_EMULATION") != "1":
+            raise RuntimeError("only liboc_b200.so (CUDA) is a product backend; the host emulation of the device "
+                               "code is a test aid and needs OC_TEST_EMULATION=1 (set by tests/parity_util.py)")
         if self.lib.prefix == "oc_":
             if self.device.type != "cuda":
                 raise RuntimeError("OvercookedVecEnv runs on a CUDA device only (no CPU fallback)")

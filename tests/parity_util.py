@@ -27,6 +27,7 @@ def emu_library():
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I" + EMU_DIR,
                                os.path.join(EMU_DIR, "oc_emu.cpp"), "-o", so])
+    os.environ["OC_TEST_EMULATION"] = "1"          # the product refuses non-CUDA backends without this
     return _cabi.OcLibrary(so, prefix="emu_")
 
 

@@ -52,3 +52,14 @@ def test_no_cpu_fallback(lib):
         OvercookedVecEnv(ns, num_envs=4, device="cuda")
     with pytest.raises(RuntimeError):
         OvercookedVecEnv(ns, num_envs=4, device="cpu")
+
+
+def test_emulation_backend_is_refused_outside_tests(monkeypatch):
+    import argparse
+    from gym_comm_b200.vec_env import OvercookedVecEnv
+    from tests.parity_util import emu_library
+    emu = emu_library()
+    monkeypatch.delenv("OC_TEST_EMULATION", raising=False)
+    ns = argparse.Namespace(level="open-divider_tomato", num_agents=2, max_num_timesteps=100)
+    with pytest.raises(RuntimeError):
+        OvercookedVecEnv(ns, num_envs=4, device="cpu", lib=emu)

@@ -1,4 +1,5 @@
-import sys, argparse
+import sys, argparse, os
+os.environ['OC_TEST_EMULATION'] = '1'
 sys.path.insert(0, '/root/repo')
 import numpy as np, torch
 from gym_comm_b200 import _cabi
