@@ -38,6 +38,7 @@ def main(argv=None):
     ap.add_argument("--log-every", type=int, default=10)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--device", default="cuda:0")
+    ap.add_argument("--eval-steps", type=int, default=0, help="after training: deterministic evaluation for this many steps")
     ap.add_argument("--save", default=None, help="path to save the two policies (torch.save)")
     args = ap.parse_args(argv)
 
@@ -76,6 +77,23 @@ def main(argv=None):
                         ego_loss=stats, partner_updates=partner.iteration)
             history.append(line)
             print(json.dumps(line), flush=True)
+    if args.eval_steps > 0:
+        # tester.py-style evaluation (tester.py:72-106): deterministic (argmax) actions, no learning
+        obs = penv.reset()
+        penv.pop_episode_stats()
+
+        class _Frozen:                      # partner with the same policy, recording nothing
+            def get_action(self, o, record=True):
+                return partner.model.policy.act(o, deterministic=True)[0]
+
+            def update(self, r, d):
+                pass
+        penv.add_partner_agent(_Frozen())
+        for _ in range(args.eval_steps):
+            obs, _, _ = penv.step(ego.policy.act(obs, deterministic=True)[0].to(torch.int32))
+        ev = penv.pop_episode_stats()
+        print(json.dumps(dict(eval=True, steps=args.eval_steps, **ev)), flush=True)
+        history.append(dict(eval=True, **ev))
     if args.save:
         torch.save({"ego": ego.policy.state_dict(), "partner": partner.model.policy.state_dict(),
                     "config": vars(ns)}, args.save)
