@@ -1,0 +1,91 @@
+"""Host logic of `OvercookedVecEnv` / `PantheonVecEnv` / `SB3VecEnvAdapter` exercised on CPU through the
+test-only emulation backend (tests/emu): argument validation, views, statistics, state decode.
+(Parity of the results is the GPU tests' job; this covers the Python plumbing without a GPU.)"""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+from gym_comm_b200.pantheon import PantheonVecEnv, SB3VecEnvAdapter
+from gym_comm_b200.vec_env import OvercookedVecEnv
+from tests.parity_util import emu_library
+
+D = dict(CAN_MOVE=True, ALLERGIC=False, BLIND=False)
+
+
+def make(E=5, T=6, **kw):
+    ns = argparse.Namespace(level="open-divider_tomato", num_agents=2, max_num_timesteps=T, communication_on=True,
+                            num_communication=4, ego_led=False, fow_radius=2, ego_config=D, partner_config=D)
+    return OvercookedVecEnv(ns, num_envs=E, device="cpu", lib=emu_library(), **kw)
+
+
+def test_spaces_layout_and_views():
+    env = make()
+    assert env.obs_width == 23 + 3 + 2 * 4 and env.action_space.nvec.tolist() == [4, 4]
+    assert list(env.observation_space.spaces) == sorted(env.observation_space.spaces)      # gym sorts Dict keys
+    obs = env.reset()
+    views = env.obs_dict(obs)
+    assert sum(v.shape[-1] for v in views.values()) == env.obs_width
+    assert views["agent1_comm"].data_ptr() == obs.data_ptr()                                # zero-copy
+    assert torch.all(views["agent1_comm"][..., 0] == 1) and torch.all(views["timestep"] == 0)
+    assert views["agent1_location"][0, 0].tolist() == [2.0, 1.0] and views["agent2_location"][0, 0].tolist() == [4.0, 1.0]
+    env.close()
+
+
+def test_argument_validation():
+    env = make()
+    a = torch.zeros((5, 2, 2), dtype=torch.int32)
+    with pytest.raises(ValueError):
+        env.step(a.to(torch.int64))
+    with pytest.raises(ValueError):
+        env.step(a[:4])
+    with pytest.raises(ValueError):
+        env.step(a.transpose(0, 1).contiguous().transpose(0, 1))       # right shape, wrong strides
+    with pytest.raises(ValueError):
+        env.step(a, obs_out=torch.zeros((5, 2, env.obs_width + 1)))
+    with pytest.raises(ValueError):
+        env.reset(mask=torch.zeros(5, dtype=torch.bool))
+    with pytest.raises(ValueError):
+        env.rollout(3, rew_out=torch.zeros((2, 5, 2)))
+    env.close()
+
+
+def test_stats_decode_and_render():
+    env = make(E=3, T=4)
+    a = torch.zeros((3, 2, 2), dtype=torch.int32)
+    a[:, 0, 0] = 3
+    for _ in range(4):
+        obs, rew, done = env.step(a)
+    assert done.tolist() == [1, 1, 1]                       # time limit, auto-reset happened
+    st = env.stats()
+    assert st["episodes"].tolist() == [1, 1, 1] and st["num_completed_subtasks"].tolist() == [0, 0, 0]
+    dec = env.decode_state()
+    assert dec["t"].tolist() == [0, 0, 0] and dec["agent_x"][0].tolist() == [2, 4]
+    assert (dec["obj_contents"][0] != 0).sum() == 4
+    pic = env.render(0).split("\n")
+    assert len(pic) == 7 and pic[1].startswith("/   0   1")
+    env.close()
+
+
+def test_pantheon_and_sb3_plumbing():
+    class Partner:
+        def get_action(self, obs, record=True):
+            return torch.zeros((obs.shape[0], 2), dtype=torch.int32)
+
+        def update(self, r, d):
+            self.last = (r.clone(), d.clone())
+
+    penv = PantheonVecEnv(make(E=4, T=3), Partner())
+    venv = SB3VecEnvAdapter(penv)
+    o = venv.reset()
+    assert o.shape == (4, penv.obs_dim) and o.dtype == np.float32
+    for t in range(3):
+        o, r, d, infos = venv.step(np.zeros((4, 2), dtype=np.int64))
+    assert d.all() and all("terminal_observation" in i for i in infos)
+    assert penv.pop_episode_stats()["episodes"] == 4
+    with pytest.raises(ValueError):
+        PantheonVecEnv(make(auto_reset=False), Partner())
+    with pytest.raises(AttributeError):
+        venv.set_attr("x", 1)
+    venv.close()
