@@ -29,6 +29,7 @@ struct Tables {
     const double*   q;        // q[n] = n / MAX_PATH as the reference's Python float (f64)
     const uint32_t* tmlut;    // [128] object signature -> bitmask of subtasks whose goal template it equals
     const float2*   xyf;      // [ncell] (x, y) of a cell as floats (only ever indexed with live cells)
+    const float*    ts;       // [T+1] float32(t / T) when small enough for shared memory (else nullptr)
     const uint16_t* mvt;      // [ncell*4] inbounds(cell + NAV[a]) | tile(target) << 8     world.py:317-320
     const uint16_t* xy16;     // [ncell] x | y << 8
     const uint8_t*  dmin;     // [ncell] min over Delivery tiles of pd + manhattan   overcooked_environment.py:383-388
@@ -48,6 +49,7 @@ __device__ __forceinline__ Tables make_tables(const OcParams& p, const uint8_t* 
     t.counters = smem + p.o_counters;
     t.pd = smem + p.o_pd;
     t.pdm = smem + p.o_pdm;
+    t.ts = (p.o_ts >= 0) ? reinterpret_cast<const float*>(smem + p.o_ts) : nullptr;
     return t;
 }
 
@@ -651,7 +653,11 @@ __device__ __forceinline__ void thread_expand_row(const OcParams& p, const uint8
 template <int A, int NOBJ, bool ROWF>
 __device__ __forceinline__ float finish_obs(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
                                             const Info& in, uint8_t* myrow) {
-    const float ts = __ldg(p.ts_table + (e.w0 & 0xFFFFu));
+    // timestep = float32(t / max_num_timesteps) (overcooked_env.py:146): from the shared-memory copy of
+    // the table when it fits -- a global load here would queue behind this warp's own obs stores --
+    // else computed (IEEE f64 division + one rounding, identical to the host table)
+    const uint32_t t = e.w0 & 0xFFFFu;
+    const float ts = (p.o_ts >= 0) ? tb.ts[t] : (float)__ddiv_rn((double)t, (double)p.T);
     if (ROWF) build_rows_f32<A, NOBJ>(e, p, tb, in, ts, reinterpret_cast<float*>(myrow));
     else build_rows_u8<A, NOBJ>(e, p, tb, in, myrow);
     return ts;

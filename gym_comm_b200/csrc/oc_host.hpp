@@ -231,6 +231,8 @@ static inline int compile_config(const oc_config* c, HostImage& h, std::string& 
     p.o_counters = (int)off; off += align_up(std::max<size_t>(counters.size(), 1), 16);
     p.o_pd = (int)off; off += align_up((size_t)n * n, 16);
     p.o_pdm = (int)off; off += align_up((size_t)n * n, 16);
+    p.o_ts = -1;
+    if (ts.size() * 4 <= 4096) { p.o_ts = (int)off; off += align_up(ts.size() * 4, 16); }
     p.blob_bytes = (int)off;
     std::vector<uint8_t>& blob = h.blob; blob.assign(off, 0);
     memcpy(blob.data() + p.o_q, q.data(), q.size() * 8);
@@ -242,6 +244,7 @@ static inline int compile_config(const oc_config* c, HostImage& h, std::string& 
     if (!counters.empty()) memcpy(blob.data() + p.o_counters, counters.data(), counters.size());
     memcpy(blob.data() + p.o_pd, pd.data(), pd.size());
     memcpy(blob.data() + p.o_pdm, pdm.data(), pdm.size());
+    if (p.o_ts >= 0) memcpy(blob.data() + p.o_ts, ts.data(), ts.size() * 4);
     return OC_OK;
 #undef OC_BAD
 }

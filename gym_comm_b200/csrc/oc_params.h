@@ -63,6 +63,6 @@ struct OcParams {
     // table blob (device pointer) and the byte offsets of its sections; copied to smem per CTA
     const uint8_t* blob;
     int32_t blob_bytes;        // multiple of 16
-    int32_t o_q, o_tmlut, o_xyf, o_mvt, o_xy16, o_dmin, o_counters, o_pd, o_pdm;
+    int32_t o_q, o_tmlut, o_xyf, o_mvt, o_xy16, o_dmin, o_counters, o_pd, o_pdm, o_ts /* -1: timestep table not in the blob */;
     const float* ts_table;     // [T+1] float32(t / T)   (overcooked_env.py:146)
 };

@@ -32,6 +32,7 @@ static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t s) {
 static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static inline float __saturatef(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
 static inline float __fmaf_rn(float a, float b, float c) { return __builtin_fmaf(a, b, c); }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
 template <typename T> static inline T __ldg(const T* p) { return *p; }

@@ -35,6 +35,9 @@ CONFIGS = {
                  num_communication=100, ego_led=False, fow_radius=2, ego_config=DEF, partner_config=DEF),
     "tl3_oddrow": dict(level="open-divider_tl", num_agents=3, max_num_timesteps=200, communication_on=True,
                        num_communication=5, ego_led=True, fow_radius=3, ego_config=DEF, partner_config=DEF),
+    # T > 1023: the timestep table no longer fits the shared-memory blob -> computed with an f64 division
+    "longT": dict(level="open-divider_tomato", num_agents=2, max_num_timesteps=3001, communication_on=True,
+                  num_communication=10, ego_led=False, fow_radius=2, ego_config=DEF, partner_config=DEF),
     "salad4_commoff": dict(level="open-divider_salad", num_agents=4, max_num_timesteps=150, communication_on=False,
                            num_communication=7, ego_led=False, fow_radius=1, ego_config=DEF, partner_config=DEF),
 }
@@ -116,7 +119,7 @@ def test_goal_chasing_streams_vs_python_oracle(name):
 
 
 @pytest.mark.parametrize("name,E,T", [("cfg2", 65536, 1100), ("cfg3", 262144, 120), ("cfg4", 65536, 1000),
-                                      ("cfg5", 131072, 60), ("tl3_oddrow", 4099, 450)])
+                                      ("cfg5", 131072, 60), ("tl3_oddrow", 4099, 450), ("longT", 2000, 3100)])
 def test_random_streams_autoreset_vs_c_oracle(name, E, T):
     """BASELINE.json env counts; uniform random actions; auto-reset on the device (random levels
     draw their placements from the shared Philox spec); every step: f64 reward, done, and all
