@@ -50,6 +50,19 @@ Salad
 4 5
 """
 
+ONION_LEVEL = """--/--*-
+t     l
+-     o
+/     p
+---p-p-
+
+OnionSalad
+
+1 1
+5 1
+3 2
+"""
+
 SCENARIOS = [
     # name, level, steps, kwargs
     ("tomato_a9_script", "open-divider_tomato", 0, dict(num_communication=5, max_num_timesteps=500, script="a9")),
@@ -79,6 +92,8 @@ SCENARIOS = [
                                             level_text=random_level(1003))),
     ("fuzz_kitchen_b", "fuzz-b", 400, dict(num_agents=3, max_num_timesteps=80, num_communication=6, fow_radius=2,
                                             level_text=random_level(1008, 3))),
+    # three Foods, 29 subtasks, 6 shaping item pairs
+    ("onion_salad_2a", "onion-salad", 900, dict(max_num_timesteps=250, num_communication=6, level_text=ONION_LEVEL)),
     ("fuzz_kitchen_c", "fuzz-c", 400, dict(max_num_timesteps=100, num_communication=7, fow_radius=3, ego_led=True,
                                             level_text=random_level(1011))),
 ]
