@@ -88,8 +88,16 @@ struct Env {
 };
 
 template <int A, int NOBJ>
+__device__ __forceinline__ void unpack_env(Env<A, NOBJ>& e, const uint4 a, const uint4 b, const uint4 c, const uint4 d);
+
+template <int A, int NOBJ>
 __device__ __forceinline__ void load_env(Env<A, NOBJ>& e, const uint4* __restrict__ st, int E, int i) {
-    const uint4 a = st[i], b = st[E + i], c = st[2 * E + i], d = st[3 * E + i];
+    unpack_env<A, NOBJ>(e, st[i], st[E + i], st[2 * E + i], st[3 * E + i]);
+}
+
+// the four 16-byte state planes of one env -> fields
+template <int A, int NOBJ>
+__device__ __forceinline__ void unpack_env(Env<A, NOBJ>& e, const uint4 a, const uint4 b, const uint4 c, const uint4 d) {
     e.w0 = a.x; e.episodes = a.y; e.completed = a.z; e.countbits = a.w;
 #pragma unroll
     for (int k = 0; k < A; ++k) e.acell[k] = (b.x >> (8 * k)) & 0xFF;
@@ -482,47 +490,47 @@ __device__ __forceinline__ void build_rows_f32(const Env<A, NOBJ>& e, const OcPa
     }
 }
 
+// one observer's row as biased bytes (r = F bytes, 0x80-filled)
 template <int A, int NOBJ>
-__device__ __forceinline__ void build_rows_u8(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
-                                              const Info& in, uint8_t* __restrict__ row /* 0x80-filled */) {
+__device__ __forceinline__ void build_row_u8_one(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
+                                                 const Info& in, int k, uint8_t* __restrict__ r) {
     const uint32_t xy0 = tb.xy16[e.acell[0]], xy1 = tb.xy16[e.acell[1]];
     const uint32_t c0 = e.comm & 0xFFFFu, c1 = e.comm >> 16;
     const float fow = (float)p.fow;
+    const bool blind = p.blind[k] != 0;
+    if (c0 != OCK_COMM_NONE) r[p.off_a1comm + c0] = OCK_BIAS + 1;
+    if (c1 != OCK_COMM_NONE) r[p.off_a2comm + c1] = OCK_BIAS + 1;
+    if (!blind) {
+        r[p.off_a1loc] = OCK_BIAS + (xy0 & 0xFF);  r[p.off_a1loc + 1] = OCK_BIAS + (xy0 >> 8);
+        r[p.off_a2loc] = OCK_BIAS + (xy1 & 0xFF);  r[p.off_a2loc + 1] = OCK_BIAS + (xy1 >> 8);
+    }
+    if (!p.ego_blind && ((in.holdmask >> k) & 1u)) r[p.off_hold] = OCK_BIAS + 1;
+    if (blind) {
 #pragma unroll
-    for (int k = 0; k < A; ++k) {
-        uint8_t* r = row + k * p.F;
-        const bool blind = p.blind[k] != 0;
-        if (c0 != OCK_COMM_NONE) r[p.off_a1comm + c0] = OCK_BIAS + 1;
-        if (c1 != OCK_COMM_NONE) r[p.off_a2comm + c1] = OCK_BIAS + 1;
-        if (!blind) {
-            r[p.off_a1loc] = OCK_BIAS + (xy0 & 0xFF);  r[p.off_a1loc + 1] = OCK_BIAS + (xy0 >> 8);
-            r[p.off_a2loc] = OCK_BIAS + (xy1 & 0xFF);  r[p.off_a2loc + 1] = OCK_BIAS + (xy1 >> 8);
-        }
-        if (!p.ego_blind && ((in.holdmask >> k) & 1u)) r[p.off_hold] = OCK_BIAS + 1;
-        if (blind) {
+        for (int c = 0; c < 4; ++c) r[p.off_hidden + c] = OCK_BIAS + 1;
+    } else {
+        const float2 me = tb.xyf[e.acell[k]];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) r[p.off_hidden + c] = OCK_BIAS + 1;
-        } else {
-            const float2 me = tb.xyf[e.acell[k]];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const uint32_t w = (c < 3) ? in.fword[c] : in.pword;
-                if (obj_alive(w)) {
-                    float hid, ex, ey, st;
-                    channel_features(tb, w, me, fow, c, hid, ex, ey, st);
-                    r[p.off_hidden + c] = (uint8_t)(OCK_BIAS + (int)hid);
-                    r[p.off_encx + c] = (uint8_t)(OCK_BIAS + (int)ex);
-                    r[p.off_ency + c] = (uint8_t)(OCK_BIAS + (int)ey);
-                    if (c < 3) r[p.off_state + c] = (uint8_t)(OCK_BIAS + (int)st);
-                }
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t w = (c < 3) ? in.fword[c] : in.pword;
+            if (obj_alive(w)) {
+                float hid, ex, ey, st;
+                channel_features(tb, w, me, fow, c, hid, ex, ey, st);
+                r[p.off_hidden + c] = (uint8_t)(OCK_BIAS + (int)hid);
+                r[p.off_encx + c] = (uint8_t)(OCK_BIAS + (int)ex);
+                r[p.off_ency + c] = (uint8_t)(OCK_BIAS + (int)ey);
+                if (c < 3) r[p.off_state + c] = (uint8_t)(OCK_BIAS + (int)st);
             }
         }
     }
-    for (uint32_t m = e.completed; m != 0; m &= m - 1) {
-        uint8_t* r = row + p.off_completed + (__ffs((int)m) - 1);
+    for (uint32_t m = e.completed; m != 0; m &= m - 1) r[p.off_completed + (__ffs((int)m) - 1)] = OCK_BIAS + 1;
+}
+
+template <int A, int NOBJ>
+__device__ __forceinline__ void build_rows_u8(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
+                                              const Info& in, uint8_t* __restrict__ row /* 0x80-filled */) {
 #pragma unroll
-        for (int k = 0; k < A; ++k) r[k * p.F] = OCK_BIAS + 1;
-    }
+    for (int k = 0; k < A; ++k) build_row_u8_one<A, NOBJ>(e, p, tb, in, k, row + k * p.F);
 }
 
 // warp-cooperative fill of the warp's 32 rows with the "all features 0.0" pattern
@@ -555,10 +563,11 @@ __device__ __forceinline__ void rows_wait_read(const OcParams& p) {
 #endif
     __syncwarp();
 }
-// before the kernel exits: all bulk stores complete
+// before the CTA exits: the copy engine must have read the rows out of its shared memory; the
+// global writes themselves complete, like any store, by the end of the grid
 __device__ __forceinline__ void rows_wait_done(const OcParams& p) {
 #ifndef OCK_HOST_EMU
-    if (p.use_tma) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (p.use_tma) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 #endif
 }
 
@@ -629,50 +638,99 @@ __device__ __forceinline__ void warp_expand_rows(const OcParams& p, const uint8_
     }
 }
 
+// timestep = float32(t / max_num_timesteps) (overcooked_env.py:146): from the shared-memory copy of the
+// table when it fits -- a global load here would queue behind this warp's own obs stores -- else
+// computed (IEEE f64 division + one rounding, identical to the host table)
+template <int A, int NOBJ>
+__device__ __forceinline__ float timestep_of(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb) {
+    const uint32_t t = e.w0 & 0xFFFFu;
+    return (p.o_ts >= 0) ? tb.ts[t] : (float)__ddiv_rn((double)t, (double)p.T);
+}
+
+template <int A, int NOBJ, bool ROWF>
+__device__ __forceinline__ void fill_rows(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
+                                          const Info& in, float ts, uint8_t* myrow) {
+    if (ROWF) build_rows_f32<A, NOBJ>(e, p, tb, in, ts, reinterpret_cast<float*>(myrow));
+    else build_rows_u8<A, NOBJ>(e, p, tb, in, myrow);
+}
+
 // byte rows only: after the expansion (and a __syncwarp) each thread stores the timestep feature
-// of its own env rows, timestep = float32(t / max_num_timesteps)  (overcooked_env.py:146)
+// of its own env rows (the byte rows carry 0.0 there)
 template <int A>
 __device__ __forceinline__ void store_timesteps(const OcParams& p, float* __restrict__ env_row, float ts) {
 #pragma unroll
     for (int k = 0; k < A; ++k) env_row[k * p.F + p.off_ts] = ts;
 }
 
-// a single thread expands its own row (rare path: terminal observations)
-template <bool ROWF>
-__device__ __forceinline__ void thread_expand_row(const OcParams& p, const uint8_t* __restrict__ row, float ts,
-                                                  float* __restrict__ out) {
-    if (ROWF) {
-        for (int j = 0; j < p.row_bytes; ++j) out[j] = reinterpret_cast<const float*>(row)[j];
-    } else {
-        for (int j = 0; j < p.row_bytes; ++j) out[j] = (float)((int)row[j] - 128);
-        for (int k = 0; k < p.A; ++k) out[k * p.F + p.off_ts] = ts;
+// ---- observation emission of one warp's 32 envs.  The warp's row buffer holds p.nb env rows
+// (32, or 16 / 8 for wide float rows, so that enough warps stay resident); the envs go out in
+// 32 / nb passes, lanes [pass * nb, pass * nb + nb) filling the buffer in their pass.  Rows must be
+// clear (and, with bulk stores, read out) on entry; they are dirty on exit.
+template <int A, int NOBJ, int MODE /* 0 byte rows, 1 float rows, 2 float rows in several passes */>
+__device__ __forceinline__ void emit_obs(const Env<A, NOBJ>& e, const Info& in, bool valid, const OcParams& p,
+                                         const Tables& tb, uint8_t* wrows, int lane,
+                                         float* __restrict__ out_env0 /* warp's first env row */, int nvalid) {
+    constexpr bool ROWF = MODE != 0;
+    constexpr bool MULTI = MODE == 2;               // compile-time: e / in stay live across passes only here
+    uint8_t* myrow = wrows + (MULTI ? (lane & (p.nb - 1)) : lane) * p.row_stride;
+    const float ts = valid ? timestep_of<A, NOBJ>(e, p, tb) : 0.0f;
+    const int passes = MULTI ? p.obs_passes : 1;
+    for (int pass = 0; pass < passes; ++pass) {
+        if (pass > 0) {
+            rows_wait_read(p);
+            warp_clear_rows<ROWF>(wrows, p.warp_row_bytes, lane);
+            __syncwarp();
+        }
+        if (valid && (!MULTI || (lane >> p.nb_shift) == pass)) fill_rows<A, NOBJ, ROWF>(e, p, tb, in, ts, myrow);
+        __syncwarp();
+        const int first = MULTI ? (pass << p.nb_shift) : 0;
+        const int nv = min(MULTI ? p.nb : 32, nvalid - first);
+        if (nv > 0) warp_expand_rows<ROWF>(p, wrows, out_env0 + (size_t)first * p.row_bytes, nv, lane);
+    }
+    if (!ROWF) {                                    // byte rows are never split into passes
+        __syncwarp();                               // orders the float4 stores before the timestep patch
+        if (valid) store_timesteps<A>(p, out_env0 + (size_t)lane * p.row_bytes, ts);
     }
 }
 
-// observation of the env as it stands: fills this thread's row, returns the timestep float
+// a single thread emits its own env's rows (rare path: terminal observations); its row must be
+// clear on entry and is clear again on exit
 template <int A, int NOBJ, bool ROWF>
-__device__ __forceinline__ float finish_obs(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
-                                            const Info& in, uint8_t* myrow) {
-    // timestep = float32(t / max_num_timesteps) (overcooked_env.py:146): from the shared-memory copy of
-    // the table when it fits -- a global load here would queue behind this warp's own obs stores --
-    // else computed (IEEE f64 division + one rounding, identical to the host table)
-    const uint32_t t = e.w0 & 0xFFFFu;
-    const float ts = (p.o_ts >= 0) ? tb.ts[t] : (float)__ddiv_rn((double)t, (double)p.T);
-    if (ROWF) build_rows_f32<A, NOBJ>(e, p, tb, in, ts, reinterpret_cast<float*>(myrow));
-    else build_rows_u8<A, NOBJ>(e, p, tb, in, myrow);
-    return ts;
+__device__ __forceinline__ void thread_emit_rows(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
+                                                 const Info& in, uint8_t* myrow, float* __restrict__ out) {
+    const float ts = timestep_of<A, NOBJ>(e, p, tb);
+    fill_rows<A, NOBJ, ROWF>(e, p, tb, in, ts, myrow);
+    if (ROWF) {
+        for (int j = 0; j < p.row_bytes; ++j) out[j] = reinterpret_cast<const float*>(myrow)[j];
+    } else {
+        for (int j = 0; j < p.row_bytes; ++j) out[j] = (float)((int)myrow[j] - 128);
+        store_timesteps<A>(p, out, ts);
+    }
+    const uint32_t z = ROWF ? 0u : 0x80808080u;
+    for (int j = 0; j < (p.row_stride >> 2); ++j) reinterpret_cast<uint32_t*>(myrow)[j] = z;
+}
+
+// infos["terminal_observation"] of the envs of this warp that just finished (SB3 VecEnv contract);
+// lanes that share a row slot (nb < 32) take turns.  Rows must be clear; they stay clear.
+template <int A, int NOBJ, int MODE>
+__device__ __forceinline__ void warp_terminal_obs(const Env<A, NOBJ>& e, const Info& in, bool fin, const OcParams& p,
+                                                  const Tables& tb, uint8_t* wrows, int lane,
+                                                  float* __restrict__ term_row) {
+    constexpr bool ROWF = MODE != 0;
+    if (MODE != 2) {
+        if (fin) thread_emit_rows<A, NOBJ, ROWF>(e, p, tb, in, wrows + lane * p.row_stride, term_row);
+        return;
+    }
+    uint8_t* myrow = wrows + (lane & (p.nb - 1)) * p.row_stride;
+    for (int pass = 0; pass < p.obs_passes; ++pass) {
+        if (fin && (lane >> p.nb_shift) == pass) thread_emit_rows<A, NOBJ, ROWF>(e, p, tb, in, myrow, term_row);
+        __syncwarp();
+    }
 }
 
 // terminal bookkeeping + in-place reset of one finished env (SB3 VecEnv auto-reset contract)
-template <int A, int NOBJ, bool ROWF>
-__device__ __forceinline__ void finish_episode(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb, const Info& in,
-                                               uint8_t* myrow, float* __restrict__ term_row, uint32_t env_id) {
-    if (term_row != nullptr) {                       // infos["terminal_observation"]
-        const float ts = finish_obs<A, NOBJ, ROWF>(e, p, tb, in, myrow);
-        thread_expand_row<ROWF>(p, myrow, ts, term_row);
-        const uint32_t z = ROWF ? 0u : 0x80808080u;
-        for (int j = 0; j < (p.row_stride >> 2); ++j) reinterpret_cast<uint32_t*>(myrow)[j] = z;
-    }
+template <int A, int NOBJ>
+__device__ __forceinline__ void finish_episode(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb, uint32_t env_id) {
     e.w5 = (e.w5 & ~0xFFu) | (uint32_t)__popc(e.completed);    // episode_recorder.py:29
     e.episodes += 1;
     env_reset<A, NOBJ>(e, p, tb, nullptr, env_id);
@@ -697,30 +755,6 @@ __device__ __forceinline__ Info step_logic(Env<A, NOBJ>& e, const OcParams& p, c
     }
     done_out[env] = done ? 1 : 0;
     return in;
-}
-
-// oc_step, part 2: auto-reset (with the optional terminal observation) and the observation rows
-template <int A, int NOBJ, bool ROWF>
-__device__ __forceinline__ float step_finish(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb, Info in, bool done,
-                                             uint32_t env, uint8_t* myrow, float* __restrict__ term_obs, uint32_t flags) {
-    if (done && (flags & 1u /*OC_FLAG_AUTO_RESET*/)) {
-        finish_episode<A, NOBJ, ROWF>(e, p, tb, in, myrow, term_obs ? term_obs + (size_t)env * p.row_bytes : nullptr, env);
-        in = gather_info<A, NOBJ>(e, p, tb);
-    }
-    return finish_obs<A, NOBJ, ROWF>(e, p, tb, in, myrow);
-}
-
-// both parts in one call (the CPU emulation harness drives this form)
-template <int A, int NOBJ, bool ROWF>
-__device__ __forceinline__ float step_one_env(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
-                                              const int (&nav)[A], int comm0, int comm1, uint32_t env,
-                                              uint8_t* myrow,
-                                              float* __restrict__ rew32, double* __restrict__ rew64,
-                                              uint8_t* __restrict__ done_out, float* __restrict__ term_obs,
-                                              uint32_t flags) {
-    bool done;
-    const Info in = step_logic<A, NOBJ>(e, p, tb, nav, comm0, comm1, env, rew32, rew64, done_out, done);
-    return step_finish<A, NOBJ, ROWF>(e, p, tb, in, done, env, myrow, term_obs, flags);
 }
 
 // one env, one step of the fused synthetic rollout: Philox actions (nav ~ U{0..3}, comm ~ U{0..C-1}),
@@ -762,29 +796,17 @@ __device__ __forceinline__ Info rollout_logic(Env<A, NOBJ>& e, const OcParams& p
     }
     if (done_out != nullptr) done_out[(size_t)s * p.E + env] = done ? 1 : 0;
     if (done) {                                      // no terminal observation in the fused rollout: rows untouched
-        finish_episode<A, NOBJ, ROWF>(e, p, tb, in, nullptr, nullptr, env);
+        finish_episode<A, NOBJ>(e, p, tb, env);
         in = gather_info<A, NOBJ>(e, p, tb);
     }
     return in;
 }
 
-// logic + observation rows in one call (the CPU emulation harness drives this form)
-template <int A, int NOBJ, bool ROWF>
-__device__ __forceinline__ float rollout_one_env(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
-                                                 uint32_t env, uint32_t s, uint32_t step0,
-                                                 uint8_t* myrow, bool want_obs,
-                                                 float* __restrict__ rew32, uint8_t* __restrict__ done_out,
-                                                 int32_t* __restrict__ actions_out) {
-    const Info in = rollout_logic<A, NOBJ, ROWF>(e, p, tb, env, s, step0, rew32, done_out, actions_out);
-    return want_obs ? finish_obs<A, NOBJ, ROWF>(e, p, tb, in, myrow) : 0.0f;
-}
-
 // oc_reset / initial bring-up of one env
-template <int A, int NOBJ, bool ROWF>
-__device__ __forceinline__ float reset_one_env(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb, uint32_t env,
-                                               bool initial, const uint8_t* __restrict__ mask,
-                                               const int32_t* __restrict__ placements, bool want_obs,
-                                               uint8_t* myrow) {
+template <int A, int NOBJ>
+__device__ __forceinline__ void reset_logic(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb, uint32_t env,
+                                            bool initial, const uint8_t* __restrict__ mask,
+                                            const int32_t* __restrict__ placements) {
     const int32_t* pl = placements ? placements + (size_t)env * p.nrandom : nullptr;
     if (initial) {
         e.episodes = 0; e.w5 = 0; e.w15 = 0;
@@ -794,9 +816,6 @@ __device__ __forceinline__ float reset_one_env(Env<A, NOBJ>& e, const OcParams& 
         e.episodes += 1;
         env_reset<A, NOBJ>(e, p, tb, pl, env);
     }
-    if (!want_obs) return 0.0f;
-    const Info in = gather_info<A, NOBJ>(e, p, tb);
-    return finish_obs<A, NOBJ, ROWF>(e, p, tb, in, myrow);
 }
 
 }  // namespace ock

@@ -106,17 +106,37 @@ static inline int compile_config(const oc_config* c, HostImage& h, std::string& 
     // and the expansion needs no index arithmetic at all
     p.row_stride = (int)align_up(p.row_bytes, 4);
     if (((p.row_stride >> 2) & 1) == 0) p.row_stride += 4;
-    // float rows when a warp's 32 rows stay small (<= 24 KB) and rows are 16-byte multiples
-    p.rowf = ((p.row_bytes & 3) == 0 && 32 * p.row_bytes * 4 <= 24 * 1024) ? 1 : 0;
-    if (const char* f = getenv("OC_ROW_FORMAT")) p.rowf = (f[0] == 'f' && (p.row_bytes & 3) == 0) ? 1 : 0;
+    // float rows (bulk-stored by the copy engine) when rows are 16-byte multiples and a warp's buffer stays
+    // small: all 32 env rows when they fit in 24 KB, else 16 or 8 rows (<= 30 KB) emitted in 2 / 4 passes
+    p.nb = 32;
+    p.rowf = 0;
+    if ((p.row_bytes & 3) == 0) {
+        if (32 * p.row_bytes * 4 <= 24 * 1024) p.rowf = 1;
+        else for (int nb = 16; nb >= 8 && !p.rowf; nb >>= 1)
+            if (nb * p.row_bytes * 4 <= 30 * 1024) { p.rowf = 1; p.nb = nb; }
+    }
+    if (const char* f = getenv("OC_ROW_FORMAT")) {
+        if (f[0] != 'f') { p.rowf = 0; p.nb = 32; }
+        else if ((p.row_bytes & 3) == 0) p.rowf = 1;
+    }
+    if (const char* o = getenv("OC_ROW_ENVS")) {
+        const int nb = atoi(o);
+        if (p.rowf && (nb == 32 || nb == 16 || nb == 8 || nb == 4)) p.nb = nb;
+    }
     // float rows stay 16-byte aligned, so the best the per-thread scatter can do is a stride of
     // 4 (mod 8) words (8 distinct banks, 4-way conflict); a multiple of 8 words would put all 32 lanes
     // on 1-4 banks (cfg4: 96 floats -> 32-way), so such rows get 4 floats of padding
-    if (p.rowf) p.row_stride = (p.row_bytes + ((p.row_bytes & 7) == 0 ? 4 : 0)) * 4;
-    // 1: one bulk copy per warp (contiguous rows).  Padded rows would need 32 small copies per warp: that
+    // (multi-pass rows stay contiguous: one bulk copy per pass measured faster than conflict-free fills)
+    bool pad = (p.row_bytes & 7) == 0 && p.nb == 32;
+    if (const char* o = getenv("OC_ROW_PAD")) pad = pad && atoi(o) != 0;
+    if (p.rowf) p.row_stride = (p.row_bytes + (pad ? 4 : 0)) * 4;
+    // 1: one bulk copy per pass (contiguous rows).  Padded rows would need one small copy per row: that
     // measured slower in the fused rollout but faster in the single-step kernel, which sets 2 itself.
     p.use_tma = (p.rowf && p.row_stride == p.row_bytes * 4) ? 1 : 0;
     if (const char* t = getenv("OC_TMA")) p.use_tma = (p.use_tma && atoi(t) != 0) ? 1 : 0;
+    p.nb_shift = p.nb == 32 ? 5 : p.nb == 16 ? 4 : p.nb == 8 ? 3 : 2;
+    p.obs_passes = 32 / p.nb;
+    p.warp_row_bytes = p.nb * p.row_stride;
     p.r4_magic = (p.row_bytes >= 4) ? (uint32_t)((1ull << 32) / (uint64_t)(p.row_bytes >> 2)) + 1u : 0u;
     p.rf_magic = (uint32_t)((1ull << 32) / (uint64_t)p.row_bytes) + 1u;
     for (int k = 0; k < OC_MAX_AGENTS; ++k) {

@@ -21,12 +21,13 @@ using namespace ock;
 // =============================================================================================
 
 // dynamic shared memory: [table blob][per warp: 32 byte-rows]
-template <int A, int NOBJ, bool ROWF>
+template <int A, int NOBJ, int MODE>
 __global__ void __launch_bounds__(256)
 oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
                const int32_t* __restrict__ actions, float* __restrict__ obs,
                float* __restrict__ rew32, double* __restrict__ rew64, uint8_t* __restrict__ done_out,
                float* __restrict__ term_obs, uint32_t flags) {
+    constexpr bool ROWF = MODE != 0;
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -36,9 +37,8 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
     // actions).  Both instructions are no-ops when the launch carries no PDL attribute.
     asm volatile("griddepcontrol.launch_dependents;");
     load_tables(p, smem);
-    uint8_t* wrows = smem + p.blob_bytes + (size_t)warp * 32 * p.row_stride;
-    uint8_t* myrow = wrows + lane * p.row_stride;
-    warp_clear_rows<ROWF>(wrows, 32 * p.row_stride, lane);
+    uint8_t* wrows = smem + p.blob_bytes + (size_t)warp * p.warp_row_bytes;
+    warp_clear_rows<ROWF>(wrows, p.warp_row_bytes, lane);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
     const Tables tb = make_tables(p, smem);
@@ -62,42 +62,41 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
         }
         if (!first) {                                   // rows of the previous chunk: read out, then clear
             rows_wait_read(p);
-            warp_clear_rows<ROWF>(wrows, 32 * p.row_stride, lane);
+            warp_clear_rows<ROWF>(wrows, p.warp_row_bytes, lane);
             __syncwarp();
         }
         first = false;
-        float ts = 0.0f;
-        if (valid) {
-            ts = step_finish<A, NOBJ, ROWF>(e, p, tb, in, done, (uint32_t)env, myrow, term_obs, flags);
-            store_env<A, NOBJ>(e, state, p.E, env);
+        const bool fin = valid && done && (flags & OC_FLAG_AUTO_RESET);
+        if (term_obs != nullptr && __any_sync(0xFFFFFFFFu, fin))      // rare: some env of this warp finished
+            warp_terminal_obs<A, NOBJ, MODE>(e, in, fin, p, tb, wrows, lane, term_obs + (size_t)env * p.row_bytes);
+        if (fin) {
+            finish_episode<A, NOBJ>(e, p, tb, (uint32_t)env);
+            in = gather_info<A, NOBJ>(e, p, tb);
         }
-        __syncwarp();
+        if (valid) store_env<A, NOBJ>(e, state, p.E, env);
         const int env0 = base + warp * 32;
-        const int nvalid = min(32, p.E - env0);
-        if (nvalid > 0) warp_expand_rows<ROWF>(p, wrows, obs + (size_t)env0 * p.row_bytes, nvalid, lane);
-        __syncwarp();                               // order the float4 stores before the timestep patch
-        if (!ROWF && valid) store_timesteps<A>(p, obs + (size_t)env * p.row_bytes, ts);
+        emit_obs<A, NOBJ, MODE>(e, in, valid, p, tb, wrows, lane, obs + (size_t)env0 * p.row_bytes, min(32, p.E - env0));
     }
     rows_wait_done(p);
 }
 
 // n_steps steps per launch, state in registers, Philox actions (SURVEY section 8d synthetic inputs)
-template <int A, int NOBJ, bool ROWF>
+template <int A, int NOBJ, int MODE>
 __global__ void __launch_bounds__(256)
 oc_rollout_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, int n_steps, uint32_t step0,
                   float* __restrict__ obs, float* __restrict__ rew32, uint8_t* __restrict__ done_out,
                   int32_t* __restrict__ actions_out, const int32_t* __restrict__ actions_in) {
+    constexpr bool ROWF = MODE != 0;
     extern __shared__ __align__(16) uint8_t smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = env < p.E;
     Env<A, NOBJ> e;
     if (valid) load_env<A, NOBJ>(e, state, p.E, env);
     load_tables(p, smem);
-    uint8_t* wrows = smem + p.blob_bytes + (size_t)warp * 32 * p.row_stride;
+    uint8_t* wrows = smem + p.blob_bytes + (size_t)warp * p.warp_row_bytes;
     __syncthreads();
     const Tables tb = make_tables(p, smem);
-    uint8_t* myrow = wrows + lane * p.row_stride;
     const int env0 = blockIdx.x * blockDim.x + warp * 32;
     const int nvalid = min(32, p.E - env0);
     const size_t step_floats = (size_t)p.E * p.row_bytes;
@@ -109,15 +108,10 @@ oc_rollout_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
         if (valid) in = rollout_logic<A, NOBJ, ROWF>(e, p, tb, (uint32_t)env, (uint32_t)s, step0, rew32, done_out, actions_out, actions_in);
         if (obs != nullptr) {
             if (s > 0) rows_wait_read(p);
-            warp_clear_rows<ROWF>(wrows, 32 * p.row_stride, lane);
+            warp_clear_rows<ROWF>(wrows, p.warp_row_bytes, lane);
             __syncwarp();
-            float ts = 0.0f;
-            if (valid) ts = finish_obs<A, NOBJ, ROWF>(e, p, tb, in, myrow);
-            float* step_obs = obs + (size_t)s * step_floats;
-            __syncwarp();
-            if (nvalid > 0) warp_expand_rows<ROWF>(p, wrows, step_obs + (size_t)env0 * p.row_bytes, nvalid, lane);
-            __syncwarp();
-            if (!ROWF && valid) store_timesteps<A>(p, step_obs + (size_t)env * p.row_bytes, ts);
+            emit_obs<A, NOBJ, MODE>(e, in, valid, p, tb, wrows, lane,
+                                    obs + (size_t)s * step_floats + (size_t)env0 * p.row_bytes, nvalid);
         }
     }
     if (valid) store_env<A, NOBJ>(e, state, p.E, env);
@@ -125,35 +119,31 @@ oc_rollout_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
 }
 
 // reset (masked) + observation of every env
-template <int A, int NOBJ, bool ROWF>
+template <int A, int NOBJ, int MODE>
 __global__ void __launch_bounds__(256)
 oc_reset_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, const uint8_t* __restrict__ mask,
                 const int32_t* __restrict__ placements, float* __restrict__ obs, int initial) {
+    constexpr bool ROWF = MODE != 0;
     extern __shared__ __align__(16) uint8_t smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = env < p.E;
     Env<A, NOBJ> e;
     if (valid && !initial) load_env<A, NOBJ>(e, state, p.E, env);
     load_tables(p, smem);
-    uint8_t* wrows = smem + p.blob_bytes + (size_t)warp * 32 * p.row_stride;
-    warp_clear_rows<ROWF>(wrows, 32 * p.row_stride, lane);
+    uint8_t* wrows = smem + p.blob_bytes + (size_t)warp * p.warp_row_bytes;
+    warp_clear_rows<ROWF>(wrows, p.warp_row_bytes, lane);
     __syncthreads();
     const Tables tb = make_tables(p, smem);
-    float ts = 0.0f;
+    Info in;
     if (valid) {
-        ts = reset_one_env<A, NOBJ, ROWF>(e, p, tb, (uint32_t)env, initial != 0, mask, placements, obs != nullptr,
-                                    wrows + lane * p.row_stride);
+        reset_logic<A, NOBJ>(e, p, tb, (uint32_t)env, initial != 0, mask, placements);
         store_env<A, NOBJ>(e, state, p.E, env);
+        if (obs != nullptr) in = gather_info<A, NOBJ>(e, p, tb);
     }
-    __syncwarp();
     const int env0 = blockIdx.x * blockDim.x + warp * 32;
-    const int nvalid = min(32, p.E - env0);
-    if (obs != nullptr) {
-        if (nvalid > 0) warp_expand_rows<ROWF>(p, wrows, obs + (size_t)env0 * p.row_bytes, nvalid, lane);
-        __syncwarp();
-        if (!ROWF && valid) store_timesteps<A>(p, obs + (size_t)env * p.row_bytes, ts);
-    }
+    if (obs != nullptr)
+        emit_obs<A, NOBJ, MODE>(e, in, valid, p, tb, wrows, lane, obs + (size_t)env0 * p.row_bytes, min(32, p.E - env0));
     rows_wait_done(p);
 }
 
@@ -206,12 +196,18 @@ struct oc_env {
     int obs_off[OC_NUM_OBS_KEYS], obs_size[OC_NUM_OBS_KEYS];
 };
 
+// kernel template MODE: 0 byte rows, 1 float rows (all 32 envs of a warp in one pass), 2 float rows in passes
+static int row_mode(const OcParams& p) { return !p.rowf ? 0 : (p.obs_passes > 1 ? 2 : 1); }
+
 template <typename F>
-static int dispatch(int A, int NOBJ, int rowf, F&& f) {
-#define OC_CASE(a, n)                                                                                              \
-    if (A == a && NOBJ == n) {                                                                                     \
-        if (rowf) return f(std::integral_constant<int, a>(), std::integral_constant<int, n>(), std::true_type());  \
-        return f(std::integral_constant<int, a>(), std::integral_constant<int, n>(), std::false_type());           \
+static int dispatch(int A, int NOBJ, int mode, F&& f) {
+#define OC_CASE(a, n)                                                                                                   \
+    if (A == a && NOBJ == n) {                                                                                          \
+        using IA = std::integral_constant<int, a>;                                                                      \
+        using IN = std::integral_constant<int, n>;                                                                      \
+        if (mode == 2) return f(IA(), IN(), std::integral_constant<int, 2>());                                          \
+        if (mode == 1) return f(IA(), IN(), std::integral_constant<int, 1>());                                          \
+        return f(IA(), IN(), std::integral_constant<int, 0>());                                                         \
     }
     OC_CASE(2, 4) OC_CASE(3, 4) OC_CASE(4, 4) OC_CASE(2, 6) OC_CASE(3, 6) OC_CASE(4, 6)
 #undef OC_CASE
@@ -244,30 +240,56 @@ extern "C" int oc_create(const oc_config* c, oc_env** out) {
 
     if (const char* pe = getenv("OC_PDL")) h->pdl = atoi(pe) != 0;
     if (const char* te = getenv("OC_TMA")) h->tma_rows_in_step = atoi(te) != 0;
-    // CTA shape: the work is one warp per 32 envs; pick the CTA size whose resident wave
-    // (limited by shared memory: table blob + 32 rows per warp, by 2048 threads and 32 CTAs per
-    // SM) covers the envs with the smallest makespan, preferring fewer table copies on ties.
     cudaDeviceProp prop;
     {
         cudaError_t cep = cudaGetDeviceProperties(&prop, dev);
         if (cep != cudaSuccess) { delete h; return fail(OC_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(cep)); }
     }
     const int num_sm = prop.multiProcessorCount;
-    const size_t smem_sm = prop.sharedMemPerMultiprocessor, smem_cta_max = prop.sharedMemPerBlockOptin;
-    auto smem_for = [&](int threads) { return (size_t)p.blob_bytes + (size_t)(threads / 32) * (32 * (size_t)p.row_stride); };
+    const size_t smem_cta_max = prop.sharedMemPerBlockOptin;
+    auto smem_for = [&](int threads) { return (size_t)p.blob_bytes + (size_t)(threads / 32) * (size_t)p.warp_row_bytes; };
+
+    // opt in to large dynamic shared memory for the instantiations we launch.  The attribute is per
+    // function, not per handle, so it is always set to the device maximum: a second handle with a
+    // smaller footprint must not lower it under the first one's feet.  Then ask the runtime how many
+    // CTAs of each candidate size are resident per SM (shared memory AND registers).
+    const int smem_optin = (int)smem_cta_max;
+    int caps[9] = {0};
+    int rc = dispatch(p.A, p.NOBJ, row_mode(p), [&](auto a, auto nobj, auto rf) -> int {
+        constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
+        constexpr int RF = decltype(rf)::value;
+        CUDA_TRY(cudaFuncSetAttribute(oc_step_kernel<AA, NN, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(oc_rollout_kernel<AA, NN, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(oc_reset_kernel<AA, NN, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+        for (int t = 32; t <= 256; t += 32) {
+            if (smem_for(t) > smem_cta_max) continue;
+            int cs = 0, cr = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cs, oc_step_kernel<AA, NN, RF>, t, smem_for(t)));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cr, oc_rollout_kernel<AA, NN, RF>, t, smem_for(t)));
+            caps[t / 32] = std::min(cs, cr);
+        }
+        return OC_OK;
+    });
+    if (rc != OC_OK) { std::string m = g_err; delete h; return fail(rc, m); }
+
+    // CTA shape: the work is one warp per 32 envs; pick the CTA size whose resident wave covers the
+    // envs with the smallest makespan, preferring fewer table copies on ties.
     const char* tenv = getenv("OC_BLOCK_THREADS");
+    // resident warps per SM that hide the latencies: byte rows run LDS -> convert -> STG chains, float rows
+    // leave through the copy engine, multi-pass float rows wait on it most of the time
+    const double want_warps = !p.rowf ? 24.0 : (p.obs_passes > 1 ? 6.0 : 14.0);
     int best_t = 0, best_cap = 1; double best_cost = 1e30;
     for (int t = 32; t <= 256; t += 32) {
         if (tenv && atoi(tenv) != t) continue;
-        const size_t sm = smem_for(t);
-        if (sm > smem_cta_max) continue;
-        int cap = (int)std::min<size_t>(smem_sm / (sm + 1024), (size_t)std::min(2048 / t, 32));
+        const int cap = caps[t / 32];
         if (cap < 1) continue;
         const long long ctas = ((long long)p.E + t - 1) / t;
         const long long per_sm = (ctas + num_sm - 1) / num_sm;              // CTAs of work on the busiest SM
         const double conc = (double)std::min<long long>(per_sm, cap) * (t / 32); // warps resident together
-        const double eff = std::min(1.0, conc / 14.0);                      // ~14 warps/SM hide the ALU/LDS latency
-        const double cost = (double)per_sm * (t / 32) / eff + 1e-3 * (double)(256 - t) / 256.0;
+        const double eff = std::min(1.0, conc / want_warps);
+        double cost = (double)per_sm * (t / 32) / eff + 1e-3 * (double)(256 - t) / 256.0;
+        // several waves through ONE resident CTA per SM: the SM idles while each new CTA loads its tables
+        if (per_sm > cap && cap < 2) cost *= 1.25;
         if (cost < best_cost) { best_cost = cost; best_t = t; best_cap = cap; }
     }
     if (best_t == 0) { delete h; return fail(OC_ERR_INVALID, "observation row too wide for shared memory"); }
@@ -287,16 +309,9 @@ extern "C" int oc_create(const oc_config* c, oc_env** out) {
     }
     p.blob = h->blob; p.ts_table = h->ts;
 
-    // opt in to large dynamic shared memory for the instantiations we launch.  The attribute is per
-    // function, not per handle, so it is always set to the device maximum: a second handle with a
-    // smaller footprint must not lower it under the first one's feet.
-    const int smem_optin = (int)smem_cta_max;
-    int rc = dispatch(p.A, p.NOBJ, p.rowf, [&](auto a, auto nobj, auto rf) -> int {
+    rc = dispatch(p.A, p.NOBJ, row_mode(p), [&](auto a, auto nobj, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
-        constexpr bool RF = decltype(rf)::value;
-        CUDA_TRY(cudaFuncSetAttribute(oc_step_kernel<AA, NN, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
-        CUDA_TRY(cudaFuncSetAttribute(oc_rollout_kernel<AA, NN, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
-        CUDA_TRY(cudaFuncSetAttribute(oc_reset_kernel<AA, NN, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+        constexpr int RF = decltype(rf)::value;
         const int grid = (p.E + h->threads - 1) / h->threads;
         oc_reset_kernel<AA, NN, RF><<<grid, h->threads, h->smem_bytes, 0>>>(p, h->state, nullptr, nullptr, nullptr, 1);
         CUDA_TRY(cudaGetLastError());
@@ -342,9 +357,9 @@ extern "C" int oc_reset(oc_env* h, const uint8_t* mask, const int32_t* placement
     if (obs && misaligned16(obs)) return fail(OC_ERR_INVALID, "obs must be 16-byte aligned");
     if (int dc = check_device(h)) return dc;
     const OcParams& p = h->p;
-    int rc = dispatch(p.A, p.NOBJ, p.rowf, [&](auto a, auto nobj, auto rf) -> int {
+    int rc = dispatch(p.A, p.NOBJ, row_mode(p), [&](auto a, auto nobj, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
-        constexpr bool RF = decltype(rf)::value;
+        constexpr int RF = decltype(rf)::value;
         const int grid = (p.E + h->threads - 1) / h->threads;
         oc_reset_kernel<AA, NN, RF><<<grid, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(p, h->state, mask, placements, obs, 0);
         CUDA_TRY(cudaGetLastError());
@@ -360,9 +375,9 @@ extern "C" int oc_step(oc_env* h, const int32_t* actions, float* obs, float* rew
     if (misaligned16(obs) || (reinterpret_cast<uintptr_t>(actions) & 7)) return fail(OC_ERR_INVALID, "obs must be 16-byte and actions 8-byte aligned");
     if (int dc = check_device(h)) return dc;
     const OcParams& p = h->p;
-    int rc = dispatch(p.A, p.NOBJ, p.rowf, [&](auto a, auto nobj, auto rf) -> int {
+    int rc = dispatch(p.A, p.NOBJ, row_mode(p), [&](auto a, auto nobj, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
-        constexpr bool RF = decltype(rf)::value;
+        constexpr int RF = decltype(rf)::value;
         const int grid = h->step_grid;
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
@@ -403,9 +418,9 @@ static int launch_rollout(oc_env* h, int32_t n_steps, float* obs, float* rew_f32
     if (obs && misaligned16(obs)) return fail(OC_ERR_INVALID, "obs must be 16-byte aligned");
     if (int dc = check_device(h)) return dc;
     const OcParams& p = h->p;
-    int rc = dispatch(p.A, p.NOBJ, p.rowf, [&](auto a, auto nobj, auto rf) -> int {
+    int rc = dispatch(p.A, p.NOBJ, row_mode(p), [&](auto a, auto nobj, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
-        constexpr bool RF = decltype(rf)::value;
+        constexpr int RF = decltype(rf)::value;
         const int grid = (p.E + h->threads - 1) / h->threads;
         oc_rollout_kernel<AA, NN, RF><<<grid, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(
             p, h->state, n_steps, h->rollout_step, obs, rew_f32, done, actions_out, actions_in);

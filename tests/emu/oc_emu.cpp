@@ -36,23 +36,48 @@ static int dispatch(int A, int NOBJ, int rowf, F&& f) {
     return OC_ERR_INVALID;
 }
 
+// one warp at a time: every lane runs the logic (body; returns true when its env just finished
+// and wants the auto-reset), then terminal observations, auto-reset and the observation passes run
+// the way the kernels order them
 template <int A, int NOBJ, bool ROWF, typename Body>
-static void for_each_warp(emu_env* h, float* obs, Body&& body) {
+static void for_each_warp(emu_env* h, float* obs, float* term_obs, Body&& body) {
     const OcParams& p = h->p;
     const Tables tb = make_tables(p, h->blob.data());
-    std::vector<uint8_t> rows((size_t)32 * p.row_stride);
-    float wts[32];
+    std::vector<uint8_t> rows((size_t)p.warp_row_bytes);
+    Env<A, NOBJ> we[32];
+    Info win[32];
+    auto rowof = [&](int lane) { return rows.data() + (size_t)(lane & (p.nb - 1)) * p.row_stride; };
     for (int env0 = 0; env0 < p.E; env0 += 32) {
         const int nvalid = std::min(32, p.E - env0);
-        for (int lane = 0; lane < 32; ++lane) warp_clear_rows<ROWF>(rows.data(), 32 * p.row_stride, lane);
-        for (int lane = 0; lane < nvalid; ++lane) wts[lane] = body(tb, env0 + lane, rows.data() + (size_t)lane * p.row_stride);
-        if (obs) {
-            for (int lane = 0; lane < 32; ++lane)
-                warp_expand_rows<ROWF>(p, rows.data(), obs + (size_t)env0 * p.row_bytes, nvalid, lane);
-            if (!ROWF)
-                for (int lane = 0; lane < nvalid; ++lane)
-                    store_timesteps<A>(p, obs + (size_t)(env0 + lane) * p.row_bytes, wts[lane]);
+        for (int lane = 0; lane < 32; ++lane) warp_clear_rows<ROWF>(rows.data(), p.warp_row_bytes, lane);
+        for (int lane = 0; lane < nvalid; ++lane) {
+            const int env = env0 + lane;
+            const bool fin = body(tb, env, we[lane], win[lane]);
+            if (fin) {
+                if (term_obs)
+                    thread_emit_rows<A, NOBJ, ROWF>(we[lane], p, tb, win[lane], rowof(lane), term_obs + (size_t)env * p.row_bytes);
+                finish_episode<A, NOBJ>(we[lane], p, tb, (uint32_t)env);
+                win[lane] = gather_info<A, NOBJ>(we[lane], p, tb);
+            }
+            store_env<A, NOBJ>(we[lane], h->state.data(), p.E, env);
         }
+        if (!obs) continue;
+        float* out0 = obs + (size_t)env0 * p.row_bytes;
+        for (int pass = 0; pass < p.obs_passes; ++pass) {
+            if (pass > 0)
+                for (int lane = 0; lane < 32; ++lane) warp_clear_rows<ROWF>(rows.data(), p.warp_row_bytes, lane);
+            for (int lane = 0; lane < nvalid; ++lane)
+                if ((lane >> p.nb_shift) == pass)
+                    fill_rows<A, NOBJ, ROWF>(we[lane], p, tb, win[lane], timestep_of<A, NOBJ>(we[lane], p, tb), rowof(lane));
+            const int first = pass << p.nb_shift;
+            const int nv = std::min(p.nb, nvalid - first);
+            if (nv > 0)
+                for (int lane = 0; lane < 32; ++lane)
+                    warp_expand_rows<ROWF>(p, rows.data(), out0 + (size_t)first * p.row_bytes, nv, lane);
+        }
+        if (!ROWF)
+            for (int lane = 0; lane < nvalid; ++lane)
+                store_timesteps<A>(p, out0 + (size_t)lane * p.row_bytes, timestep_of<A, NOBJ>(we[lane], p, tb));
     }
 }
 
@@ -72,11 +97,9 @@ int emu_create(const oc_config* c, emu_env** out) {
     dispatch(h->p.A, h->p.NOBJ, h->p.rowf, [&](auto a, auto n, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = decltype(n)::value;
         constexpr bool RF = decltype(rf)::value;
-        for_each_warp<AA, NN, RF>(h, nullptr, [&](const Tables& tb, int env, uint8_t* row) -> float {
-            Env<AA, NN> e;
-            const float ts = reset_one_env<AA, NN, RF>(e, h->p, tb, (uint32_t)env, true, nullptr, nullptr, false, row);
-            store_env<AA, NN>(e, h->state.data(), h->p.E, env);
-            return ts;
+        for_each_warp<AA, NN, RF>(h, nullptr, nullptr, [&](const Tables& tb, int env, Env<AA, NN>& e, Info&) {
+            reset_logic<AA, NN>(e, h->p, tb, (uint32_t)env, true, nullptr, nullptr);
+            return false;
         });
         return 0;
     });
@@ -94,12 +117,11 @@ int emu_reset(emu_env* h, const uint8_t* mask, const int32_t* placements, float*
     return dispatch(h->p.A, h->p.NOBJ, h->p.rowf, [&](auto a, auto n, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = decltype(n)::value;
         constexpr bool RF = decltype(rf)::value;
-        for_each_warp<AA, NN, RF>(h, obs, [&](const Tables& tb, int env, uint8_t* row) -> float {
-            Env<AA, NN> e;
+        for_each_warp<AA, NN, RF>(h, obs, nullptr, [&](const Tables& tb, int env, Env<AA, NN>& e, Info& in) {
             load_env<AA, NN>(e, h->state.data(), h->p.E, env);
-            const float ts = reset_one_env<AA, NN, RF>(e, h->p, tb, (uint32_t)env, false, mask, placements, obs != nullptr, row);
-            store_env<AA, NN>(e, h->state.data(), h->p.E, env);
-            return ts;
+            reset_logic<AA, NN>(e, h->p, tb, (uint32_t)env, false, mask, placements);
+            if (obs) in = gather_info<AA, NN>(e, h->p, tb);
+            return false;
         });
         return OC_OK;
     });
@@ -110,14 +132,13 @@ int emu_step(emu_env* h, const int32_t* actions, float* obs, float* rew32, doubl
     return dispatch(h->p.A, h->p.NOBJ, h->p.rowf, [&](auto a, auto n, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = decltype(n)::value;
         constexpr bool RF = decltype(rf)::value;
-        for_each_warp<AA, NN, RF>(h, obs, [&](const Tables& tb, int env, uint8_t* row) -> float {
-            Env<AA, NN> e;
+        for_each_warp<AA, NN, RF>(h, obs, term_obs, [&](const Tables& tb, int env, Env<AA, NN>& e, Info& in) {
             load_env<AA, NN>(e, h->state.data(), h->p.E, env);
             int nav[AA], comm[AA];
             for (int k = 0; k < AA; ++k) { nav[k] = actions[((size_t)env * AA + k) * 2] & 3; comm[k] = actions[((size_t)env * AA + k) * 2 + 1]; }
-            const float ts = step_one_env<AA, NN, RF>(e, h->p, tb, nav, comm[0], comm[1], (uint32_t)env, row, rew32, rew64, done, term_obs, flags);
-            store_env<AA, NN>(e, h->state.data(), h->p.E, env);
-            return ts;
+            bool fin;
+            in = step_logic<AA, NN>(e, h->p, tb, nav, comm[0], comm[1], (uint32_t)env, rew32, rew64, done, fin);
+            return fin && (flags & OC_FLAG_AUTO_RESET);
         });
         return OC_OK;
     });
@@ -129,14 +150,11 @@ int emu_rollout(emu_env* h, int32_t n_steps, float* obs, float* rew32, uint8_t* 
         constexpr int AA = decltype(a)::value, NN = decltype(n)::value;
         constexpr bool RF = decltype(rf)::value;
         for (int s = 0; s < n_steps; ++s)
-            for_each_warp<AA, NN, RF>(h, obs ? obs + (size_t)s * step_floats : nullptr,
-                                  [&](const Tables& tb, int env, uint8_t* row) -> float {
-                Env<AA, NN> e;
+            for_each_warp<AA, NN, RF>(h, obs ? obs + (size_t)s * step_floats : nullptr, nullptr,
+                                  [&](const Tables& tb, int env, Env<AA, NN>& e, Info& in) {
                 load_env<AA, NN>(e, h->state.data(), h->p.E, env);
-                const float ts = rollout_one_env<AA, NN, RF>(e, h->p, tb, (uint32_t)env, (uint32_t)s, h->rollout_step, row,
-                                                         obs != nullptr, rew32, done, actions_out);
-                store_env<AA, NN>(e, h->state.data(), h->p.E, env);
-                return ts;
+                in = rollout_logic<AA, NN, RF>(e, h->p, tb, (uint32_t)env, (uint32_t)s, h->rollout_step, rew32, done, actions_out);
+                return false;
             });
         return OC_OK;
     });

@@ -1,0 +1,68 @@
+"""The device code (tests/emu: oc_device.cuh compiled for the host, TEST ONLY) against the C oracle
+on ragged multi-warp batches with auto-reset and terminal observations, under every shared-memory
+row format the host can select (float rows of 32 / 16 / 8 envs per pass, padded or not, byte rows).
+The GPU suite repeats this at BASELINE.json's sizes; this one runs without a GPU."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+from gym_comm_b200 import levels_data
+from gym_comm_b200.vec_env import OvercookedVecEnv
+from oracle.c_oracle import COracle
+from tests.parity_util import emu_library
+
+D = dict(CAN_MOVE=True, ALLERGIC=False, BLIND=False)
+CONFIGS = {
+    "tomato_c10": dict(level="open-divider_tomato", num_agents=2, max_num_timesteps=23, communication_on=True,
+                       num_communication=10, ego_led=False, fow_radius=2, ego_config=D, partner_config=D),
+    "salad3_c13": dict(level="partial-divider_salad", num_agents=3, max_num_timesteps=17, communication_on=True,
+                       num_communication=13, ego_led=False, fow_radius=2, ego_config=D, partner_config=D),
+    "random_wide_c100": dict(level="random-salad-superwide", num_agents=2, max_num_timesteps=19,
+                             communication_on=True, num_communication=100, ego_led=False, fow_radius=2,
+                             ego_config=D, partner_config=D),
+}
+FORMATS = {
+    "default": {},
+    "f16": dict(OC_ROW_FORMAT="f", OC_ROW_ENVS="16"),
+    "f8_nopad": dict(OC_ROW_FORMAT="f", OC_ROW_ENVS="8", OC_ROW_PAD="0"),
+    "f4": dict(OC_ROW_FORMAT="f", OC_ROW_ENVS="4"),
+    "bytes": dict(OC_ROW_FORMAT="b"),
+}
+
+
+@pytest.mark.parametrize("fmt", sorted(FORMATS))
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_step_autoreset_terminal_obs(name, fmt, monkeypatch):
+    for k, v in FORMATS[fmt].items():
+        monkeypatch.setenv(k, v)
+    cfg = CONFIGS[name]
+    text = levels_data.LEVELS[cfg["level"]]
+    subtasks = levels_data.SUBTASKS[tuple(text.split("\n\n")[1].split("\n"))]
+    E, n, seed = 75, cfg["num_agents"], 99
+    env = OvercookedVecEnv(argparse.Namespace(**cfg), num_envs=E, device="cpu", lib=emu_library(), seed=seed,
+                           auto_reset=True)
+    ora = COracle(text, subtasks, E, seed=seed, **{k: v for k, v in cfg.items() if k != "level"})
+    rng = np.random.default_rng(5)
+    term = torch.full((E, n, env.obs_width), -7.0)
+    term_o = np.full((E, n, env.obs_width), -7.0)
+    assert np.array_equal(env.reset().numpy(), ora.reset().astype(np.float32))
+    for t in range(3 * cfg["max_num_timesteps"] + 2):
+        a = np.stack([rng.integers(0, 4, (E, n)), rng.integers(0, cfg["num_communication"], (E, n))], -1).astype(np.int32)
+        obs, rew, done = env.step(torch.from_numpy(a), term_obs_out=term, want_f64=True)
+        oo, orr, od = ora.step(a, auto_reset=True, term_obs=term_o)
+        assert np.array_equal(env.rewards64.numpy(), orr), (name, fmt, t)
+        assert np.array_equal(done.numpy(), od), (name, fmt, t)
+        assert np.array_equal(obs.numpy(), oo.astype(np.float32)), (name, fmt, t)
+    assert np.array_equal(term.numpy(), term_o.astype(np.float32))
+    assert env.decode_state()["episodes"].min() >= 3
+
+    # the fused rollout continues from the same state with the shared Philox action spec
+    obs = torch.zeros((7, E, n, env.obs_width))
+    done = torch.zeros((7, E), dtype=torch.uint8)
+    env.rollout(7, obs_out=obs, done_out=done)
+    oo, orr, od, _ = ora.rollout(7, want_obs=True, want_actions=True)
+    assert np.array_equal(done.numpy(), od) and np.array_equal(obs.numpy(), oo.astype(np.float32))
+    env.close()
+    ora.close()
