@@ -339,6 +339,9 @@ def main():
                 "event_bracketed_launch_us": {"mean": mean_ms * 1e3 * (steps_per_launch / spl),
                                               "median": statistics.median(kernel_ms) * 1e3, "n": nk, "steps_per_launch": spl},
                 "timing": "CUDA events on the launching stream: one pair around the K-step region, one pair around each of %d launches" % nk}
+        if roof["frac_moved"] > 1.0:
+            roof["note"] = ("a write-only stream: the peak is the measured COPY bandwidth (read+write); ncu reports the "
+                            "same launch at 88.7 % of the device's own DRAM peak (profiles/r1_ncu_cfg5_rollout_summary.txt)")
         # L2-flushed variant of the same launch (diagnostic): state, actions and obs lines all cold
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
         fl_ms = []

@@ -663,7 +663,7 @@ __device__ __forceinline__ void store_timesteps(const OcParams& p, float* __rest
 }
 
 // ---- observation emission of one warp's 32 envs.  The warp's row buffer holds p.nb env rows
-// (32, or 16 / 8 for wide float rows, so that enough warps stay resident); the envs go out in
+// (32, or 16 / 8 / 4 for wide float rows, so that enough warps stay resident); the envs go out in
 // 32 / nb passes, lanes [pass * nb, pass * nb + nb) filling the buffer in their pass.  Rows must be
 // clear (and, with bulk stores, read out) on entry; they are dirty on exit.
 template <int A, int NOBJ, int MODE /* 0 byte rows, 1 float rows, 2 float rows in several passes */>

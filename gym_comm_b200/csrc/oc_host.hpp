@@ -107,12 +107,12 @@ static inline int compile_config(const oc_config* c, HostImage& h, std::string& 
     p.row_stride = (int)align_up(p.row_bytes, 4);
     if (((p.row_stride >> 2) & 1) == 0) p.row_stride += 4;
     // float rows (bulk-stored by the copy engine) when rows are 16-byte multiples and a warp's buffer stays
-    // small: all 32 env rows when they fit in 24 KB, else 16 or 8 rows (<= 30 KB) emitted in 2 / 4 passes
+    // small: all 32 env rows when they fit in 24 KB, else 16 / 8 / 4 rows (<= 30 KB) emitted in 2 / 4 / 8 passes
     p.nb = 32;
     p.rowf = 0;
     if ((p.row_bytes & 3) == 0) {
         if (32 * p.row_bytes * 4 <= 24 * 1024) p.rowf = 1;
-        else for (int nb = 16; nb >= 8 && !p.rowf; nb >>= 1)
+        else for (int nb = 16; nb >= 4 && !p.rowf; nb >>= 1)
             if (nb * p.row_bytes * 4 <= 30 * 1024) { p.rowf = 1; p.nb = nb; }
     }
     if (const char* f = getenv("OC_ROW_FORMAT")) {

@@ -56,7 +56,7 @@ struct OcParams {
     int32_t  npairs;                        // C(num_items, 2) item pairs of calculate_reward_shaping
     uint32_t item_foods;                    // Food bits among the shaping items (items[0] is always Plate)
     uint32_t r4_magic, rf_magic;            // floor(2^32 / d) + 1 for d = row_bytes / 4 and row_bytes
-    int32_t nb, nb_shift;                   // env rows in one warp's shared-memory buffer: 32, or 16 / 8 (wide float rows)
+    int32_t nb, nb_shift;                   // env rows in one warp's shared-memory buffer: 32, or 16 / 8 / 4 (wide float rows)
     int32_t obs_passes;                     // 32 / nb: a warp emits its 32 envs in this many passes
     int32_t warp_row_bytes;                 // nb * row_stride
     // observation layout (float offsets inside one observer row)

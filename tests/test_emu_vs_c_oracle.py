@@ -22,6 +22,10 @@ CONFIGS = {
     "random_wide_c100": dict(level="random-salad-superwide", num_agents=2, max_num_timesteps=19,
                              communication_on=True, num_communication=100, ego_led=False, fow_radius=2,
                              ego_config=D, partner_config=D),
+    "wide3_c60": dict(level="partial-divider_salad", num_agents=3, max_num_timesteps=13, communication_on=True,
+                      num_communication=60, ego_led=False, fow_radius=2, ego_config=D, partner_config=D),
+    "wide4_c100": dict(level="open-divider_salad", num_agents=4, max_num_timesteps=11, communication_on=True,
+                       num_communication=100, ego_led=True, fow_radius=1, ego_config=D, partner_config=D),
 }
 FORMATS = {
     "default": {},

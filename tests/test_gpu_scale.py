@@ -38,6 +38,11 @@ CONFIGS = {
     # T > 1023: the timestep table no longer fits the shared-memory blob -> computed with an f64 division
     "longT": dict(level="open-divider_tomato", num_agents=2, max_num_timesteps=3001, communication_on=True,
                   num_communication=10, ego_led=False, fow_radius=2, ego_config=DEF, partner_config=DEF),
+    # wide rows with 3 / 4 observers: float rows of 16 / 8 envs per pass (multi-pass bulk stores)
+    "wide3_c60": dict(level="partial-divider_salad", num_agents=3, max_num_timesteps=40, communication_on=True,
+                      num_communication=60, ego_led=False, fow_radius=2, ego_config=DEF, partner_config=DEF),
+    "wide4_c100": dict(level="open-divider_salad", num_agents=4, max_num_timesteps=30, communication_on=True,
+                       num_communication=100, ego_led=True, fow_radius=1, ego_config=DEF, partner_config=DEF),
     "salad4_commoff": dict(level="open-divider_salad", num_agents=4, max_num_timesteps=150, communication_on=False,
                            num_communication=7, ego_led=False, fow_radius=1, ego_config=DEF, partner_config=DEF),
 }
@@ -119,7 +124,8 @@ def test_goal_chasing_streams_vs_python_oracle(name):
 
 
 @pytest.mark.parametrize("name,E,T", [("cfg2", 65536, 1100), ("cfg3", 262144, 120), ("cfg4", 65536, 1000),
-                                      ("cfg5", 131072, 60), ("tl3_oddrow", 4099, 450), ("longT", 2000, 3100)])
+                                      ("cfg5", 131072, 60), ("tl3_oddrow", 4099, 450), ("longT", 2000, 3100),
+                                      ("wide3_c60", 4099, 90), ("wide4_c100", 3001, 70)])
 def test_random_streams_autoreset_vs_c_oracle(name, E, T):
     """BASELINE.json env counts; uniform random actions; auto-reset on the device (random levels
     draw their placements from the shared Philox spec); every step: f64 reward, done, and all
@@ -157,7 +163,8 @@ def test_random_streams_autoreset_vs_c_oracle(name, E, T):
     ora.close()
 
 
-@pytest.mark.parametrize("name,E", [("cfg2", 65536), ("cfg4", 20000), ("cfg3_full", 9000)])
+@pytest.mark.parametrize("name,E", [("cfg2", 65536), ("cfg4", 20000), ("cfg3_full", 9000), ("cfg5", 10007),
+                                    ("wide4_c100", 1501)])
 def test_fused_rollout_vs_c_oracle(name, E):
     """oc_rollout (one launch, Philox actions on the device) == the C oracle's twin rollout:
     identical actions, rewards (f32 of the f64), dones and observations, across chunks."""
