@@ -366,35 +366,32 @@ def main():
     other_mode = "step" if args.mode == "rollout" else "rollout"
     secondary = None if args.single_mode else measure(other_mode)
 
-    # ---- e2e: the public VecEnv API with HOST buffers (pinned), H2D actions + D2H obs/reward/done every step
+    # ---- e2e: the reference-facing call with HOST buffers: OvercookedHostVecEnv.step = C ABI oc_step_host
+    # (pinned numpy buffers; every step copies the actions host->device, runs the step kernel, copies
+    # observations / rewards / dones device->host and synchronises before returning)
     e2e = None
     if not args.no_e2e:
+        from gym_comm_b200.host_env import OvercookedHostVecEnv
         Ke = min(K, 200)
-        h_obs = torch.empty((E, A, F), dtype=torch.float32).pin_memory()
-        h_rew = torch.empty((E, A), dtype=torch.float32).pin_memory()
-        h_done = torch.empty((E,), dtype=torch.uint8).pin_memory()
-        d_act = torch.empty((E, A, 2), dtype=torch.int32, device=dev)
-        host_actions = actions[:8].cpu().pin_memory()      # the steps' inputs live in pinned host memory
+        henv = OvercookedHostVecEnv(ns, num_envs=E, device_index=local_rank, seed=1234 + rank, auto_reset=True,
+                                    terminal_observations=False)
+        host_actions = actions[:8].cpu().numpy()           # the steps' inputs live in host memory
+        henv.reset()
         for i in range(3):
-            d_act.copy_(host_actions[i], non_blocking=True)
-            env.step(d_act)
+            henv.step(host_actions[i])
         barrier()
         t0 = time.perf_counter()
         for i in range(Ke):
-            d_act.copy_(host_actions[i % 8], non_blocking=True)
-            o, r, d = env.step(d_act)
-            h_obs.copy_(o, non_blocking=True)
-            h_rew.copy_(r, non_blocking=True)
-            h_done.copy_(d, non_blocking=True)
-            torch.cuda.synchronize(dev)
+            henv.step(host_actions[i % 8])                 # returns with obs / reward / done valid on the host
         barrier()
         dt = time.perf_counter() - t0
+        henv.close()
         tm = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         e2e = {"value": float(E) * A * Ke * world / float(tm.item()), "unit": "agent-steps/s",
                "h2d_bytes_per_step": E * A * 2 * 4, "d2h_bytes_per_step": E * A * F * 4 + E * A * 4 + E,
-               "steps": Ke, "api": "OvercookedVecEnv.step (C ABI oc_step) with pinned host buffers, synchronised every step"}
+               "steps": Ke, "api": "OvercookedHostVecEnv.step = C ABI oc_step_host, pinned numpy buffers, synchronised every step"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

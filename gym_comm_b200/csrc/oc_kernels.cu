@@ -194,6 +194,12 @@ struct oc_env {
     int tma_rows_in_step = 1;
     int step_grid = 1;
     int obs_off[OC_NUM_OBS_KEYS], obs_size[OC_NUM_OBS_KEYS];
+    // device-side staging of the host-buffer entry points (oc_step_host / oc_reset_host), allocated on first use
+    struct HostPath {
+        int32_t* actions = nullptr; float* obs = nullptr; float* rew32 = nullptr; double* rew64 = nullptr;
+        uint8_t* done = nullptr; float* term = nullptr; uint8_t* mask = nullptr; int32_t* place = nullptr;
+        float* h_term = nullptr;       // pinned host copy of `term` for steps where many envs finish
+    } hp;
 };
 
 // kernel template MODE: 0 byte rows, 1 float rows (all 32 envs of a warp in one pass), 2 float rows in passes
@@ -329,6 +335,10 @@ extern "C" int oc_destroy(oc_env* h) {
     if (h->state) cudaFree(h->state);
     if (h->blob) cudaFree(h->blob);
     if (h->ts) cudaFree(h->ts);
+    for (void* q : {(void*)h->hp.actions, (void*)h->hp.obs, (void*)h->hp.rew32, (void*)h->hp.rew64, (void*)h->hp.done,
+                    (void*)h->hp.term, (void*)h->hp.mask, (void*)h->hp.place})
+        if (q) cudaFree(q);
+    if (h->hp.h_term) cudaFreeHost(h->hp.h_term);
     delete h;
     return OC_OK;
 }
@@ -463,3 +473,97 @@ extern "C" int oc_get_stats(oc_env* h, uint32_t* episodes, uint32_t* last_comple
 }
 
 extern "C" uint64_t oc_launch_count(const oc_env* h) { return h ? h->launches : 0; }
+
+// ---- host-buffer entry points: what a caller without device memory of its own (numpy, SB3 on the CPU) binds
+
+extern "C" int oc_set_device(int device) {
+    CUDA_TRY(cudaSetDevice(device));
+    return OC_OK;
+}
+
+extern "C" int oc_host_alloc(uint64_t bytes, void** out) {
+    if (!out) return fail(OC_ERR_INVALID, "null argument");
+    *out = nullptr;
+    cudaError_t ce = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (ce != cudaSuccess) return fail(OC_ERR_ALLOC, std::string("cudaHostAlloc: ") + cudaGetErrorString(ce));
+    return OC_OK;
+}
+
+extern "C" int oc_host_free(void* ptr) {
+    if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+    return OC_OK;
+}
+
+template <typename T>
+static int ensure_dev(T*& ptr, size_t count) {
+    if (ptr) return OC_OK;
+    cudaError_t ce = cudaMalloc(&ptr, count * sizeof(T));
+    if (ce != cudaSuccess) { ptr = nullptr; return fail(OC_ERR_ALLOC, std::string("cudaMalloc (host path staging): ") + cudaGetErrorString(ce)); }
+    return OC_OK;
+}
+
+extern "C" int oc_reset_host(oc_env* h, const uint8_t* mask, const int32_t* placements, float* obs, void* stream) {
+    if (!h) return fail(OC_ERR_INVALID, "null handle");
+    if (int dc = check_device(h)) return dc;
+    const OcParams& p = h->p;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t E = (size_t)p.E, row = (size_t)p.row_bytes;
+    int rc;
+    if (mask) {
+        if ((rc = ensure_dev(h->hp.mask, E))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h->hp.mask, mask, E, cudaMemcpyHostToDevice, st));
+    }
+    if (placements && p.nrandom > 0) {
+        if ((rc = ensure_dev(h->hp.place, E * p.nrandom))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h->hp.place, placements, E * p.nrandom * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    }
+    if (obs && (rc = ensure_dev(h->hp.obs, E * row))) return rc;
+    if ((rc = oc_reset(h, mask ? h->hp.mask : nullptr, (placements && p.nrandom > 0) ? h->hp.place : nullptr,
+                       obs ? h->hp.obs : nullptr, stream))) return rc;
+    if (obs) CUDA_TRY(cudaMemcpyAsync(obs, h->hp.obs, E * row * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return OC_OK;
+}
+
+extern "C" int oc_step_host(oc_env* h, const int32_t* actions, float* obs, float* rew_f32, double* rew_f64,
+                            uint8_t* done, float* term_obs, uint32_t flags, void* stream) {
+    if (!h || !actions || !obs || !done) return fail(OC_ERR_INVALID, "null argument");
+    if (int dc = check_device(h)) return dc;
+    const OcParams& p = h->p;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t E = (size_t)p.E, A = (size_t)p.A, row = (size_t)p.row_bytes;
+    int rc;
+    if ((rc = ensure_dev(h->hp.actions, E * A * 2)) || (rc = ensure_dev(h->hp.obs, E * row)) ||
+        (rc = ensure_dev(h->hp.done, E))) return rc;
+    if (rew_f32 && (rc = ensure_dev(h->hp.rew32, E * A))) return rc;
+    if (rew_f64 && (rc = ensure_dev(h->hp.rew64, E))) return rc;
+    const bool want_term = term_obs != nullptr && (flags & OC_FLAG_AUTO_RESET);
+    if (want_term && (rc = ensure_dev(h->hp.term, E * row))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h->hp.actions, actions, E * A * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if ((rc = oc_step(h, h->hp.actions, h->hp.obs, rew_f32 ? h->hp.rew32 : nullptr, rew_f64 ? h->hp.rew64 : nullptr,
+                      h->hp.done, want_term ? h->hp.term : nullptr, flags, stream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(done, h->hp.done, E, cudaMemcpyDeviceToHost, st));
+    if (rew_f32) CUDA_TRY(cudaMemcpyAsync(rew_f32, h->hp.rew32, E * A * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (rew_f64) CUDA_TRY(cudaMemcpyAsync(rew_f64, h->hp.rew64, E * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(obs, h->hp.obs, E * row * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (want_term) {                                   // only the rows of envs that just finished reach the caller's buffer
+        size_t nfin = 0;
+        for (size_t e = 0; e < E; ++e) nfin += done[e] != 0;
+        if (nfin > 0 && nfin <= 64) {
+            for (size_t e = 0; e < E; ++e)
+                if (done[e]) CUDA_TRY(cudaMemcpyAsync(term_obs + e * row, h->hp.term + e * row, row * sizeof(float), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+        } else if (nfin > 0) {
+            if (!h->hp.h_term) {
+                cudaError_t ce = cudaHostAlloc((void**)&h->hp.h_term, E * row * sizeof(float), cudaHostAllocDefault);
+                if (ce != cudaSuccess) { h->hp.h_term = nullptr; return fail(OC_ERR_ALLOC, std::string("cudaHostAlloc: ") + cudaGetErrorString(ce)); }
+            }
+            CUDA_TRY(cudaMemcpyAsync(h->hp.h_term, h->hp.term, E * row * sizeof(float), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            for (size_t e = 0; e < E; ++e)
+                if (done[e]) memcpy(term_obs + e * row, h->hp.h_term + e * row, row * sizeof(float));
+        }
+    }
+    return OC_OK;
+}

@@ -1,0 +1,150 @@
+"""The batched Overcooked env for a caller whose buffers live in HOST memory -- numpy in, numpy out,
+no torch anywhere: the C ABI's host-buffer entry points (`oc_reset_host` / `oc_step_host`,
+include/overcooked_b200.h) behind the SB3 `VecEnv` calling convention.
+
+This is what stands where the reference's `DummyVecEnv([lambda: OvercookedMultiEnv])` stands when
+the learner stays on the CPU (sb3_contrib/ppo_recurrent/ppo_recurrent.py:233-252 reads numpy
+observations and writes numpy actions): every `step` copies the actions host->device, runs the CUDA
+step kernel, copies observations / rewards / dones device->host and synchronises, so it is
+PCIe-bound (`bench.py` reports it as `e2e`).  A learner on the GPU should use
+`gym_comm_b200.vec_env.OvercookedVecEnv` and never leave the device.
+
+The compute is `liboc_b200.so` (sm_100a CUDA); there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _cabi
+from .arglist import normalize
+from .level_compiler import CompiledLevel, compile_level
+from .spaces import make_spaces
+
+
+class OvercookedHostVecEnv:
+    """E lock-step envs on one GPU, host (numpy) buffers.
+
+    ``reset() -> obs [E, A, F] f32``;
+    ``step(actions int32 [E, A, 2]) -> (obs [E, A, F] f32, rewards [E, A] f32, dones [E] bool, infos)``
+    with SB3's auto-reset contract: for an env that finished, ``obs`` is the first observation of its
+    next episode and ``infos[e]["terminal_observation"]`` the last one of the finished episode.
+    The returned arrays (and the `infos` list) are the env's own pinned buffers, overwritten by the next
+    call (copy them to keep them, as SB3's rollout buffer does) and invalid after `close()`.
+    """
+
+    def __init__(self, arglist, num_envs: int = 1, device_index: int = 0, seed: int = 0, auto_reset: bool = True,
+                 terminal_observations: bool = True, level_text: Optional[str] = None, subtasks=None,
+                 lib: Optional[_cabi.OcLibrary] = None):
+        self.arglist = normalize(arglist)
+        a = self.arglist
+        self.lib = lib if lib is not None else _cabi.default_library()
+        if self.lib.prefix != "oc_":
+            raise RuntimeError("OvercookedHostVecEnv needs liboc_b200.so (CUDA); there is no CPU backend")
+        self.device_index = int(device_index)
+        self.num_envs, self.num_agents = int(num_envs), int(a.num_agents)
+        self.auto_reset = bool(auto_reset)
+        self.level: CompiledLevel = compile_level(a.level, self.num_agents, level_text=level_text, subtasks=subtasks)
+        cfg, self._keep = _cabi.make_config(
+            self.level, num_envs=self.num_envs, num_agents=self.num_agents,
+            max_num_timesteps=a.max_num_timesteps, num_communication=a.num_communication,
+            communication_on=a.communication_on, ego_led=a.ego_led, fow_radius=a.fow_radius,
+            ego_config=a.ego_config, partner_config=a.partner_config, seed=seed)
+        self._handle = C.c_void_p()
+        self._pinned = []
+        self._closed = False
+        self.lib.check(self.lib.set_device(self.device_index), "oc_set_device")
+        self.lib.check(self.lib.create(C.byref(cfg), C.byref(self._handle)), "oc_create")
+        self.obs_width = self.lib.obs_width(self._handle)
+        off = (C.c_int32 * _cabi.OC_NUM_OBS_KEYS)()
+        size = (C.c_int32 * _cabi.OC_NUM_OBS_KEYS)()
+        self.lib.check(self.lib.obs_layout(self._handle, off, size), "oc_obs_layout")
+        self.obs_layout = {k: slice(off[i], off[i] + size[i]) for i, k in enumerate(_cabi.OBS_KEYS)}
+        self.observation_space, self.action_space = make_spaces(self.level, a.num_communication)
+        E, A, F = self.num_envs, self.num_agents, self.obs_width
+        self.obs = self._pinned_array((E, A, F), np.float32)
+        self.rewards = self._pinned_array((E, A), np.float32)
+        self.dones = self._pinned_array((E,), np.uint8)
+        self.actions = self._pinned_array((E, A, 2), np.int32)
+        self.terminal_obs = self._pinned_array((E, A, F), np.float32) if (terminal_observations and auto_reset) else None
+        self._infos = [{} for _ in range(E)]
+        self._touched = ()
+
+    # ------------------------------------------------------------------ plumbing
+    def _pinned_array(self, shape, dtype) -> np.ndarray:
+        """numpy view of page-locked host memory from oc_host_alloc (freed in close())."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = C.c_void_p()
+        self.lib.check(self.lib.host_alloc(n, C.byref(ptr)), "oc_host_alloc")
+        self._pinned.append(ptr)
+        buf = (C.c_uint8 * max(n, 1)).from_address(ptr.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        arr[...] = 0
+        return arr
+
+    @staticmethod
+    def _p(a: Optional[np.ndarray]):
+        return None if a is None else C.c_void_p(a.ctypes.data)
+
+    def _check(self, a: np.ndarray, shape, dtype, name):
+        if not isinstance(a, np.ndarray) or a.dtype != dtype or tuple(a.shape) != tuple(shape) or not a.flags.c_contiguous:
+            raise ValueError("%s must be a C-contiguous %s array of shape %s" % (name, np.dtype(dtype).name, tuple(shape)))
+
+    # ------------------------------------------------------------------ API
+    def reset(self, mask: Optional[np.ndarray] = None, placements: Optional[np.ndarray] = None) -> np.ndarray:
+        if mask is not None:
+            self._check(mask, (self.num_envs,), np.uint8, "mask")
+        if placements is not None:
+            self._check(placements, (self.num_envs, self.level.num_random), np.int32, "placements")
+        self.lib.check(self.lib.set_device(self.device_index), "oc_set_device")
+        self.lib.check(self.lib.reset_host(self._handle, self._p(mask), self._p(placements), self._p(self.obs), None),
+                       "oc_reset_host")
+        return self.obs
+
+    def step(self, actions: np.ndarray):
+        if actions is not self.actions:
+            a = np.asarray(actions)
+            if a.shape != self.actions.shape:
+                raise ValueError("actions must have shape %s (nav, comm per agent)" % (self.actions.shape,))
+            np.copyto(self.actions, a, casting="same_kind")
+        flags = _cabi.OC_FLAG_AUTO_RESET if self.auto_reset else 0
+        self.lib.check(self.lib.set_device(self.device_index), "oc_set_device")
+        self.lib.check(self.lib.step_host(self._handle, self._p(self.actions), self._p(self.obs), self._p(self.rewards),
+                                          None, self._p(self.dones), self._p(self.terminal_obs), flags, None),
+                       "oc_step_host")
+        d = self.dones.view(np.bool_)
+        # one dict per env, allocated once; only the entries of envs that finished are touched
+        for e in self._touched:
+            self._infos[e].clear()
+        self._touched = np.flatnonzero(d) if self.terminal_obs is not None else ()
+        for e in self._touched:
+            self._infos[e]["terminal_observation"] = self.terminal_obs[e].copy()
+        return self.obs, self.rewards, d, self._infos
+
+    def obs_dict(self, obs: Optional[np.ndarray] = None) -> dict:
+        """Per-key zero-copy views of flat rows (the reference's Dict observation)."""
+        o = self.obs if obs is None else obs
+        return {k: o[..., s] for k, s in self.obs_layout.items()}
+
+    def close(self):
+        if self._closed:
+            return
+        self._closed = True
+        try:
+            self.lib.set_device(self.device_index)
+            if self._handle:
+                self.lib.destroy(self._handle)
+            for ptr in self._pinned:
+                self.lib.host_free(ptr)
+        finally:
+            self._handle = C.c_void_p()
+            self._pinned = []
+            self.obs = self.rewards = self.dones = self.actions = self.terminal_obs = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import Dict, Optional
+from typing import Optional
 
 import numpy as np
 import torch
@@ -23,28 +23,7 @@ from .arglist import normalize
 from .level_compiler import NAV_ACTIONS, CompiledLevel, compile_level
 
 
-# --------------------------------------------------------------------------- gym-free spaces
-class Box:
-    def __init__(self, low, high, shape=None, dtype=np.float32):
-        self.low, self.high, self.dtype = low, high, dtype
-        self.shape = tuple(shape) if shape is not None else np.asarray(low).shape
-
-
-class MultiBinary:
-    def __init__(self, n):
-        self.n, self.shape, self.dtype = n, (n,), np.int8
-
-
-class MultiDiscrete:
-    def __init__(self, nvec):
-        self.nvec = np.asarray(nvec)
-        self.shape, self.dtype = self.nvec.shape, np.int64
-
-
-class Dict:
-    def __init__(self, spaces):
-        # gym.spaces.Dict sorts a plain dict by key; that order is the flat feature order
-        self.spaces = dict(sorted(spaces.items()))
+from .spaces import Box, Dict, MultiBinary, MultiDiscrete, make_spaces  # noqa: F401  (re-exported)
 
 
 class OvercookedVecEnv:
@@ -87,19 +66,7 @@ class OvercookedVecEnv:
         size = (C.c_int32 * _cabi.OC_NUM_OBS_KEYS)()
         self.lib.check(self.lib.obs_layout(self._handle, off, size), "oc_obs_layout")
         self.obs_layout = {k: slice(off[i], off[i] + size[i]) for i, k in enumerate(_cabi.OBS_KEYS)}
-        S, Cn = len(self.level.subtasks), a.num_communication
-        w, h = self.level.width, self.level.height
-        self.observation_space = Dict({
-            "timestep": Box(0.0, 1.0, (1,), np.float32),
-            "object_encodings_x": Box(-w, w, (4,), np.int64),
-            "object_encodings_y": Box(h, h, (4,), np.int64),          # sic: low == high in the reference (:62)
-            "state_encodings": MultiBinary(4), "is_hidden": MultiBinary(4),
-            "completed_subtasks": MultiBinary(S),
-            "agent1_location": Box(np.array([0, 0]), np.array([w - 1, h - 1]), dtype=np.float32),
-            "agent2_location": Box(np.array([0, 0]), np.array([w - 1, h - 1]), dtype=np.float32),
-            "agent_is_holding": MultiBinary(2),
-            "agent1_comm": MultiBinary(Cn), "agent2_comm": MultiBinary(Cn)})
-        self.action_space = MultiDiscrete([len(NAV_ACTIONS), Cn])      # overcooked_env.py:85
+        self.observation_space, self.action_space = make_spaces(self.level, a.num_communication)
         E, A, F = self.num_envs, self.num_agents, self.obs_width
         kw = dict(device=self.device)
         self.obs = torch.zeros((E, A, F), dtype=torch.float32, **kw)
@@ -216,7 +183,7 @@ class OvercookedVecEnv:
     def launch_count(self) -> int:
         return int(self.lib.launch_count(self._handle)) if self.lib.prefix == "oc_" else 0
 
-    def obs_dict(self, obs: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    def obs_dict(self, obs: Optional[torch.Tensor] = None) -> dict:
         """Zero-copy per-key views ``[..., size]`` of flat observation rows."""
         obs = self.obs if obs is None else obs
         return {k: obs[..., s] for k, s in self.obs_layout.items()}

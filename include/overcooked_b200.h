@@ -178,6 +178,24 @@ int oc_get_stats(oc_env* env, uint32_t* episodes /*[E]*/, uint32_t* last_complet
 /* Number of kernel launches issued through this handle so far (bench.py "gpu_launches"). */
 uint64_t oc_launch_count(const oc_env* env);
 
+/* ---- Host-buffer entry points: for a caller that keeps its buffers in HOST memory (numpy arrays, SB3 rollout
+ * buffers on the CPU -- exactly what the reference's DummyVecEnv.step_wait hands to
+ * sb3_contrib/ppo_recurrent/ppo_recurrent.py:233-252).  Same arguments and semantics as oc_reset / oc_step,
+ * but every pointer is a HOST pointer; the handle stages through device buffers it owns (allocated on first
+ * use), copies host->device and device->host on `stream`, and SYNCHRONISES the stream before returning, so
+ * the results are valid on return.  Pinned buffers (oc_host_alloc) make the copies run at PCIe speed;
+ * pageable memory works but is slower.  term_obs: only the rows of envs that finished in this step are
+ * written; other rows of the caller's buffer are left untouched. */
+int oc_reset_host(oc_env* env, const uint8_t* mask, const int32_t* placements, float* obs, void* stream);
+int oc_step_host(oc_env* env, const int32_t* actions, float* obs, float* rew_f32, double* rew_f64,
+                 uint8_t* done, float* term_obs, uint32_t flags, void* stream);
+/* Page-locked host memory for those buffers (cudaHostAlloc / cudaFreeHost without linking the CUDA runtime). */
+int oc_host_alloc(uint64_t bytes, void** out);
+int oc_host_free(void* ptr);
+/* Select the CUDA device of the calling thread (cudaSetDevice) -- for callers that do not otherwise touch
+ * the CUDA runtime; a handle stays bound to the device that was current at oc_create. */
+int oc_set_device(int device);
+
 const char* oc_last_error(void);
 int oc_abi_version(void);
 

@@ -1,6 +1,6 @@
 /* The C ABI used from plain C (no Python, no torch): builds the 5x4 kitchen below by hand, steps 64
  * envs for 200 random steps through oc_step / oc_rollout / oc_reset and checks structural facts of
- * the outputs.  Compiled and run by tests/test_gpu_cabi_c.py (nvcc only links the CUDA runtime).
+ * the outputs, then checks the host-buffer entry points (oc_step_host) against the device-pointer path.  Compiled and run by tests/test_gpu_cabi_c.py (nvcc only links the CUDA runtime).
  *
  *      - - * - -          tiles: 1 Counter, 3 Delivery, 2 Cutboard, 0 Floor
  *      t       p          objects: Tomato on (0,1), Plate on (4,1)
@@ -86,6 +86,46 @@ int main(void) {
     CHECK(oc_rollout(env, 8, d_obs, d_rew, d_done, NULL, NULL));
     CU(cudaDeviceSynchronize());
     if (oc_launch_count(env) < 203) { fprintf(stderr, "launch count %llu\n", (unsigned long long)oc_launch_count(env)); return 1; }
+    /* host-buffer entry points: same env continued through oc_step_host with pinned buffers from
+     * oc_host_alloc must agree with the device-pointer path run on a second handle */
+    {
+        cfg.seed = 11;
+        oc_env *ha = NULL, *hb = NULL;
+        CHECK(oc_create(&cfg, &ha));
+        CHECK(oc_create(&cfg, &hb));
+        int32_t* p_act; float *p_obs, *p_rew, *p_term; uint8_t* p_done;
+        CHECK(oc_host_alloc(sizeof(h_act), (void**)&p_act));
+        CHECK(oc_host_alloc(sizeof(h_obs), (void**)&p_obs));
+        CHECK(oc_host_alloc(sizeof(h_obs), (void**)&p_term));
+        CHECK(oc_host_alloc(E * A * sizeof(float), (void**)&p_rew));
+        CHECK(oc_host_alloc(E, (void**)&p_done));
+        memset(p_term, 0, sizeof(h_obs));
+        CHECK(oc_reset_host(ha, NULL, NULL, p_obs, NULL));
+        CHECK(oc_reset(hb, NULL, NULL, d_obs, NULL));
+        long term_rows = 0;
+        for (int t = 0; t < 120; ++t) {
+            for (int i = 0; i < E * A; ++i) { p_act[2 * i] = rand() % 4; p_act[2 * i + 1] = rand() % C; }
+            CHECK(oc_step_host(ha, p_act, p_obs, p_rew, NULL, p_done, p_term, OC_FLAG_AUTO_RESET, NULL));
+            CU(cudaMemcpy(d_act, p_act, sizeof(h_act), cudaMemcpyHostToDevice));
+            CHECK(oc_step(hb, d_act, d_obs, d_rew, NULL, d_done, NULL, OC_FLAG_AUTO_RESET, NULL));
+            CU(cudaMemcpy(h_obs, d_obs, sizeof(h_obs), cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(h_done, d_done, sizeof(h_done), cudaMemcpyDeviceToHost));
+            if (memcmp(h_obs, p_obs, sizeof(h_obs)) != 0 || memcmp(h_done, p_done, E) != 0) {
+                fprintf(stderr, "oc_step_host differs from oc_step at t=%d\n", t); return 1;
+            }
+            for (int e = 0; e < E; ++e)
+                if (p_done[e]) {                      /* terminal observation: the clock feature of the last step = 49/50 or earlier */
+                    const float ts = p_term[((size_t)e * A) * F + off[OC_OBS_TIMESTEP]];
+                    if (!(ts > 0.0f && ts <= 1.0f)) { fprintf(stderr, "terminal observation missing (ts=%f)\n", ts); return 1; }
+                    term_rows += 1;
+                }
+        }
+        if (term_rows != (long)E * 2) { fprintf(stderr, "expected %d terminal observations, got %ld\n", E * 2, term_rows); return 1; }
+        CHECK(oc_host_free(p_act)); CHECK(oc_host_free(p_obs)); CHECK(oc_host_free(p_term));
+        CHECK(oc_host_free(p_rew)); CHECK(oc_host_free(p_done));
+        CHECK(oc_destroy(ha)); CHECK(oc_destroy(hb));
+        cfg.seed = 7;
+    }
     /* error path: a level with two tomatoes is outside the supported domain */
     cfg.object_contents[1] = 1;
     oc_env* bad = NULL;
