@@ -375,7 +375,11 @@ def main():
         Ke = min(K, 200)
         henv = OvercookedHostVecEnv(ns, num_envs=E, device_index=local_rank, seed=1234 + rank, auto_reset=True,
                                     terminal_observations=False)
-        host_actions = actions[:8].cpu().numpy()           # the steps' inputs live in host memory
+        host_actions = []                                  # the steps' inputs live in pinned host memory
+        for i in range(8):
+            pa = henv.pinned_array((E, A, 2), "int32")
+            pa[...] = actions[i].cpu().numpy()
+            host_actions.append(pa)
         henv.reset()
         for i in range(3):
             henv.step(host_actions[i])

@@ -64,17 +64,18 @@ class OvercookedHostVecEnv:
         self.obs_layout = {k: slice(off[i], off[i] + size[i]) for i, k in enumerate(_cabi.OBS_KEYS)}
         self.observation_space, self.action_space = make_spaces(self.level, a.num_communication)
         E, A, F = self.num_envs, self.num_agents, self.obs_width
-        self.obs = self._pinned_array((E, A, F), np.float32)
-        self.rewards = self._pinned_array((E, A), np.float32)
-        self.dones = self._pinned_array((E,), np.uint8)
-        self.actions = self._pinned_array((E, A, 2), np.int32)
-        self.terminal_obs = self._pinned_array((E, A, F), np.float32) if (terminal_observations and auto_reset) else None
+        self.obs = self.pinned_array((E, A, F), np.float32)
+        self.rewards = self.pinned_array((E, A), np.float32)
+        self.dones = self.pinned_array((E,), np.uint8)
+        self.actions = self.pinned_array((E, A, 2), np.int32)
+        self.terminal_obs = self.pinned_array((E, A, F), np.float32) if (terminal_observations and auto_reset) else None
         self._infos = [{} for _ in range(E)]
         self._touched = ()
 
     # ------------------------------------------------------------------ plumbing
-    def _pinned_array(self, shape, dtype) -> np.ndarray:
-        """numpy view of page-locked host memory from oc_host_alloc (freed in close())."""
+    def pinned_array(self, shape, dtype) -> np.ndarray:
+        """numpy view of page-locked host memory from oc_host_alloc (freed in close()).  int32
+        [E, A, 2] arrays made here can be passed to `step` directly (no staging copy)."""
         n = int(np.prod(shape)) * np.dtype(dtype).itemsize
         ptr = C.c_void_p()
         self.lib.check(self.lib.host_alloc(n, C.byref(ptr)), "oc_host_alloc")
@@ -104,14 +105,16 @@ class OvercookedHostVecEnv:
         return self.obs
 
     def step(self, actions: np.ndarray):
-        if actions is not self.actions:
-            a = np.asarray(actions)
+        a = actions
+        if not (isinstance(a, np.ndarray) and a.dtype == np.int32 and a.flags.c_contiguous and a.shape == self.actions.shape):
+            a = np.asarray(actions)                  # any integer array-like: converted into the env's pinned buffer
             if a.shape != self.actions.shape:
                 raise ValueError("actions must have shape %s (nav, comm per agent)" % (self.actions.shape,))
             np.copyto(self.actions, a, casting="same_kind")
+            a = self.actions
         flags = _cabi.OC_FLAG_AUTO_RESET if self.auto_reset else 0
         self.lib.check(self.lib.set_device(self.device_index), "oc_set_device")
-        self.lib.check(self.lib.step_host(self._handle, self._p(self.actions), self._p(self.obs), self._p(self.rewards),
+        self.lib.check(self.lib.step_host(self._handle, self._p(a), self._p(self.obs), self._p(self.rewards),
                                           None, self._p(self.dones), self._p(self.terminal_obs), flags, None),
                        "oc_step_host")
         d = self.dones.view(np.bool_)
