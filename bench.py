@@ -187,10 +187,12 @@ def main():
 
     import torch
     import torch.distributed as dist
+    from gym_comm_b200.sharding import bind_cpu_to_device
     from gym_comm_b200.vec_env import OvercookedVecEnv
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
     torch.cuda.set_device(local_rank)
+    affinity = bind_cpu_to_device(local_rank) if world > 1 else False      # NUMA-local pinned buffers (e2e path)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -395,7 +397,8 @@ def main():
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         e2e = {"value": float(E) * A * Ke * world / float(tm.item()), "unit": "agent-steps/s",
                "h2d_bytes_per_step": E * A * 2 * 4, "d2h_bytes_per_step": E * A * F * 4 + E * A * 4 + E,
-               "steps": Ke, "api": "OvercookedHostVecEnv.step = C ABI oc_step_host, pinned numpy buffers, synchronised every step"}
+               "steps": Ke, "api": "OvercookedHostVecEnv.step = C ABI oc_step_host, pinned numpy buffers, synchronised every step",
+               "cpu_affinity": "nvml (GPU-local cores)" if affinity else "none"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -54,3 +54,26 @@ def make_sharded_env(arglist, total_envs: int, seed: int = 0, **kw):
     lo, hi = shard_range(total_envs, rank, world)
     return OvercookedVecEnv(arglist, num_envs=hi - lo, device=torch.device("cuda", local),
                             seed=shard_seed(seed, rank), **kw), (lo, hi)
+
+
+def bind_cpu_to_device(device_index: int) -> bool:
+    """Pin the calling process to the CPU cores NVML reports as local to GPU `device_index` (same NUMA
+    node / PCIe root).  Matters for the host-buffer path only: page-locked buffers allocated afterwards
+    land on that node, so eight ranks copying observations to the host do not all cross the socket
+    interconnect.  Returns False (and changes nothing) when NVML is unavailable; `OC_NO_AFFINITY=1`
+    disables it."""
+    if os.environ.get("OC_NO_AFFINITY") == "1":
+        return False
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[device_index]) if visible and visible.split(",")[device_index].isdigit() else device_index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            pynvml.nvmlDeviceSetCpuAffinity(h)
+        finally:
+            pynvml.nvmlShutdown()
+        return True
+    except Exception:
+        return False

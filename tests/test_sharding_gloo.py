@@ -60,3 +60,17 @@ def test_shard_range_properties():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_bind_cpu_to_device_is_safe_without_a_gpu(monkeypatch):
+    """No NVML / no GPU: the helper reports False and leaves the affinity mask alone."""
+    import os
+    from gym_comm_b200.sharding import bind_cpu_to_device
+    before = os.sched_getaffinity(0)
+    monkeypatch.setenv("OC_NO_AFFINITY", "1")
+    assert bind_cpu_to_device(0) is False
+    monkeypatch.delenv("OC_NO_AFFINITY")
+    import torch
+    if not torch.cuda.is_available():
+        assert bind_cpu_to_device(0) is False
+        assert os.sched_getaffinity(0) == before
