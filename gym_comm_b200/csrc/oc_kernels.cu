@@ -20,7 +20,7 @@ using namespace ock;
 // kernels
 // =============================================================================================
 
-// dynamic shared memory: [table blob][per warp: 32 byte-rows]
+// dynamic shared memory: [table blob][per warp: nb env rows (float or biased-byte format)]
 template <int A, int NOBJ, int MODE>
 __global__ void __launch_bounds__(256)
 oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
