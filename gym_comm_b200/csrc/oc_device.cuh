@@ -204,7 +204,7 @@ struct Info {
     uint32_t pres, deliv;   // subtasks whose goal template exists somewhere / on the first Delivery tile
 };
 
-template <int A, int NOBJ>
+template <int A, int NOBJ, int NF>
 __device__ __forceinline__ Info gather_info(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb) {
     Info in;
     in.fword[0] = in.fword[1] = in.fword[2] = OCK_DEAD;
@@ -218,7 +218,7 @@ __device__ __forceinline__ Info gather_info(const Env<A, NOBJ>& e, const OcParam
         in.pres |= tm;
         if ((o & 0x00FF0000u) == ((uint32_t)p.delivery0 << 16)) in.deliv |= tm;   // first Delivery tile only (:259,:402)
 #pragma unroll
-        for (int f = 0; f < 3; ++f)
+        for (int f = 0; f < NF; ++f)
             if ((o >> f) & 1u) in.fword[f] = o;
         if (o & 8u) {
             const uint32_t key = ((uint32_t)((e.ranks >> (4 * (o & 0xFu))) & 15ull) << 8) | (o >> 24);
@@ -239,7 +239,7 @@ __device__ __forceinline__ Info gather_info(const Env<A, NOBJ>& e, const OcParam
 //   done                            :243-270
 //   reward/subtask_reward           :399-432
 //   calculate_reward_shaping x2     :272-397
-template <int A, int NOBJ>
+template <int A, int NOBJ, int NF>
 __device__ __forceinline__ Info env_step(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
                                          const int (&nav)[A], int comm0, int comm1,
                                          double& reward, bool& done) {
@@ -339,7 +339,7 @@ __device__ __forceinline__ Info env_step(Env<A, NOBJ>& e, const OcParams& p, con
     e.w0 = t | (next_stamp << 16) | (nkeys << 24);
 
     // ---- done + sparse reward through the signature -> subtask-mask table
-    const Info in = gather_info<A, NOBJ>(e, p, tb);
+    const Info in = gather_info<A, NOBJ, NF>(e, p, tb);
     const uint32_t dl = in.deliv & p.deliver_mask;
     done = (p.T != 0 && t >= (uint32_t)p.T) || (dl == p.deliver_mask);       // :243-270
     const uint32_t nw = in.pres & ~e.countbits & p.nondeliver_mask;          // count rose (:409-415)
@@ -351,7 +351,9 @@ __device__ __forceinline__ Info env_step(Env<A, NOBJ>& e, const OcParams& p, con
     // (1) Chop subtasks still open: U = [pd(agent, FreshX)], needs min(U) and len(U)
     int lenU = 0, nf[3];
 #pragma unroll
-    for (int f = 0; f < 3; ++f) {
+    for (int f = 0; f < 3; ++f) nf[f] = 0;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {                                          // NF = food channels this level can use
         const bool fresh = (in.fword[f] & 0x7Fu) == (1u << f);              // X alone and un-chopped
         nf[f] = fresh ? __popc(~e.completed & p.chop_mask[f]) : 0;
         lenU += nf[f];
@@ -369,18 +371,19 @@ __device__ __forceinline__ Info env_step(Env<A, NOBJ>& e, const OcParams& p, con
             if ((o & 8u) && obj_held(o)) {                                   // a carried plate-bearing object
                 const uint8_t* row = tb.pd + obj_cell(o) * p.ncell;
 #pragma unroll
-                for (int f = 0; f < 3; ++f)
+                for (int f = 0; f < NF; ++f)
                     if (((p.item_foods >> f) & 1u) && obj_alive(in.fword[f]))
                         mP[f] = min(mP[f], (int)row[obj_cell(in.fword[f])]);
             }
         }
 #pragma unroll
-        for (int f = 0; f < 3; ++f)
+        for (int f = 0; f < NF; ++f)
             if (((p.item_foods >> f) & 1u) && mP[f] != 0) { lenP += 1; minP = min(minP, mP[f]); }
         // Food-Food pairs, first item alphabetically first: (Lettuce, Onion) (Lettuce, Tomato) (Onion, Tomato)
         const int px[3] = {1, 1, 2}, py[3] = {2, 0, 0};
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
+            if (px[q] >= NF || py[q] >= NF) continue;                            // compile-time after unrolling
             if (((p.item_foods >> px[q]) & 1u) && ((p.item_foods >> py[q]) & 1u)) {
                 const uint32_t ox = in.fword[px[q]], oy = in.fword[py[q]];
                 int m = p.M;
@@ -397,7 +400,7 @@ __device__ __forceinline__ Info env_step(Env<A, NOBJ>& e, const OcParams& p, con
             const uint8_t* row = tb.pd + e.acell[a] * p.ncell;
             int minU = 1 << 20;
 #pragma unroll
-            for (int f = 0; f < 3; ++f)
+            for (int f = 0; f < NF; ++f)
                 if (nf[f] > 0) minU = min(minU, (int)row[obj_cell(in.fword[f])]);
             tp[a] = tb.q[minU + p.M + (lenU - 1) * 2 * p.M];                         // :303-304
             if (lenP > 0) tp[a] = __dadd_rn(tp[a], (double)lenP);                    // :363
@@ -445,7 +448,7 @@ __device__ __forceinline__ void channel_features(const Tables& tb, uint32_t word
     ey = __fmaf_rn(dy, hid, 0.0f);
 }
 
-template <int A, int NOBJ>
+template <int A, int NOBJ, int NF>
 __device__ __forceinline__ void build_rows_f32(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
                                                const Info& in, float ts, float* __restrict__ row /* zero-filled */) {
     const float2 a0 = tb.xyf[e.acell[0]], a1 = tb.xyf[e.acell[1]];
@@ -469,6 +472,7 @@ __device__ __forceinline__ void build_rows_f32(const Env<A, NOBJ>& e, const OcPa
             const float2 me = (k == 0) ? a0 : ((k == 1) ? a1 : tb.xyf[e.acell[k]]);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
+                if (c < 3 && c >= NF) continue;                 // a food this level never holds: features stay 0
                 const uint32_t w = (c < 3) ? in.fword[c] : in.pword;
                 if (obj_alive(w)) {                                            // absent channel: all zeros already
                     float hid, ex, ey, st;
@@ -491,7 +495,7 @@ __device__ __forceinline__ void build_rows_f32(const Env<A, NOBJ>& e, const OcPa
 }
 
 // one observer's row as biased bytes (r = F bytes, 0x80-filled)
-template <int A, int NOBJ>
+template <int A, int NOBJ, int NF>
 __device__ __forceinline__ void build_row_u8_one(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
                                                  const Info& in, int k, uint8_t* __restrict__ r) {
     const uint32_t xy0 = tb.xy16[e.acell[0]], xy1 = tb.xy16[e.acell[1]];
@@ -512,6 +516,7 @@ __device__ __forceinline__ void build_row_u8_one(const Env<A, NOBJ>& e, const Oc
         const float2 me = tb.xyf[e.acell[k]];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+            if (c < 3 && c >= NF) continue;                     // a food this level never holds: features stay 0
             const uint32_t w = (c < 3) ? in.fword[c] : in.pword;
             if (obj_alive(w)) {
                 float hid, ex, ey, st;
@@ -526,11 +531,11 @@ __device__ __forceinline__ void build_row_u8_one(const Env<A, NOBJ>& e, const Oc
     for (uint32_t m = e.completed; m != 0; m &= m - 1) r[p.off_completed + (__ffs((int)m) - 1)] = OCK_BIAS + 1;
 }
 
-template <int A, int NOBJ>
+template <int A, int NOBJ, int NF>
 __device__ __forceinline__ void build_rows_u8(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
                                               const Info& in, uint8_t* __restrict__ row /* 0x80-filled */) {
 #pragma unroll
-    for (int k = 0; k < A; ++k) build_row_u8_one<A, NOBJ>(e, p, tb, in, k, row + k * p.F);
+    for (int k = 0; k < A; ++k) build_row_u8_one<A, NOBJ, NF>(e, p, tb, in, k, row + k * p.F);
 }
 
 // warp-cooperative fill of the warp's 32 rows with the "all features 0.0" pattern
@@ -647,11 +652,11 @@ __device__ __forceinline__ float timestep_of(const Env<A, NOBJ>& e, const OcPara
     return (p.o_ts >= 0) ? tb.ts[t] : (float)__ddiv_rn((double)t, (double)p.T);
 }
 
-template <int A, int NOBJ, bool ROWF>
+template <int A, int NOBJ, int NF, bool ROWF>
 __device__ __forceinline__ void fill_rows(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
                                           const Info& in, float ts, uint8_t* myrow) {
-    if (ROWF) build_rows_f32<A, NOBJ>(e, p, tb, in, ts, reinterpret_cast<float*>(myrow));
-    else build_rows_u8<A, NOBJ>(e, p, tb, in, myrow);
+    if (ROWF) build_rows_f32<A, NOBJ, NF>(e, p, tb, in, ts, reinterpret_cast<float*>(myrow));
+    else build_rows_u8<A, NOBJ, NF>(e, p, tb, in, myrow);
 }
 
 // byte rows only: after the expansion (and a __syncwarp) each thread stores the timestep feature
@@ -666,7 +671,7 @@ __device__ __forceinline__ void store_timesteps(const OcParams& p, float* __rest
 // (32, or 16 / 8 / 4 for wide float rows, so that enough warps stay resident); the envs go out in
 // 32 / nb passes, lanes [pass * nb, pass * nb + nb) filling the buffer in their pass.  Rows must be
 // clear (and, with bulk stores, read out) on entry; they are dirty on exit.
-template <int A, int NOBJ, int MODE /* 0 byte rows, 1 float rows, 2 float rows in several passes */>
+template <int A, int NOBJ, int NF, int MODE /* 0 byte rows, 1 float rows, 2 float rows in several passes */>
 __device__ __forceinline__ void emit_obs(const Env<A, NOBJ>& e, const Info& in, bool valid, const OcParams& p,
                                          const Tables& tb, uint8_t* wrows, int lane,
                                          float* __restrict__ out_env0 /* warp's first env row */, int nvalid) {
@@ -681,7 +686,7 @@ __device__ __forceinline__ void emit_obs(const Env<A, NOBJ>& e, const Info& in, 
             warp_clear_rows<ROWF>(wrows, p.warp_row_bytes, lane);
             __syncwarp();
         }
-        if (valid && (!MULTI || (lane >> p.nb_shift) == pass)) fill_rows<A, NOBJ, ROWF>(e, p, tb, in, ts, myrow);
+        if (valid && (!MULTI || (lane >> p.nb_shift) == pass)) fill_rows<A, NOBJ, NF, ROWF>(e, p, tb, in, ts, myrow);
         __syncwarp();
         const int first = MULTI ? (pass << p.nb_shift) : 0;
         const int nv = min(MULTI ? p.nb : 32, nvalid - first);
@@ -695,11 +700,11 @@ __device__ __forceinline__ void emit_obs(const Env<A, NOBJ>& e, const Info& in, 
 
 // a single thread emits its own env's rows (rare path: terminal observations); its row must be
 // clear on entry and is clear again on exit
-template <int A, int NOBJ, bool ROWF>
+template <int A, int NOBJ, int NF, bool ROWF>
 __device__ __forceinline__ void thread_emit_rows(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
                                                  const Info& in, uint8_t* myrow, float* __restrict__ out) {
     const float ts = timestep_of<A, NOBJ>(e, p, tb);
-    fill_rows<A, NOBJ, ROWF>(e, p, tb, in, ts, myrow);
+    fill_rows<A, NOBJ, NF, ROWF>(e, p, tb, in, ts, myrow);
     if (ROWF) {
         for (int j = 0; j < p.row_bytes; ++j) out[j] = reinterpret_cast<const float*>(myrow)[j];
     } else {
@@ -712,18 +717,18 @@ __device__ __forceinline__ void thread_emit_rows(const Env<A, NOBJ>& e, const Oc
 
 // infos["terminal_observation"] of the envs of this warp that just finished (SB3 VecEnv contract);
 // lanes that share a row slot (nb < 32) take turns.  Rows must be clear; they stay clear.
-template <int A, int NOBJ, int MODE>
+template <int A, int NOBJ, int NF, int MODE>
 __device__ __forceinline__ void warp_terminal_obs(const Env<A, NOBJ>& e, const Info& in, bool fin, const OcParams& p,
                                                   const Tables& tb, uint8_t* wrows, int lane,
                                                   float* __restrict__ term_row) {
     constexpr bool ROWF = MODE != 0;
     if (MODE != 2) {
-        if (fin) thread_emit_rows<A, NOBJ, ROWF>(e, p, tb, in, wrows + lane * p.row_stride, term_row);
+        if (fin) thread_emit_rows<A, NOBJ, NF, ROWF>(e, p, tb, in, wrows + lane * p.row_stride, term_row);
         return;
     }
     uint8_t* myrow = wrows + (lane & (p.nb - 1)) * p.row_stride;
     for (int pass = 0; pass < p.obs_passes; ++pass) {
-        if (fin && (lane >> p.nb_shift) == pass) thread_emit_rows<A, NOBJ, ROWF>(e, p, tb, in, myrow, term_row);
+        if (fin && (lane >> p.nb_shift) == pass) thread_emit_rows<A, NOBJ, NF, ROWF>(e, p, tb, in, myrow, term_row);
         __syncwarp();
     }
 }
@@ -737,7 +742,7 @@ __device__ __forceinline__ void finish_episode(Env<A, NOBJ>& e, const OcParams& 
 }
 
 // oc_step, part 1: dynamics + reward / done outputs (does not touch the observation rows)
-template <int A, int NOBJ>
+template <int A, int NOBJ, int NF>
 __device__ __forceinline__ Info step_logic(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
                                            const int (&nav)[A], int comm0, int comm1, uint32_t env,
                                            float* __restrict__ rew32, double* __restrict__ rew64,
@@ -746,7 +751,7 @@ __device__ __forceinline__ Info step_logic(Env<A, NOBJ>& e, const OcParams& p, c
     // out-of-range message index -> zero vector (the reference raises IndexError)
     const int c0 = ((uint32_t)comm0 < (uint32_t)p.C) ? comm0 : (int)OCK_COMM_NONE;
     const int c1 = ((uint32_t)comm1 < (uint32_t)p.C) ? comm1 : (int)OCK_COMM_NONE;
-    const Info in = env_step<A, NOBJ>(e, p, tb, nav, c0, c1, reward, done);
+    const Info in = env_step<A, NOBJ, NF>(e, p, tb, nav, c0, c1, reward, done);
     if (rew64 != nullptr) rew64[env] = reward;
     if (rew32 != nullptr) {
         const float r = (float)reward;
@@ -760,7 +765,7 @@ __device__ __forceinline__ Info step_logic(Env<A, NOBJ>& e, const OcParams& p, c
 // one env, one step of the fused synthetic rollout: Philox actions (nav ~ U{0..3}, comm ~ U{0..C-1}),
 // auto-reset always on.  Draw layout (same in oracle/oc_oracle.c): counter (env, global step,
 // 'ACTS', 0); nav_k = bits [2k, 2k+2) of word 0; comm_0/1 = mulhi(word 1/2, C).
-template <int A, int NOBJ, bool ROWF>
+template <int A, int NOBJ, int NF, bool ROWF>
 __device__ __forceinline__ Info rollout_logic(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
                                               uint32_t env, uint32_t s, uint32_t step0,
                                               float* __restrict__ rew32, uint8_t* __restrict__ done_out,
@@ -788,7 +793,7 @@ __device__ __forceinline__ Info rollout_logic(Env<A, NOBJ>& e, const OcParams& p
         for (int k = 0; k < A; ++k) { ao[2 * k] = nav[k]; ao[2 * k + 1] = (k == 0) ? c0 : (k == 1 ? c1 : 0); }
     }
     double reward; bool done;
-    Info in = env_step<A, NOBJ>(e, p, tb, nav, c0, c1, reward, done);
+    Info in = env_step<A, NOBJ, NF>(e, p, tb, nav, c0, c1, reward, done);
     if (rew32 != nullptr) {
         const float rr = (float)reward;
 #pragma unroll
@@ -797,7 +802,7 @@ __device__ __forceinline__ Info rollout_logic(Env<A, NOBJ>& e, const OcParams& p
     if (done_out != nullptr) done_out[(size_t)s * p.E + env] = done ? 1 : 0;
     if (done) {                                      // no terminal observation in the fused rollout: rows untouched
         finish_episode<A, NOBJ>(e, p, tb, env);
-        in = gather_info<A, NOBJ>(e, p, tb);
+        in = gather_info<A, NOBJ, NF>(e, p, tb);
     }
     return in;
 }

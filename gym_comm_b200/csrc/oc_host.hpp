@@ -97,7 +97,7 @@ static inline int compile_config(const oc_config* c, HostImage& h, std::string& 
 
     OcParams& p = h.p;
     memset(&p, 0, sizeof(p));
-    p.E = c->num_envs; p.A = A; p.NOBJ = c->num_objects <= 4 ? 4 : 6;
+    p.E = c->num_envs; p.A = A;
     p.W = W; p.H = H; p.ncell = n; p.T = c->max_num_timesteps; p.C = C; p.S = S;
     p.F = 23 + S + 2 * C; p.fow = c->fow_radius; p.M = M;
     p.row_bytes = A * p.F;
@@ -213,6 +213,21 @@ static inline int compile_config(const oc_config* c, HostImage& h, std::string& 
         p.item_foods |= (uint32_t)b;
     }
     p.npairs = c->num_items * (c->num_items - 1) / 2;
+    // kernel shape (template instantiation): object slots and food channels the device loops run over.
+    // A food can only matter if some object, subtask goal, Chop subtask or recipe item names it.
+    {
+        uint32_t foods = p.item_foods;
+        for (int s = 0; s < c->num_objects; ++s) foods |= c->object_contents[s] & 7u;
+        for (int i = 0; i < S; ++i) foods |= (c->subtask_goal[i] & 7u) | (c->subtask_kind[i] == 0 ? (c->subtask_arg0[i] & 7u) : 0u);
+        const int nf = (foods & 4u) ? 3 : ((foods & 2u) ? 2 : 1);
+        if (c->num_objects <= 2 && nf == 1) { p.NOBJ = 2; p.NF = 1; }
+        else if (c->num_objects <= 4 && nf <= 2) { p.NOBJ = 4; p.NF = 2; }
+        else { p.NOBJ = 6; p.NF = 3; }
+        if (const char* sh = getenv("OC_KERNEL_SHAPE")) {       // A/B knob: force a larger shape
+            const int v = atoi(sh);
+            if (v >= 6) { p.NOBJ = 6; p.NF = 3; } else if (v >= 4 && p.NOBJ <= 4) { p.NOBJ = 4; p.NF = 2; }
+        }
+    }
 
     // tables
     std::vector<uint8_t> pd;

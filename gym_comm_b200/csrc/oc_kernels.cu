@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/overcooked_b200.h"
@@ -21,7 +22,7 @@ using namespace ock;
 // =============================================================================================
 
 // dynamic shared memory: [table blob][per warp: nb env rows (float or biased-byte format)]
-template <int A, int NOBJ, int MODE>
+template <int A, int NOBJ, int NF, int MODE>
 __global__ void __launch_bounds__(256)
 oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
                const int32_t* __restrict__ actions, float* __restrict__ obs,
@@ -58,7 +59,7 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
             const int2* a2 = reinterpret_cast<const int2*>(actions) + (size_t)env * A;
 #pragma unroll
             for (int k = 0; k < A; ++k) { const int2 v = __ldg(a2 + k); nav[k] = v.x & 3; comm[k] = v.y; }
-            in = step_logic<A, NOBJ>(e, p, tb, nav, comm[0], comm[1], (uint32_t)env, rew32, rew64, done_out, done);
+            in = step_logic<A, NOBJ, NF>(e, p, tb, nav, comm[0], comm[1], (uint32_t)env, rew32, rew64, done_out, done);
         }
         if (!first) {                                   // rows of the previous chunk: read out, then clear
             rows_wait_read(p);
@@ -68,20 +69,20 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
         first = false;
         const bool fin = valid && done && (flags & OC_FLAG_AUTO_RESET);
         if (term_obs != nullptr && __any_sync(0xFFFFFFFFu, fin))      // rare: some env of this warp finished
-            warp_terminal_obs<A, NOBJ, MODE>(e, in, fin, p, tb, wrows, lane, term_obs + (size_t)env * p.row_bytes);
+            warp_terminal_obs<A, NOBJ, NF, MODE>(e, in, fin, p, tb, wrows, lane, term_obs + (size_t)env * p.row_bytes);
         if (fin) {
             finish_episode<A, NOBJ>(e, p, tb, (uint32_t)env);
-            in = gather_info<A, NOBJ>(e, p, tb);
+            in = gather_info<A, NOBJ, NF>(e, p, tb);
         }
         if (valid) store_env<A, NOBJ>(e, state, p.E, env);
         const int env0 = base + warp * 32;
-        emit_obs<A, NOBJ, MODE>(e, in, valid, p, tb, wrows, lane, obs + (size_t)env0 * p.row_bytes, min(32, p.E - env0));
+        emit_obs<A, NOBJ, NF, MODE>(e, in, valid, p, tb, wrows, lane, obs + (size_t)env0 * p.row_bytes, min(32, p.E - env0));
     }
     rows_wait_done(p);
 }
 
 // n_steps steps per launch, state in registers, Philox actions (SURVEY section 8d synthetic inputs)
-template <int A, int NOBJ, int MODE>
+template <int A, int NOBJ, int NF, int MODE>
 __global__ void __launch_bounds__(256)
 oc_rollout_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, int n_steps, uint32_t step0,
                   float* __restrict__ obs, float* __restrict__ rew32, uint8_t* __restrict__ done_out,
@@ -105,12 +106,12 @@ oc_rollout_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
         // dynamics first: they do not touch the rows, so the copy engine may still be reading the
         // previous step's rows out of shared memory while this runs
         Info in;
-        if (valid) in = rollout_logic<A, NOBJ, ROWF>(e, p, tb, (uint32_t)env, (uint32_t)s, step0, rew32, done_out, actions_out, actions_in);
+        if (valid) in = rollout_logic<A, NOBJ, NF, ROWF>(e, p, tb, (uint32_t)env, (uint32_t)s, step0, rew32, done_out, actions_out, actions_in);
         if (obs != nullptr) {
             if (s > 0) rows_wait_read(p);
             warp_clear_rows<ROWF>(wrows, p.warp_row_bytes, lane);
             __syncwarp();
-            emit_obs<A, NOBJ, MODE>(e, in, valid, p, tb, wrows, lane,
+            emit_obs<A, NOBJ, NF, MODE>(e, in, valid, p, tb, wrows, lane,
                                     obs + (size_t)s * step_floats + (size_t)env0 * p.row_bytes, nvalid);
         }
     }
@@ -119,7 +120,7 @@ oc_rollout_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
 }
 
 // reset (masked) + observation of every env
-template <int A, int NOBJ, int MODE>
+template <int A, int NOBJ, int NF, int MODE>
 __global__ void __launch_bounds__(256)
 oc_reset_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, const uint8_t* __restrict__ mask,
                 const int32_t* __restrict__ placements, float* __restrict__ obs, int initial) {
@@ -139,11 +140,11 @@ oc_reset_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, c
     if (valid) {
         reset_logic<A, NOBJ>(e, p, tb, (uint32_t)env, initial != 0, mask, placements);
         store_env<A, NOBJ>(e, state, p.E, env);
-        if (obs != nullptr) in = gather_info<A, NOBJ>(e, p, tb);
+        if (obs != nullptr) in = gather_info<A, NOBJ, NF>(e, p, tb);
     }
     const int env0 = blockIdx.x * blockDim.x + warp * 32;
     if (obs != nullptr)
-        emit_obs<A, NOBJ, MODE>(e, in, valid, p, tb, wrows, lane, obs + (size_t)env0 * p.row_bytes, min(32, p.E - env0));
+        emit_obs<A, NOBJ, NF, MODE>(e, in, valid, p, tb, wrows, lane, obs + (size_t)env0 * p.row_bytes, min(32, p.E - env0));
     rows_wait_done(p);
 }
 
@@ -205,17 +206,22 @@ struct oc_env {
 // kernel template MODE: 0 byte rows, 1 float rows (all 32 envs of a warp in one pass), 2 float rows in passes
 static int row_mode(const OcParams& p) { return !p.rowf ? 0 : (p.obs_passes > 1 ? 2 : 1); }
 
+template <int N, int NFOOD> constexpr int shape_nobj(std::integer_sequence<int, N, NFOOD>) { return N; }
+template <int N, int NFOOD> constexpr int shape_nf(std::integer_sequence<int, N, NFOOD>) { return NFOOD; }
+
 template <typename F>
 static int dispatch(int A, int NOBJ, int mode, F&& f) {
-#define OC_CASE(a, n)                                                                                                   \
+    // shapes: (2 object slots, 1 food channel), (4, 2), (6, 3) -- chosen by compile_config
+#define OC_CASE(a, n, nfood)                                                                                            \
     if (A == a && NOBJ == n) {                                                                                          \
         using IA = std::integral_constant<int, a>;                                                                      \
-        using IN = std::integral_constant<int, n>;                                                                      \
-        if (mode == 2) return f(IA(), IN(), std::integral_constant<int, 2>());                                          \
-        if (mode == 1) return f(IA(), IN(), std::integral_constant<int, 1>());                                          \
-        return f(IA(), IN(), std::integral_constant<int, 0>());                                                         \
+        using IS = std::integer_sequence<int, n, nfood>;                                                                \
+        if (mode == 2) return f(IA(), IS(), std::integral_constant<int, 2>());                                          \
+        if (mode == 1) return f(IA(), IS(), std::integral_constant<int, 1>());                                          \
+        return f(IA(), IS(), std::integral_constant<int, 0>());                                                         \
     }
-    OC_CASE(2, 4) OC_CASE(3, 4) OC_CASE(4, 4) OC_CASE(2, 6) OC_CASE(3, 6) OC_CASE(4, 6)
+    OC_CASE(2, 2, 1) OC_CASE(3, 2, 1) OC_CASE(4, 2, 1) OC_CASE(2, 4, 2) OC_CASE(3, 4, 2) OC_CASE(4, 4, 2)
+    OC_CASE(2, 6, 3) OC_CASE(3, 6, 3) OC_CASE(4, 6, 3)
 #undef OC_CASE
     return fail(OC_ERR_INVALID, "unsupported (num_agents, num_objects)");
 }
@@ -262,16 +268,16 @@ extern "C" int oc_create(const oc_config* c, oc_env** out) {
     const int smem_optin = (int)smem_cta_max;
     int caps[9] = {0};
     int rc = dispatch(p.A, p.NOBJ, row_mode(p), [&](auto a, auto nobj, auto rf) -> int {
-        constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
+        constexpr int AA = decltype(a)::value, NN = shape_nobj(nobj), FF = shape_nf(nobj);
         constexpr int RF = decltype(rf)::value;
-        CUDA_TRY(cudaFuncSetAttribute(oc_step_kernel<AA, NN, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
-        CUDA_TRY(cudaFuncSetAttribute(oc_rollout_kernel<AA, NN, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
-        CUDA_TRY(cudaFuncSetAttribute(oc_reset_kernel<AA, NN, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(oc_step_kernel<AA, NN, FF, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(oc_rollout_kernel<AA, NN, FF, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(oc_reset_kernel<AA, NN, FF, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
         for (int t = 32; t <= 256; t += 32) {
             if (smem_for(t) > smem_cta_max) continue;
             int cs = 0, cr = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cs, oc_step_kernel<AA, NN, RF>, t, smem_for(t)));
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cr, oc_rollout_kernel<AA, NN, RF>, t, smem_for(t)));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cs, oc_step_kernel<AA, NN, FF, RF>, t, smem_for(t)));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cr, oc_rollout_kernel<AA, NN, FF, RF>, t, smem_for(t)));
             caps[t / 32] = std::min(cs, cr);
         }
         return OC_OK;
@@ -316,10 +322,10 @@ extern "C" int oc_create(const oc_config* c, oc_env** out) {
     p.blob = h->blob; p.ts_table = h->ts;
 
     rc = dispatch(p.A, p.NOBJ, row_mode(p), [&](auto a, auto nobj, auto rf) -> int {
-        constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
+        constexpr int AA = decltype(a)::value, NN = shape_nobj(nobj), FF = shape_nf(nobj);
         constexpr int RF = decltype(rf)::value;
         const int grid = (p.E + h->threads - 1) / h->threads;
-        oc_reset_kernel<AA, NN, RF><<<grid, h->threads, h->smem_bytes, 0>>>(p, h->state, nullptr, nullptr, nullptr, 1);
+        oc_reset_kernel<AA, NN, FF, RF><<<grid, h->threads, h->smem_bytes, 0>>>(p, h->state, nullptr, nullptr, nullptr, 1);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaDeviceSynchronize());
         return OC_OK;
@@ -368,10 +374,10 @@ extern "C" int oc_reset(oc_env* h, const uint8_t* mask, const int32_t* placement
     if (int dc = check_device(h)) return dc;
     const OcParams& p = h->p;
     int rc = dispatch(p.A, p.NOBJ, row_mode(p), [&](auto a, auto nobj, auto rf) -> int {
-        constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
+        constexpr int AA = decltype(a)::value, NN = shape_nobj(nobj), FF = shape_nf(nobj);
         constexpr int RF = decltype(rf)::value;
         const int grid = (p.E + h->threads - 1) / h->threads;
-        oc_reset_kernel<AA, NN, RF><<<grid, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(p, h->state, mask, placements, obs, 0);
+        oc_reset_kernel<AA, NN, FF, RF><<<grid, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(p, h->state, mask, placements, obs, 0);
         CUDA_TRY(cudaGetLastError());
         return OC_OK;
     });
@@ -386,7 +392,7 @@ extern "C" int oc_step(oc_env* h, const int32_t* actions, float* obs, float* rew
     if (int dc = check_device(h)) return dc;
     const OcParams& p = h->p;
     int rc = dispatch(p.A, p.NOBJ, row_mode(p), [&](auto a, auto nobj, auto rf) -> int {
-        constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
+        constexpr int AA = decltype(a)::value, NN = shape_nobj(nobj), FF = shape_nf(nobj);
         constexpr int RF = decltype(rf)::value;
         const int grid = h->step_grid;
         cudaLaunchConfig_t cfg;
@@ -399,7 +405,7 @@ extern "C" int oc_step(oc_env* h, const int32_t* actions, float* obs, float* rew
         cfg.attrs = attr; cfg.numAttrs = h->pdl ? 1 : 0;
         OcParams ps = p;
         if (ps.rowf && !ps.use_tma && h->tma_rows_in_step) ps.use_tma = 2;      // padded float rows: per-row bulk copies
-        CUDA_TRY(cudaLaunchKernelEx(&cfg, oc_step_kernel<AA, NN, RF>, ps, h->state, actions, obs, rew_f32, rew_f64,
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, oc_step_kernel<AA, NN, FF, RF>, ps, h->state, actions, obs, rew_f32, rew_f64,
                                     done, term_obs, flags));
         return OC_OK;
     });
@@ -429,10 +435,10 @@ static int launch_rollout(oc_env* h, int32_t n_steps, float* obs, float* rew_f32
     if (int dc = check_device(h)) return dc;
     const OcParams& p = h->p;
     int rc = dispatch(p.A, p.NOBJ, row_mode(p), [&](auto a, auto nobj, auto rf) -> int {
-        constexpr int AA = decltype(a)::value, NN = decltype(nobj)::value;
+        constexpr int AA = decltype(a)::value, NN = shape_nobj(nobj), FF = shape_nf(nobj);
         constexpr int RF = decltype(rf)::value;
         const int grid = (p.E + h->threads - 1) / h->threads;
-        oc_rollout_kernel<AA, NN, RF><<<grid, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(
+        oc_rollout_kernel<AA, NN, FF, RF><<<grid, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(
             p, h->state, n_steps, h->rollout_step, obs, rew_f32, done, actions_out, actions_in);
         CUDA_TRY(cudaGetLastError());
         return OC_OK;

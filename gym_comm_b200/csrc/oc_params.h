@@ -27,7 +27,7 @@
 #define OCK_COMM_NONE 0xFFFFu
 
 struct OcParams {
-    int32_t E, A, NOBJ;
+    int32_t E, A, NOBJ, NF;   // NOBJ / NF: object slots (2 / 4 / 6) and food channels (1 / 2 / 3) the kernels are instantiated for
     int32_t W, H, ncell;
     int32_t T, C, S, F;
     int32_t fow, M;

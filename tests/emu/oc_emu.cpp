@@ -10,6 +10,7 @@
 #include "../../gym_comm_b200/csrc/oc_host.hpp"
 
 #include <string>
+#include <utility>
 #include <vector>
 
 using namespace ock;
@@ -24,14 +25,19 @@ struct emu_env {
 };
 static std::string g_err;
 
+template <int N, int NFOOD> constexpr int shape_nobj(std::integer_sequence<int, N, NFOOD>) { return N; }
+template <int N, int NFOOD> constexpr int shape_nf(std::integer_sequence<int, N, NFOOD>) { return NFOOD; }
+
 template <typename F>
 static int dispatch(int A, int NOBJ, int rowf, F&& f) {
-#define OC_CASE(a, n)                                                                                              \
+#define OC_CASE(a, n, nfood)                                                                                       \
     if (A == a && NOBJ == n) {                                                                                     \
-        if (rowf) return f(std::integral_constant<int, a>(), std::integral_constant<int, n>(), std::true_type());  \
-        return f(std::integral_constant<int, a>(), std::integral_constant<int, n>(), std::false_type());           \
+        using IS = std::integer_sequence<int, n, nfood>;                                                           \
+        if (rowf) return f(std::integral_constant<int, a>(), IS(), std::true_type());                              \
+        return f(std::integral_constant<int, a>(), IS(), std::false_type());                                       \
     }
-    OC_CASE(2, 4) OC_CASE(3, 4) OC_CASE(4, 4) OC_CASE(2, 6) OC_CASE(3, 6) OC_CASE(4, 6)
+    OC_CASE(2, 2, 1) OC_CASE(3, 2, 1) OC_CASE(4, 2, 1) OC_CASE(2, 4, 2) OC_CASE(3, 4, 2) OC_CASE(4, 4, 2)
+    OC_CASE(2, 6, 3) OC_CASE(3, 6, 3) OC_CASE(4, 6, 3)
 #undef OC_CASE
     return OC_ERR_INVALID;
 }
@@ -39,7 +45,7 @@ static int dispatch(int A, int NOBJ, int rowf, F&& f) {
 // one warp at a time: every lane runs the logic (body; returns true when its env just finished
 // and wants the auto-reset), then terminal observations, auto-reset and the observation passes run
 // the way the kernels order them
-template <int A, int NOBJ, bool ROWF, typename Body>
+template <int A, int NOBJ, int NF, bool ROWF, typename Body>
 static void for_each_warp(emu_env* h, float* obs, float* term_obs, Body&& body) {
     const OcParams& p = h->p;
     const Tables tb = make_tables(p, h->blob.data());
@@ -55,9 +61,9 @@ static void for_each_warp(emu_env* h, float* obs, float* term_obs, Body&& body) 
             const bool fin = body(tb, env, we[lane], win[lane]);
             if (fin) {
                 if (term_obs)
-                    thread_emit_rows<A, NOBJ, ROWF>(we[lane], p, tb, win[lane], rowof(lane), term_obs + (size_t)env * p.row_bytes);
+                    thread_emit_rows<A, NOBJ, NF, ROWF>(we[lane], p, tb, win[lane], rowof(lane), term_obs + (size_t)env * p.row_bytes);
                 finish_episode<A, NOBJ>(we[lane], p, tb, (uint32_t)env);
-                win[lane] = gather_info<A, NOBJ>(we[lane], p, tb);
+                win[lane] = gather_info<A, NOBJ, NF>(we[lane], p, tb);
             }
             store_env<A, NOBJ>(we[lane], h->state.data(), p.E, env);
         }
@@ -68,7 +74,7 @@ static void for_each_warp(emu_env* h, float* obs, float* term_obs, Body&& body) 
                 for (int lane = 0; lane < 32; ++lane) warp_clear_rows<ROWF>(rows.data(), p.warp_row_bytes, lane);
             for (int lane = 0; lane < nvalid; ++lane)
                 if ((lane >> p.nb_shift) == pass)
-                    fill_rows<A, NOBJ, ROWF>(we[lane], p, tb, win[lane], timestep_of<A, NOBJ>(we[lane], p, tb), rowof(lane));
+                    fill_rows<A, NOBJ, NF, ROWF>(we[lane], p, tb, win[lane], timestep_of<A, NOBJ>(we[lane], p, tb), rowof(lane));
             const int first = pass << p.nb_shift;
             const int nv = std::min(p.nb, nvalid - first);
             if (nv > 0)
@@ -95,9 +101,9 @@ int emu_create(const oc_config* c, emu_env** out) {
     h->p.blob = h->blob.data(); h->p.ts_table = h->ts.data();
     h->state.assign((size_t)h->p.E * 4, uint4{0, 0, 0, 0});
     dispatch(h->p.A, h->p.NOBJ, h->p.rowf, [&](auto a, auto n, auto rf) -> int {
-        constexpr int AA = decltype(a)::value, NN = decltype(n)::value;
+        constexpr int AA = decltype(a)::value, NN = shape_nobj(n), FF = shape_nf(n);
         constexpr bool RF = decltype(rf)::value;
-        for_each_warp<AA, NN, RF>(h, nullptr, nullptr, [&](const Tables& tb, int env, Env<AA, NN>& e, Info&) {
+        for_each_warp<AA, NN, FF, RF>(h, nullptr, nullptr, [&](const Tables& tb, int env, Env<AA, NN>& e, Info&) {
             reset_logic<AA, NN>(e, h->p, tb, (uint32_t)env, true, nullptr, nullptr);
             return false;
         });
@@ -115,12 +121,12 @@ int emu_obs_layout(const emu_env* h, int32_t* off, int32_t* sz) {
 
 int emu_reset(emu_env* h, const uint8_t* mask, const int32_t* placements, float* obs, void*) {
     return dispatch(h->p.A, h->p.NOBJ, h->p.rowf, [&](auto a, auto n, auto rf) -> int {
-        constexpr int AA = decltype(a)::value, NN = decltype(n)::value;
+        constexpr int AA = decltype(a)::value, NN = shape_nobj(n), FF = shape_nf(n);
         constexpr bool RF = decltype(rf)::value;
-        for_each_warp<AA, NN, RF>(h, obs, nullptr, [&](const Tables& tb, int env, Env<AA, NN>& e, Info& in) {
+        for_each_warp<AA, NN, FF, RF>(h, obs, nullptr, [&](const Tables& tb, int env, Env<AA, NN>& e, Info& in) {
             load_env<AA, NN>(e, h->state.data(), h->p.E, env);
             reset_logic<AA, NN>(e, h->p, tb, (uint32_t)env, false, mask, placements);
-            if (obs) in = gather_info<AA, NN>(e, h->p, tb);
+            if (obs) in = gather_info<AA, NN, FF>(e, h->p, tb);
             return false;
         });
         return OC_OK;
@@ -130,14 +136,14 @@ int emu_reset(emu_env* h, const uint8_t* mask, const int32_t* placements, float*
 int emu_step(emu_env* h, const int32_t* actions, float* obs, float* rew32, double* rew64, uint8_t* done,
              float* term_obs, uint32_t flags, void*) {
     return dispatch(h->p.A, h->p.NOBJ, h->p.rowf, [&](auto a, auto n, auto rf) -> int {
-        constexpr int AA = decltype(a)::value, NN = decltype(n)::value;
+        constexpr int AA = decltype(a)::value, NN = shape_nobj(n), FF = shape_nf(n);
         constexpr bool RF = decltype(rf)::value;
-        for_each_warp<AA, NN, RF>(h, obs, term_obs, [&](const Tables& tb, int env, Env<AA, NN>& e, Info& in) {
+        for_each_warp<AA, NN, FF, RF>(h, obs, term_obs, [&](const Tables& tb, int env, Env<AA, NN>& e, Info& in) {
             load_env<AA, NN>(e, h->state.data(), h->p.E, env);
             int nav[AA], comm[AA];
             for (int k = 0; k < AA; ++k) { nav[k] = actions[((size_t)env * AA + k) * 2] & 3; comm[k] = actions[((size_t)env * AA + k) * 2 + 1]; }
             bool fin;
-            in = step_logic<AA, NN>(e, h->p, tb, nav, comm[0], comm[1], (uint32_t)env, rew32, rew64, done, fin);
+            in = step_logic<AA, NN, FF>(e, h->p, tb, nav, comm[0], comm[1], (uint32_t)env, rew32, rew64, done, fin);
             return fin && (flags & OC_FLAG_AUTO_RESET);
         });
         return OC_OK;
@@ -147,13 +153,13 @@ int emu_step(emu_env* h, const int32_t* actions, float* obs, float* rew32, doubl
 int emu_rollout(emu_env* h, int32_t n_steps, float* obs, float* rew32, uint8_t* done, int32_t* actions_out, void*) {
     const size_t step_floats = (size_t)h->p.E * h->p.row_bytes;
     int rc = dispatch(h->p.A, h->p.NOBJ, h->p.rowf, [&](auto a, auto n, auto rf) -> int {
-        constexpr int AA = decltype(a)::value, NN = decltype(n)::value;
+        constexpr int AA = decltype(a)::value, NN = shape_nobj(n), FF = shape_nf(n);
         constexpr bool RF = decltype(rf)::value;
         for (int s = 0; s < n_steps; ++s)
-            for_each_warp<AA, NN, RF>(h, obs ? obs + (size_t)s * step_floats : nullptr, nullptr,
+            for_each_warp<AA, NN, FF, RF>(h, obs ? obs + (size_t)s * step_floats : nullptr, nullptr,
                                   [&](const Tables& tb, int env, Env<AA, NN>& e, Info& in) {
                 load_env<AA, NN>(e, h->state.data(), h->p.E, env);
-                in = rollout_logic<AA, NN, RF>(e, h->p, tb, (uint32_t)env, (uint32_t)s, h->rollout_step, rew32, done, actions_out);
+                in = rollout_logic<AA, NN, FF, RF>(e, h->p, tb, (uint32_t)env, (uint32_t)s, h->rollout_step, rew32, done, actions_out);
                 return false;
             });
         return OC_OK;
