@@ -568,6 +568,14 @@ __device__ __forceinline__ void rows_wait_read(const OcParams& p) {
 #endif
     __syncwarp();
 }
+// two row buffers used alternately: a buffer may be refilled once every bulk copy but the most
+// recent one (which reads the OTHER buffer) has been read
+__device__ __forceinline__ void rows_wait_read_but_one(const OcParams& p) {
+#ifndef OCK_HOST_EMU
+    if (p.use_tma) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+#endif
+    __syncwarp();
+}
 // before the CTA exits: the copy engine must have read the rows out of its shared memory; the
 // global writes themselves complete, like any store, by the end of the grid
 __device__ __forceinline__ void rows_wait_done(const OcParams& p) {
@@ -667,30 +675,36 @@ __device__ __forceinline__ void store_timesteps(const OcParams& p, float* __rest
     for (int k = 0; k < A; ++k) env_row[k * p.F + p.off_ts] = ts;
 }
 
-// ---- observation emission of one warp's 32 envs.  The warp's row buffer holds p.nb env rows
-// (32, or 16 / 8 / 4 for wide float rows, so that enough warps stay resident); the envs go out in
-// 32 / nb passes, lanes [pass * nb, pass * nb + nb) filling the buffer in their pass.  Rows must be
-// clear (and, with bulk stores, read out) on entry; they are dirty on exit.
+// ---- observation emission of one warp's 32 envs.  The warp owns nbuf buffers of p.nb env rows
+// (1 x 32, or 2 x 16 / 1 x 16 / 2 x 8 ... for float rows); the envs go out in 32 / nb passes, lanes
+// [pass * nb, pass * nb + nb) filling buffer (pass mod nbuf) in their pass, one bulk copy per pass.
+// With two buffers a pass only waits for the copy issued TWO passes ago, so filling and dynamics
+// overlap the copy engine's drain.  Each pass waits for its buffer to be read out, clears it (unless
+// the caller says the rows are clean), fills it, and hands it to the copy engine (or stores it with
+// the warp).
 template <int A, int NOBJ, int NF, int MODE /* 0 byte rows, 1 float rows, 2 float rows in several passes */>
 __device__ __forceinline__ void emit_obs(const Env<A, NOBJ>& e, const Info& in, bool valid, const OcParams& p,
                                          const Tables& tb, uint8_t* wrows, int lane,
-                                         float* __restrict__ out_env0 /* warp's first env row */, int nvalid) {
+                                         float* __restrict__ out_env0 /* warp's first env row */, int nvalid,
+                                         bool clean_on_entry = false /* rows already clear and not in flight */) {
     constexpr bool ROWF = MODE != 0;
     constexpr bool MULTI = MODE == 2;               // compile-time: e / in stay live across passes only here
-    uint8_t* myrow = wrows + (MULTI ? (lane & (p.nb - 1)) : lane) * p.row_stride;
     const float ts = valid ? timestep_of<A, NOBJ>(e, p, tb) : 0.0f;
     const int passes = MULTI ? p.obs_passes : 1;
     for (int pass = 0; pass < passes; ++pass) {
-        if (pass > 0) {
-            rows_wait_read(p);
-            warp_clear_rows<ROWF>(wrows, p.warp_row_bytes, lane);
+        uint8_t* buf = wrows;
+        if (MULTI && p.nbuf == 2) buf += (pass & 1) * p.buf_bytes;
+        if (!(clean_on_entry && pass < p.nbuf)) {
+            if (MULTI && p.nbuf == 2) rows_wait_read_but_one(p); else rows_wait_read(p);
+            warp_clear_rows<ROWF>(buf, MULTI ? p.buf_bytes : p.warp_row_bytes, lane);
             __syncwarp();
         }
+        uint8_t* myrow = buf + (MULTI ? (lane & (p.nb - 1)) : lane) * p.row_stride;
         if (valid && (!MULTI || (lane >> p.nb_shift) == pass)) fill_rows<A, NOBJ, NF, ROWF>(e, p, tb, in, ts, myrow);
         __syncwarp();
         const int first = MULTI ? (pass << p.nb_shift) : 0;
         const int nv = min(MULTI ? p.nb : 32, nvalid - first);
-        if (nv > 0) warp_expand_rows<ROWF>(p, wrows, out_env0 + (size_t)first * p.row_bytes, nv, lane);
+        if (nv > 0) warp_expand_rows<ROWF>(p, buf, out_env0 + (size_t)first * p.row_bytes, nv, lane);
     }
     if (!ROWF) {                                    // byte rows are never split into passes
         __syncwarp();                               // orders the float4 stores before the timestep patch
@@ -716,14 +730,19 @@ __device__ __forceinline__ void thread_emit_rows(const Env<A, NOBJ>& e, const Oc
 }
 
 // infos["terminal_observation"] of the envs of this warp that just finished (SB3 VecEnv contract);
-// lanes that share a row slot (nb < 32) take turns.  Rows must be clear; they stay clear.
+// rare path: waits for every pending copy, clears the warp's rows and lets the finished lanes emit
+// their rows one by one (lanes that share a row slot, nb < 32, take turns).
 template <int A, int NOBJ, int NF, int MODE>
 __device__ __forceinline__ void warp_terminal_obs(const Env<A, NOBJ>& e, const Info& in, bool fin, const OcParams& p,
                                                   const Tables& tb, uint8_t* wrows, int lane,
                                                   float* __restrict__ term_row) {
     constexpr bool ROWF = MODE != 0;
+    rows_wait_read(p);
+    warp_clear_rows<ROWF>(wrows, p.warp_row_bytes, lane);
+    __syncwarp();
     if (MODE != 2) {
         if (fin) thread_emit_rows<A, NOBJ, NF, ROWF>(e, p, tb, in, wrows + lane * p.row_stride, term_row);
+        __syncwarp();
         return;
     }
     uint8_t* myrow = wrows + (lane & (p.nb - 1)) * p.row_stride;

@@ -134,9 +134,17 @@ static inline int compile_config(const oc_config* c, HostImage& h, std::string& 
     // measured slower in the fused rollout but faster in the single-step kernel, which sets 2 itself.
     p.use_tma = (p.rowf && p.row_stride == p.row_bytes * 4) ? 1 : 0;
     if (const char* t = getenv("OC_TMA")) p.use_tma = (p.use_tma && atoi(t) != 0) ? 1 : 0;
+    // A/B knob OC_ROW_BUFS=2: two half-size buffers used alternately, so that a pass only waits for the copy
+    // issued two passes ago.  Measured slower everywhere (cfg2 5.1 vs 4.2 us, cfg3 35.4 vs 25.7, cfg5 35.0 vs
+    // 33.9): every extra pass re-executes the per-lane fill with half of the lanes idle, which costs more
+    // than the overlap gains.  Default: one buffer.
+    p.nbuf = 1;
+    if (const char* o = getenv("OC_ROW_BUFS"))
+        if (atoi(o) == 2 && p.use_tma == 1 && p.nb >= 8) { p.nb /= 2; p.nbuf = 2; }
     p.nb_shift = p.nb == 32 ? 5 : p.nb == 16 ? 4 : p.nb == 8 ? 3 : 2;
     p.obs_passes = 32 / p.nb;
-    p.warp_row_bytes = p.nb * p.row_stride;
+    p.buf_bytes = p.nb * p.row_stride;
+    p.warp_row_bytes = p.nbuf * p.buf_bytes;
     p.r4_magic = (p.row_bytes >= 4) ? (uint32_t)((1ull << 32) / (uint64_t)(p.row_bytes >> 2)) + 1u : 0u;
     p.rf_magic = (uint32_t)((1ull << 32) / (uint64_t)p.row_bytes) + 1u;
     for (int k = 0; k < OC_MAX_AGENTS; ++k) {

@@ -28,7 +28,6 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
                const int32_t* __restrict__ actions, float* __restrict__ obs,
                float* __restrict__ rew32, double* __restrict__ rew64, uint8_t* __restrict__ done_out,
                float* __restrict__ term_obs, uint32_t flags) {
-    constexpr bool ROWF = MODE != 0;
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -39,14 +38,14 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
     asm volatile("griddepcontrol.launch_dependents;");
     load_tables(p, smem);
     uint8_t* wrows = smem + p.blob_bytes + (size_t)warp * p.warp_row_bytes;
-    warp_clear_rows<ROWF>(wrows, p.warp_row_bytes, lane);
+    warp_clear_rows<MODE != 0>(wrows, p.warp_row_bytes, lane);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
     const Tables tb = make_tables(p, smem);
 
     // the grid is sized to ONE resident wave (148 SMs x CTAs that fit); with more envs than that
     // each CTA walks several chunks so the tables are loaded once per CTA, not once per chunk
-    bool first = true;
+    bool first = true;                              // rows still clear from the prologue
     for (int base = blockIdx.x * blockDim.x; base < p.E; base += gridDim.x * blockDim.x) {
         const int env = base + threadIdx.x;
         const bool valid = env < p.E;
@@ -61,12 +60,6 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
             for (int k = 0; k < A; ++k) { const int2 v = __ldg(a2 + k); nav[k] = v.x & 3; comm[k] = v.y; }
             in = step_logic<A, NOBJ, NF>(e, p, tb, nav, comm[0], comm[1], (uint32_t)env, rew32, rew64, done_out, done);
         }
-        if (!first) {                                   // rows of the previous chunk: read out, then clear
-            rows_wait_read(p);
-            warp_clear_rows<ROWF>(wrows, p.warp_row_bytes, lane);
-            __syncwarp();
-        }
-        first = false;
         const bool fin = valid && done && (flags & OC_FLAG_AUTO_RESET);
         if (term_obs != nullptr && __any_sync(0xFFFFFFFFu, fin))      // rare: some env of this warp finished
             warp_terminal_obs<A, NOBJ, NF, MODE>(e, in, fin, p, tb, wrows, lane, term_obs + (size_t)env * p.row_bytes);
@@ -76,7 +69,8 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
         }
         if (valid) store_env<A, NOBJ>(e, state, p.E, env);
         const int env0 = base + warp * 32;
-        emit_obs<A, NOBJ, NF, MODE>(e, in, valid, p, tb, wrows, lane, obs + (size_t)env0 * p.row_bytes, min(32, p.E - env0));
+        emit_obs<A, NOBJ, NF, MODE>(e, in, valid, p, tb, wrows, lane, obs + (size_t)env0 * p.row_bytes, min(32, p.E - env0), first);
+        first = false;
     }
     rows_wait_done(p);
 }
@@ -108,9 +102,6 @@ oc_rollout_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
         Info in;
         if (valid) in = rollout_logic<A, NOBJ, NF, ROWF>(e, p, tb, (uint32_t)env, (uint32_t)s, step0, rew32, done_out, actions_out, actions_in);
         if (obs != nullptr) {
-            if (s > 0) rows_wait_read(p);
-            warp_clear_rows<ROWF>(wrows, p.warp_row_bytes, lane);
-            __syncwarp();
             emit_obs<A, NOBJ, NF, MODE>(e, in, valid, p, tb, wrows, lane,
                                     obs + (size_t)s * step_floats + (size_t)env0 * p.row_bytes, nvalid);
         }
@@ -124,7 +115,6 @@ template <int A, int NOBJ, int NF, int MODE>
 __global__ void __launch_bounds__(256)
 oc_reset_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, const uint8_t* __restrict__ mask,
                 const int32_t* __restrict__ placements, float* __restrict__ obs, int initial) {
-    constexpr bool ROWF = MODE != 0;
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
@@ -133,7 +123,6 @@ oc_reset_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, c
     if (valid && !initial) load_env<A, NOBJ>(e, state, p.E, env);
     load_tables(p, smem);
     uint8_t* wrows = smem + p.blob_bytes + (size_t)warp * p.warp_row_bytes;
-    warp_clear_rows<ROWF>(wrows, p.warp_row_bytes, lane);
     __syncthreads();
     const Tables tb = make_tables(p, smem);
     Info in;

@@ -58,7 +58,8 @@ struct OcParams {
     uint32_t r4_magic, rf_magic;            // floor(2^32 / d) + 1 for d = row_bytes / 4 and row_bytes
     int32_t nb, nb_shift;                   // env rows in one warp's shared-memory buffer: 32, or 16 / 8 / 4 (wide float rows)
     int32_t obs_passes;                     // 32 / nb: a warp emits its 32 envs in this many passes
-    int32_t warp_row_bytes;                 // nb * row_stride
+    int32_t nbuf, buf_bytes;                // row buffers per warp (1 or 2, used alternately) of nb * row_stride bytes each
+    int32_t warp_row_bytes;                 // nbuf * buf_bytes
     // observation layout (float offsets inside one observer row)
     int32_t off_a1comm, off_a1loc, off_a2comm, off_a2loc, off_hold, off_completed,
             off_hidden, off_encx, off_ency, off_state, off_ts;

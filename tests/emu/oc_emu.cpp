@@ -52,7 +52,6 @@ static void for_each_warp(emu_env* h, float* obs, float* term_obs, Body&& body) 
     std::vector<uint8_t> rows((size_t)p.warp_row_bytes);
     Env<A, NOBJ> we[32];
     Info win[32];
-    auto rowof = [&](int lane) { return rows.data() + (size_t)(lane & (p.nb - 1)) * p.row_stride; };
     for (int env0 = 0; env0 < p.E; env0 += 32) {
         const int nvalid = std::min(32, p.E - env0);
         for (int lane = 0; lane < 32; ++lane) warp_clear_rows<ROWF>(rows.data(), p.warp_row_bytes, lane);
@@ -60,8 +59,10 @@ static void for_each_warp(emu_env* h, float* obs, float* term_obs, Body&& body) 
             const int env = env0 + lane;
             const bool fin = body(tb, env, we[lane], win[lane]);
             if (fin) {
-                if (term_obs)
-                    thread_emit_rows<A, NOBJ, NF, ROWF>(we[lane], p, tb, win[lane], rowof(lane), term_obs + (size_t)env * p.row_bytes);
+                if (term_obs)        // warp_terminal_obs: rows clear, finished lanes emit one by one
+                    thread_emit_rows<A, NOBJ, NF, ROWF>(we[lane], p, tb, win[lane],
+                                                        rows.data() + (size_t)(lane & (p.nb - 1)) * p.row_stride,
+                                                        term_obs + (size_t)env * p.row_bytes);
                 finish_episode<A, NOBJ>(we[lane], p, tb, (uint32_t)env);
                 win[lane] = gather_info<A, NOBJ, NF>(we[lane], p, tb);
             }
@@ -69,17 +70,18 @@ static void for_each_warp(emu_env* h, float* obs, float* term_obs, Body&& body) 
         }
         if (!obs) continue;
         float* out0 = obs + (size_t)env0 * p.row_bytes;
-        for (int pass = 0; pass < p.obs_passes; ++pass) {
-            if (pass > 0)
-                for (int lane = 0; lane < 32; ++lane) warp_clear_rows<ROWF>(rows.data(), p.warp_row_bytes, lane);
+        for (int pass = 0; pass < p.obs_passes; ++pass) {          // emit_obs, lane by lane
+            uint8_t* buf = rows.data() + (size_t)(pass & (p.nbuf - 1)) * p.buf_bytes;
+            for (int lane = 0; lane < 32; ++lane) warp_clear_rows<ROWF>(buf, p.buf_bytes, lane);
             for (int lane = 0; lane < nvalid; ++lane)
                 if ((lane >> p.nb_shift) == pass)
-                    fill_rows<A, NOBJ, NF, ROWF>(we[lane], p, tb, win[lane], timestep_of<A, NOBJ>(we[lane], p, tb), rowof(lane));
+                    fill_rows<A, NOBJ, NF, ROWF>(we[lane], p, tb, win[lane], timestep_of<A, NOBJ>(we[lane], p, tb),
+                                                 buf + (size_t)(lane & (p.nb - 1)) * p.row_stride);
             const int first = pass << p.nb_shift;
             const int nv = std::min(p.nb, nvalid - first);
             if (nv > 0)
                 for (int lane = 0; lane < 32; ++lane)
-                    warp_expand_rows<ROWF>(p, rows.data(), out0 + (size_t)first * p.row_bytes, nv, lane);
+                    warp_expand_rows<ROWF>(p, buf, out0 + (size_t)first * p.row_bytes, nv, lane);
         }
         if (!ROWF)
             for (int lane = 0; lane < nvalid; ++lane)

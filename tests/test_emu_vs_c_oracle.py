@@ -33,6 +33,8 @@ FORMATS = {
     "f8_nopad": dict(OC_ROW_FORMAT="f", OC_ROW_ENVS="8", OC_ROW_PAD="0"),
     "f4": dict(OC_ROW_FORMAT="f", OC_ROW_ENVS="4"),
     "bytes": dict(OC_ROW_FORMAT="b"),
+    "f16x2": dict(OC_ROW_BUFS="2"),
+    "f8x2": dict(OC_ROW_FORMAT="f", OC_ROW_ENVS="16", OC_ROW_PAD="0", OC_ROW_BUFS="2"),
 }
 
 
