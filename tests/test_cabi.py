@@ -54,6 +54,20 @@ def test_no_cpu_fallback(lib):
         OvercookedVecEnv(ns, num_envs=4, device="cpu")
 
 
+def test_host_env_has_no_cpu_fallback_either(lib):
+    """The numpy-only host path needs the CUDA library and a device; it refuses the test emulation."""
+    import torch
+    import argparse
+    from gym_comm_b200.host_env import OvercookedHostVecEnv
+    from tests.parity_util import emu_library
+    ns = argparse.Namespace(level="open-divider_tomato", num_agents=2, max_num_timesteps=100)
+    with pytest.raises(RuntimeError):
+        OvercookedHostVecEnv(ns, num_envs=4, lib=emu_library())
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            OvercookedHostVecEnv(ns, num_envs=4)
+
+
 def test_emulation_backend_is_refused_outside_tests(monkeypatch):
     import argparse
     from gym_comm_b200.vec_env import OvercookedVecEnv
