@@ -20,6 +20,7 @@ struct int2 { int x, y; };
 struct float2 { float x, y; };
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
