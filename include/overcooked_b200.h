@@ -154,7 +154,8 @@ int oc_step(oc_env* env, const int32_t* actions, float* obs, float* rew_f32, dou
  * ONE launch with state kept on chip; actions nav~U{0..3}, comm~U{0..C-1} from Philox4x32-10
  * keyed by (seed; env index, global step); auto-reset always on.  Step s writes
  *  obs[s]  f32[n_steps, E, A, F],  rew_f32[s] f32[n_steps, E, A],  done[s] u8[n_steps, E]
- * (any of them may be NULL = not written);  actions_out int32[n_steps, E, A, 2] or NULL. */
+ * (any of them may be NULL = not written);  actions_out int32[n_steps, E, A, 2] or NULL.
+ * The global step counter of a handle is 32-bit: its action stream repeats after 2^32 fused steps. */
 int oc_rollout(oc_env* env, int32_t n_steps, float* obs, float* rew_f32, uint8_t* done,
                int32_t* actions_out, void* stream);
 
