@@ -27,6 +27,11 @@ CONFIGS = {
     "wide4_c100": dict(level="open-divider_salad", num_agents=4, max_num_timesteps=11, communication_on=True,
                        num_communication=100, ego_led=True, fow_radius=1, ego_config=D, partner_config=D),
 }
+# a kitchen with one Tomato and one Plate: the (2 object slots, 1 food channel) kernel shape
+TINY_TOMATO = "--*--\nt   p\n/   -\n-----\n\nSimpleTomato\n\n1 1\n3 1\n2 2\n1 2"
+CONFIGS["tiny_tomato_shape21"] = dict(level="tiny", level_text=TINY_TOMATO, num_agents=2, max_num_timesteps=21,
+                                      communication_on=True, num_communication=4, ego_led=False, fow_radius=1,
+                                      ego_config=D, partner_config=D)
 FORMATS = {
     "default": {},
     "f16": dict(OC_ROW_FORMAT="f", OC_ROW_ENVS="16"),
@@ -43,12 +48,12 @@ FORMATS = {
 def test_step_autoreset_terminal_obs(name, fmt, monkeypatch):
     for k, v in FORMATS[fmt].items():
         monkeypatch.setenv(k, v)
-    cfg = CONFIGS[name]
-    text = levels_data.LEVELS[cfg["level"]]
+    cfg = dict(CONFIGS[name])
+    text = cfg.pop("level_text", None) or levels_data.LEVELS[cfg["level"]]
     subtasks = levels_data.SUBTASKS[tuple(text.split("\n\n")[1].split("\n"))]
     E, n, seed = 75, cfg["num_agents"], 99
     env = OvercookedVecEnv(argparse.Namespace(**cfg), num_envs=E, device="cpu", lib=emu_library(), seed=seed,
-                           auto_reset=True)
+                           auto_reset=True, level_text=text)
     ora = COracle(text, subtasks, E, seed=seed, **{k: v for k, v in cfg.items() if k != "level"})
     rng = np.random.default_rng(5)
     term = torch.full((E, n, env.obs_width), -7.0)
