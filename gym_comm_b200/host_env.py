@@ -30,7 +30,9 @@ class OvercookedHostVecEnv:
     ``reset() -> obs [E, A, F] f32``;
     ``step(actions int32 [E, A, 2]) -> (obs [E, A, F] f32, rewards [E, A] f32, dones [E] bool, infos)``
     with SB3's auto-reset contract: for an env that finished, ``obs`` is the first observation of its
-    next episode and ``infos[e]["terminal_observation"]`` the last one of the finished episode.
+    next episode and ``infos[e]["terminal_observation"]`` the last one of the finished episode (a view of
+    ``env.terminal_obs[e]``; with very large batches read ``env.terminal_obs`` and ``done`` directly instead
+    of walking the list).
     The returned arrays (and the `infos` list) are the env's own pinned buffers, overwritten by the next
     call (copy them to keep them, as SB3's rollout buffer does) and invalid after `close()`.
     """
@@ -122,8 +124,9 @@ class OvercookedHostVecEnv:
         for e in self._touched:
             self._infos[e].clear()
         self._touched = np.flatnonzero(d) if self.terminal_obs is not None else ()
-        for e in self._touched:
-            self._infos[e]["terminal_observation"] = self.terminal_obs[e].copy()
+        term = self.terminal_obs
+        for e in self._touched:                      # views into the pinned buffer (valid until env e finishes again)
+            self._infos[e]["terminal_observation"] = term[e]
         return self.obs, self.rewards, d, self._infos
 
     def obs_dict(self, obs: Optional[np.ndarray] = None) -> dict:
