@@ -129,6 +129,24 @@ class OvercookedHostVecEnv:
             self._infos[e]["terminal_observation"] = term[e]
         return self.obs, self.rewards, d, self._infos
 
+    # SB3 VecEnv duck type (the rest of the convention; every env shares one configuration)
+    def step_async(self, actions) -> None:
+        self._pending = actions
+
+    def step_wait(self):
+        return self.step(self._pending)
+
+    def seed(self, seed=None):
+        return [None] * self.num_envs          # placements are seeded at construction (oc_config.seed)
+
+    def get_attr(self, attr_name, indices=None):
+        n = self.num_envs if indices is None else len([indices] if isinstance(indices, int) else list(indices))
+        return [getattr(self, attr_name)] * n
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        n = self.num_envs if indices is None else len([indices] if isinstance(indices, int) else list(indices))
+        return [False] * n
+
     def obs_dict(self, obs: Optional[np.ndarray] = None) -> dict:
         """Per-key zero-copy views of flat rows (the reference's Dict observation)."""
         o = self.obs if obs is None else obs
