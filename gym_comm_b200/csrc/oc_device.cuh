@@ -432,8 +432,10 @@ __device__ __forceinline__ Info env_step(Env<A, NOBJ>& e, const OcParams& p, con
 // Observation rows.  get_observation2 (gym_comm/envs/overcooked_env.py:105-159) for every
 // observer of one env, written into this env's shared-memory row by its owning thread, then
 // streamed to global memory by the whole warp.  Two row formats:
-//   ROWF = true : float32 rows (when they fit in shared memory) -> the expansion is a 16-byte copy
+//   ROWF = true : float32 rows -> leave shared memory as they are (one bulk copy, or 16-byte stores);
+//                 rows too wide for 32 of them per warp go out in passes of 16 / 8 / 4 envs (emit_obs)
 //   ROWF = false: one biased byte per feature (value + 128) -> PRMT + FADD per float on the way out
+//                 (rows whose length is not a multiple of 4 floats, or wider than 1920 floats)
 // =============================================================================================
 #define OCK_BIAS 128u
 
