@@ -1,0 +1,1 @@
+"""TEST INFRASTRUCTURE ONLY: CPU restatements of the reference algorithm (the parity oracle); never imported by the product."""

@@ -1,0 +1,1 @@
+"""Parity and host-logic tests of gym_comm_b200 (CPU: -m \"not gpu\"; B200: -m gpu)."""
