@@ -43,7 +43,7 @@ class BatchedOnPolicyAgent:
             self.last_train_stats = self.model.train()
             self.iteration += 1
             buf.reset()
-        actions, values, log_probs = self.model.policy.act(obs)
+        actions, values, log_probs = self.model.act(obs, self._last_episode_starts)
         if record:
             buf.add(obs, actions, self._last_episode_starts, values, log_probs)
         self.num_timesteps += obs.shape[0]
@@ -139,13 +139,12 @@ def collect_and_train(penv: PantheonVecEnv, ego: PPO, obs: torch.Tensor, episode
     buf = ego.buffer
     buf.reset()
     for _ in range(buf.n_steps):
-        actions, values, log_probs = ego.policy.act(obs)
+        actions, values, log_probs = ego.act(obs, episode_starts)
         buf.add(obs, actions, episode_starts, values, log_probs)
         obs, rew, done = penv.step(actions.to(torch.int32))
         buf.add_reward(rew)
         episode_starts = done.to(torch.float32)
-    with torch.no_grad():
-        last_values = ego.policy.value(obs)
+    last_values = ego.value(obs, episode_starts)
     buf.compute_returns_and_advantage(last_values, episode_starts)
     stats = ego.train()
     return obs, episode_starts, stats

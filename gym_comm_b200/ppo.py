@@ -160,6 +160,14 @@ class PPO:
         self.buffer = RolloutBuffer(self.cfg.n_steps, num_envs, obs_dim, self.device, self.cfg.gamma, self.cfg.gae_lambda)
         self.n_updates = 0
 
+    # uniform entry points of the rollout code (the recurrent learner keeps LSTM state behind them)
+    def act(self, obs, episode_starts=None, deterministic: bool = False):
+        return self.policy.act(obs, deterministic)
+
+    def value(self, obs, episode_starts=None):
+        with torch.no_grad():
+            return self.policy.value(obs)
+
     def train(self):
         """One PPO update over the (full) rollout buffer.  Returns a dict of float stats."""
         c, b = self.cfg, self.buffer
@@ -188,6 +196,124 @@ class PPO:
                     stats["pg"] += float(pg); stats["vf"] += float(vf); stats["ent"] += float(ent.mean())
                     stats["clipfrac"] += float(((ratio - 1).abs() > c.clip_range).float().mean())
                     stats["kl"] += float((old_logp[idx] - logp).mean())
+                    stats["n"] += 1
+        self.n_updates += 1
+        k = max(stats.pop("n"), 1)
+        return {a: v / k for a, v in stats.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+# Recurrent learner: what the reference actually trains (`RecurrentPPO("MultiInputLstmPolicy", ...)`,
+# trainer.py:92-121; sb3_contrib/ppo_recurrent): separate LSTMs for actor and critic in front of the
+# 2 x 64 towers, hidden state reset at episode starts, back-propagation through the whole rollout.
+# ------------------------------------------------------------------------------------------------
+class RecurrentActorCritic(nn.Module):
+    """obs [.., F] + LSTM state -> logits over nav (4) and message (C), value.  State = (h_pi, c_pi,
+    h_vf, c_vf), each [E, H] (one layer, like sb3_contrib's default n_lstm_layers=1)."""
+
+    def __init__(self, obs_dim: int, num_nav: int, num_comm: int, lstm_hidden: int = 256, hidden=(64, 64)):
+        super().__init__()
+        self.num_nav, self.num_comm, self.lstm_hidden = num_nav, num_comm, lstm_hidden
+        self.lstm_pi = nn.LSTMCell(obs_dim, lstm_hidden)
+        self.lstm_vf = nn.LSTMCell(obs_dim, lstm_hidden)
+        self.pi = _mlp(lstm_hidden, hidden)
+        self.vf = _mlp(lstm_hidden, hidden)
+        self.action_head = nn.Linear(hidden[-1], num_nav + num_comm)
+        self.value_head = nn.Linear(hidden[-1], 1)
+        nn.init.orthogonal_(self.action_head.weight, gain=0.01)
+        nn.init.zeros_(self.action_head.bias)
+        nn.init.orthogonal_(self.value_head.weight, gain=1.0)
+        nn.init.zeros_(self.value_head.bias)
+
+    def initial_state(self, num_envs: int, device):
+        z = torch.zeros((num_envs, self.lstm_hidden), device=device)
+        return (z, z.clone(), z.clone(), z.clone())
+
+    def step(self, obs, state, episode_starts):
+        """One time step for [E] envs: the state of envs that start an episode is zeroed first
+        (sb3_contrib `_process_sequence`).  -> (dist_nav, dist_comm, value, new_state)"""
+        keep = (1.0 - episode_starts).unsqueeze(-1)
+        hp, cp = self.lstm_pi(obs, (state[0] * keep, state[1] * keep))
+        hv, cv = self.lstm_vf(obs, (state[2] * keep, state[3] * keep))
+        logits = self.action_head(self.pi(hp))
+        value = self.value_head(self.vf(hv)).squeeze(-1)
+        return (torch.distributions.Categorical(logits=logits[..., :self.num_nav]),
+                torch.distributions.Categorical(logits=logits[..., self.num_nav:]), value, (hp, cp, hv, cv))
+
+
+class RecurrentPPO:
+    """PPO over `RecurrentActorCritic`; same rollout-side interface as `PPO` (`act`, `value`, `buffer`,
+    `train`).  The LSTM state lives here, one row per env, and is snapshotted when a rollout starts so
+    that `train` can replay the rollout from the same state."""
+
+    def __init__(self, obs_dim: int, num_nav: int, num_comm: int, num_envs: int, device, cfg: PPOConfig = None,
+                 seed: int = 0, lstm_hidden: int = 256):
+        self.cfg = cfg or PPOConfig()
+        self.device = torch.device(device)
+        gen = torch.Generator().manual_seed(seed)
+        with torch.random.fork_rng(devices=[]):
+            torch.manual_seed(int(torch.randint(0, 2 ** 31 - 1, (1,), generator=gen)))
+            self.policy = RecurrentActorCritic(obs_dim, num_nav, num_comm, lstm_hidden).to(self.device)
+        self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.learning_rate, eps=1e-5)
+        self.buffer = RolloutBuffer(self.cfg.n_steps, num_envs, obs_dim, self.device, self.cfg.gamma, self.cfg.gae_lambda)
+        self.state = self.policy.initial_state(num_envs, self.device)
+        self.rollout_state = self.state
+        self.n_updates = 0
+
+    @torch.no_grad()
+    def act(self, obs, episode_starts, deterministic: bool = False):
+        if self.buffer.pos == 0:                       # first step of a rollout: remember where it started
+            self.rollout_state = tuple(s.clone() for s in self.state)
+        dn, dc, value, self.state = self.policy.step(obs, self.state, episode_starts)
+        nav = dn.probs.argmax(-1) if deterministic else dn.sample()
+        com = dc.probs.argmax(-1) if deterministic else dc.sample()
+        return torch.stack([nav, com], -1), value, dn.log_prob(nav) + dc.log_prob(com)
+
+    @torch.no_grad()
+    def value(self, obs, episode_starts):
+        """Value of `obs` as the NEXT step would see it; the state is not advanced."""
+        return self.policy.step(obs, self.state, episode_starts)[2]
+
+    def evaluate_rollout(self, env_idx):
+        """Replay the stored rollout of the envs `env_idx` from its initial state.
+        -> values, log_probs, entropy, each [n_steps, len(env_idx)]"""
+        b = self.buffer
+        state = tuple(s[env_idx] for s in self.rollout_state)
+        vals, logps, ents = [], [], []
+        for t in range(b.n_steps):
+            dn, dc, v, state = self.policy.step(b.obs[t, env_idx], state, b.episode_starts[t, env_idx])
+            a = b.actions[t, env_idx]
+            vals.append(v)
+            logps.append(dn.log_prob(a[..., 0]) + dc.log_prob(a[..., 1]))
+            ents.append(dn.entropy() + dc.entropy())
+        return torch.stack(vals), torch.stack(logps), torch.stack(ents)
+
+    def train(self):
+        """One PPO update; minibatches are sets of ENVS (whole sequences), back-propagated through time."""
+        c, b = self.cfg, self.buffer
+        E, T = b.num_envs, b.n_steps
+        envs_per_batch = max(1, min(E, c.batch_size // T))
+        stats = dict(pg=0.0, vf=0.0, ent=0.0, clipfrac=0.0, kl=0.0, n=0)
+        for _ in range(c.n_epochs):
+            perm = torch.randperm(E, device=self.device)
+            for i in range(0, E - envs_per_batch + 1, envs_per_batch):
+                idx = perm[i:i + envs_per_batch]
+                values, logp, ent = self.evaluate_rollout(idx)
+                adv = b.advantages[:, idx]
+                adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+                old_logp = b.log_probs[:, idx]
+                ratio = torch.exp(logp - old_logp)
+                pg = -torch.min(adv * ratio, adv * torch.clamp(ratio, 1 - c.clip_range, 1 + c.clip_range)).mean()
+                vf = torch.nn.functional.mse_loss(values, b.returns[:, idx])
+                loss = pg + c.vf_coef * vf - c.ent_coef * ent.mean()
+                self.optimizer.zero_grad(set_to_none=True)
+                loss.backward()
+                nn.utils.clip_grad_norm_(self.policy.parameters(), c.max_grad_norm)
+                self.optimizer.step()
+                with torch.no_grad():
+                    stats["pg"] += float(pg); stats["vf"] += float(vf); stats["ent"] += float(ent.mean())
+                    stats["clipfrac"] += float(((ratio - 1).abs() > c.clip_range).float().mean())
+                    stats["kl"] += float((old_logp - logp).mean())
                     stats["n"] += 1
         self.n_updates += 1
         k = max(stats.pop("n"), 1)

@@ -89,3 +89,40 @@ def test_pantheon_and_sb3_plumbing():
     with pytest.raises(AttributeError):
         venv.set_attr("x", 1)
     venv.close()
+
+
+@pytest.mark.parametrize("recurrent", [False, True])
+def test_ego_and_partner_learners_run_off_the_env(recurrent):
+    """collect_and_train with the feed-forward and the recurrent learner (ego + partner inside the env
+    step) on the emulated env: two iterations, finite losses, the partner trained on its own schedule."""
+    from gym_comm_b200.pantheon import BatchedOnPolicyAgent, collect_and_train
+    from gym_comm_b200.ppo import PPO, PPOConfig, RecurrentPPO
+    E = 8
+    env = make(E=E, T=5)
+    cfg = PPOConfig(n_steps=6, batch_size=24, n_epochs=1)
+    mk = (lambda seed: RecurrentPPO(env.obs_width, 4, 4, E, "cpu", cfg, seed=seed, lstm_hidden=8)) if recurrent else \
+         (lambda seed: PPO(env.obs_width, 4, 4, E, "cpu", cfg, seed=seed))
+    ego, partner = mk(0), BatchedOnPolicyAgent(mk(1))
+    penv = PantheonVecEnv(env, partner)
+    obs, starts = penv.reset(), torch.ones(E)
+    for _ in range(2):
+        obs, starts, stats = collect_and_train(penv, ego, obs, starts)
+        assert all(np.isfinite(v) for v in stats.values())
+    assert partner.iteration >= 1 and ego.n_updates == 2
+    assert penv.pop_episode_stats()["episodes"] == E * 2
+    env.close()
+
+
+@pytest.mark.parametrize("flags", [[], ["--recurrent", "--lstm-hidden", "8"]])
+def test_train_ppo_main_loop_on_the_emulated_env(flags):
+    """train_ppo.main end to end (training iterations, logging, tester.py-style deterministic
+    evaluation) with the env swapped for the CPU emulation; learning itself is the GPU test's job."""
+    import train_ppo
+
+    def factory(ns, args):
+        return OvercookedVecEnv(ns, num_envs=args.envs, device="cpu", seed=args.seed, auto_reset=True, lib=emu_library())
+    hist = train_ppo.main(["--envs", "8", "--n-steps", "5", "--iters", "3", "--log-every", "1", "--batch-size", "20",
+                           "--max-num-timesteps", "4", "--epochs", "1", "--eval-steps", "9", "--device", "cpu"] + flags,
+                          env_factory=factory)
+    assert len(hist) == 4 and hist[-1]["eval"] and hist[-1]["episodes"] == 8 * 2
+    assert all(np.isfinite(v) for h in hist[:3] for v in h["ego_loss"].values())

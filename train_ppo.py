@@ -17,10 +17,11 @@ import torch
 
 from gym_comm_b200 import OvercookedVecEnv, create_arglist, namespace_from_dict
 from gym_comm_b200.pantheon import BatchedOnPolicyAgent, PantheonVecEnv, collect_and_train
-from gym_comm_b200.ppo import PPO, PPOConfig
+from gym_comm_b200.ppo import PPO, PPOConfig, RecurrentPPO
 
 
-def main(argv=None):
+def main(argv=None, env_factory=None):
+    """`env_factory(ns, args)` lets the CPU tests put the emulated env under the same training loop."""
     ap = argparse.ArgumentParser()
     ap.add_argument("--json-path", default=None, help="env config JSON (reference trainer.py --json-path)")
     ap.add_argument("--level", default="open-divider_tomato")
@@ -35,6 +36,9 @@ def main(argv=None):
     ap.add_argument("--ent-coef", type=float, default=0.01)
     ap.add_argument("--lr", type=float, default=1e-3)
     ap.add_argument("--reward-scale", type=float, default=0.1, help="learner-side reward scaling (1.0 = the reference's raw reward)")
+    ap.add_argument("--recurrent", action="store_true",
+                    help="LSTM actor-critic for both learners (the reference's RecurrentPPO, trainer.py:92-121)")
+    ap.add_argument("--lstm-hidden", type=int, default=256)
     ap.add_argument("--log-every", type=int, default=10)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--device", default="cuda:0")
@@ -48,7 +52,8 @@ def main(argv=None):
         ns = namespace_from_dict(dict(level=args.level, num_agents=2, max_num_timesteps=args.max_num_timesteps,
                                       communication_on=True, num_communication=args.num_communication))
     torch.manual_seed(args.seed)
-    env = OvercookedVecEnv(ns, num_envs=args.envs, device=args.device, seed=args.seed, auto_reset=True)
+    env = env_factory(ns, args) if env_factory is not None else \
+        OvercookedVecEnv(ns, num_envs=args.envs, device=args.device, seed=args.seed, auto_reset=True)
     h = getattr(ns, "hyperparams", {}) or {}
     cfg = PPOConfig.from_hyperparams(h, n_steps=args.n_steps, batch_size=args.batch_size, n_epochs=args.epochs)
     if "clip_range" not in h:
@@ -58,8 +63,14 @@ def main(argv=None):
     if "learning_rate" not in h:
         cfg.learning_rate = args.lr
     C = ns.num_communication
-    ego = PPO(env.obs_width, 4, C, args.envs, env.device, cfg, seed=args.seed)
-    partner = BatchedOnPolicyAgent(PPO(env.obs_width, 4, C, args.envs, env.device, cfg, seed=args.seed + 1))
+    if args.recurrent:
+        def make_learner(seed):
+            return RecurrentPPO(env.obs_width, 4, C, args.envs, env.device, cfg, seed=seed, lstm_hidden=args.lstm_hidden)
+    else:
+        def make_learner(seed):
+            return PPO(env.obs_width, 4, C, args.envs, env.device, cfg, seed=seed)
+    ego = make_learner(args.seed)
+    partner = BatchedOnPolicyAgent(make_learner(args.seed + 1))
     penv = PantheonVecEnv(env, partner, reward_scale=args.reward_scale)
 
     obs = penv.reset()
@@ -83,14 +94,18 @@ def main(argv=None):
         penv.pop_episode_stats()
 
         class _Frozen:                      # partner with the same policy, recording nothing
+            starts = torch.ones(args.envs, device=env.device)
+
             def get_action(self, o, record=True):
-                return partner.model.policy.act(o, deterministic=True)[0]
+                return partner.model.act(o, self.starts, deterministic=True)[0]
 
             def update(self, r, d):
-                pass
+                self.starts = d.to(torch.float32)
         penv.add_partner_agent(_Frozen())
+        ego_starts = torch.ones(args.envs, device=env.device)
         for _ in range(args.eval_steps):
-            obs, _, _ = penv.step(ego.policy.act(obs, deterministic=True)[0].to(torch.int32))
+            obs, _, d = penv.step(ego.act(obs, ego_starts, deterministic=True)[0].to(torch.int32))
+            ego_starts = d.to(torch.float32)
         ev = penv.pop_episode_stats()
         print(json.dumps(dict(eval=True, steps=args.eval_steps, **ev)), flush=True)
         history.append(dict(eval=True, **ev))
