@@ -371,34 +371,50 @@ def main():
     # ---- e2e: the reference-facing call with HOST buffers: OvercookedHostVecEnv.step = C ABI oc_step_host
     # (pinned numpy buffers; every step copies the actions host->device, runs the step kernel, copies
     # observations / rewards / dones device->host and synchronises before returning)
-    e2e = None
-    if not args.no_e2e:
+    # Two observation formats: float32 rows [E,A,F] (what SB3 holds after preprocessing) and the compact integer
+    # format (int8 [E,A,F-1] + f32 clock [E]: the same values, the integer keys as integers -- the reference's own
+    # dict holds int64 arrays, overcooked_env.py:145-157).  `e2e` is the compact format; `e2e_f32` sits beside it.
+    def measure_e2e(fmt):
         from gym_comm_b200.host_env import OvercookedHostVecEnv
         Ke = min(K, 200)
         henv = OvercookedHostVecEnv(ns, num_envs=E, device_index=local_rank, seed=1234 + rank, auto_reset=True,
-                                    terminal_observations=False)
-        host_actions = []                                  # the steps' inputs live in pinned host memory
-        for i in range(8):
-            pa = henv.pinned_array((E, A, 2), "int32")
-            pa[...] = actions[i].cpu().numpy()
-            host_actions.append(pa)
-        henv.reset()
-        for i in range(3):
-            henv.step(host_actions[i])
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(Ke):
-            henv.step(host_actions[i % 8])                 # returns with obs / reward / done valid on the host
-        barrier()
-        dt = time.perf_counter() - t0
-        henv.close()
+                                    terminal_observations=False, obs_format=fmt)
+        try:
+            host_actions = []                              # the steps' inputs live in pinned host memory
+            for i in range(8):
+                pa = henv.pinned_array((E, A, 2), "int32")
+                pa[...] = actions[i].cpu().numpy()
+                host_actions.append(pa)
+            henv.reset()
+            for i in range(3):
+                henv.step(host_actions[i])
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(Ke):
+                henv.step(host_actions[i % 8])             # returns with obs / reward / done valid on the host
+            barrier()
+            dt = time.perf_counter() - t0
+            obs_bytes = henv.obs.nbytes + (henv.timestep.nbytes if henv.timestep is not None else 0)
+        finally:
+            henv.close()
         tm = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        e2e = {"value": float(E) * A * Ke * world / float(tm.item()), "unit": "agent-steps/s",
-               "h2d_bytes_per_step": E * A * 2 * 4, "d2h_bytes_per_step": E * A * F * 4 + E * A * 4 + E,
-               "steps": Ke, "api": "OvercookedHostVecEnv.step = C ABI oc_step_host, pinned numpy buffers, synchronised every step",
-               "cpu_affinity": "nvml (GPU-local cores)" if affinity else "none"}
+        entry = "oc_step_host_i8" if fmt == "i8" else "oc_step_host"
+        return {"value": float(E) * A * Ke * world / float(tm.item()), "unit": "agent-steps/s",
+                "h2d_bytes_per_step": E * A * 2 * 4, "d2h_bytes_per_step": obs_bytes + E * A * 4 + E,
+                "steps": Ke, "obs_format": ("int8 [E,A,F-1] + f32 clock [E]" if fmt == "i8" else "f32 [E,A,F]"),
+                "api": "OvercookedHostVecEnv(obs_format=%r).step = C ABI %s, pinned numpy buffers, synchronised every step" % (fmt, entry),
+                "gpu_launches_per_step": 2 if fmt == "i8" else 1,
+                "cpu_affinity": "nvml (GPU-local cores)" if affinity else "none"}
+
+    e2e = e2e_f32 = None
+    if not args.no_e2e:
+        e2e_f32 = measure_e2e("f32")
+        try:
+            e2e = measure_e2e("i8")
+        except Exception as ex:                # every rank takes the same path: the failure modes are build-level
+            e2e = dict(e2e_f32, note="compact format failed (%r); this is the float format" % (ex,))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -419,7 +435,7 @@ def main():
                            mode_desc=desc[args.mode], cuda_graphs=primary["cuda_graphs"], rollout_ring_slots=R,
                            l2="inputs/outputs larger than L2: the obs ring (%d x %.1f MB) is rewritten round-robin and the action pool is %.1f GB; only the %.1f MB packed state stays L2-resident (by design)"
                               % (R, E * A * F * 4 / 1e6, P * E * A * 8 / 1e9, E * 64 / 1e6)),
-            "roofline": primary["roofline"], "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": primary["roofline"], "cpu_baseline": cpu, "e2e": e2e, "e2e_f32": e2e_f32,
             "gpu_launches": primary["gpu_launches"], "clocks": primary["clocks"],
         }
         if secondary is not None:

@@ -20,7 +20,8 @@ OBS_KEYS = ("agent1_comm", "agent1_location", "agent2_comm", "agent2_location", 
 
 EXPORTS = ("oc_abi_version", "oc_last_error", "oc_create", "oc_destroy", "oc_obs_width", "oc_obs_layout",
            "oc_reset", "oc_step", "oc_rollout", "oc_replay", "oc_get_state", "oc_set_state", "oc_get_stats",
-           "oc_launch_count", "oc_reset_host", "oc_step_host", "oc_host_alloc", "oc_host_free", "oc_set_device")
+           "oc_launch_count", "oc_reset_host", "oc_step_host", "oc_pack_obs_i8", "oc_reset_host_i8",
+           "oc_step_host_i8", "oc_host_alloc", "oc_host_free", "oc_set_device")
 
 
 class OcConfig(C.Structure):
@@ -91,9 +92,12 @@ class OcLibrary:
         self.get_state = fn("get_state", C.c_int, [vp, vp, vp])
         self.set_state = fn("set_state", C.c_int, [vp, vp, vp])
         self.get_stats = fn("get_stats", C.c_int, [vp, vp, vp, vp])
+        self.pack_obs_i8 = fn("pack_obs_i8", C.c_int, [vp, vp, vp, vp, vp])
         if prefix == "oc_":
             self.reset_host = fn("reset_host", C.c_int, [vp, vp, vp, vp, vp])
             self.step_host = fn("step_host", C.c_int, [vp, vp, vp, vp, vp, vp, vp, u32, vp])
+            self.reset_host_i8 = fn("reset_host_i8", C.c_int, [vp, vp, vp, vp, vp, vp])
+            self.step_host_i8 = fn("step_host_i8", C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, u32, vp])
             self.host_alloc = fn("host_alloc", C.c_int, [C.c_uint64, C.POINTER(vp)])
             self.host_free = fn("host_free", C.c_int, [vp])
             self.set_device = fn("set_device", C.c_int, [C.c_int])

@@ -844,4 +844,29 @@ __device__ __forceinline__ void reset_logic(Env<A, NOBJ>& e, const OcParams& p, 
     }
 }
 
+// ---- compact integer format (oc_pack_obs_i8): every key of a row except the clock is a small
+// integer (get_observation2 builds them as int64 arrays, overcooked_env.py:145-157), so a consumer
+// on the far side of PCIe gets them as int8 [E, A, F-1] (key order kept, the `timestep` column cut
+// out) plus the clock as f32 [E] (the same for every agent of an env): 4x fewer bytes, same values.
+// One thread produces word `w` = 4 consecutive output bytes (rows are F-1 bytes, so a word may
+// straddle two rows); the first E threads also copy their env's clock.
+__device__ __forceinline__ void pack_i8_word(const OcParams& p, const float* __restrict__ obs,
+                                             int8_t* __restrict__ out, float* __restrict__ ts, uint32_t w) {
+    const uint32_t Fm = (uint32_t)p.F - 1u, F = (uint32_t)p.F, off_ts = (uint32_t)p.off_ts;
+    const uint32_t nbytes = (uint32_t)p.E * (uint32_t)p.A * Fm;
+    if (ts != nullptr && w < (uint32_t)p.E) ts[w] = obs[(size_t)w * p.row_bytes + off_ts];
+    const uint32_t j0 = w * 4u;
+    if (j0 >= nbytes) return;
+    uint32_t r = j0 / Fm, c = j0 - r * Fm;            // observer row, column inside the packed row
+    uint32_t word = 0;
+    const uint32_t n = min(4u, nbytes - j0);
+    for (uint32_t k = 0; k < n; ++k) {
+        const float v = obs[(size_t)r * F + c + (c >= off_ts ? 1u : 0u)];
+        word |= ((uint32_t)(int)v & 0xFFu) << (8u * k);
+        if (++c == Fm) { c = 0; ++r; }
+    }
+    if (n == 4u) *reinterpret_cast<uint32_t*>(out + j0) = word;
+    else for (uint32_t k = 0; k < n; ++k) out[j0 + k] = (int8_t)(word >> (8u * k));
+}
+
 }  // namespace ock

@@ -158,6 +158,14 @@ __global__ void oc_stats_kernel(const uint4* __restrict__ planes, uint32_t* __re
     if (last_completed) last_completed[i] = planes[(size_t)E + i].y & 0xFFu;
 }
 
+// float rows [E, A, F] -> int8 rows [E, A, F-1] + clock f32 [E]; one thread per output word
+__global__ void __launch_bounds__(256)
+oc_pack_i8_kernel(const __grid_constant__ OcParams p, const float* __restrict__ obs, int8_t* __restrict__ out,
+                  float* __restrict__ ts, uint32_t nwords) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < nwords) pack_i8_word(p, obs, out, ts, w);
+}
+
 // =============================================================================================
 // host side
 // =============================================================================================
@@ -189,6 +197,8 @@ struct oc_env {
         int32_t* actions = nullptr; float* obs = nullptr; float* rew32 = nullptr; double* rew64 = nullptr;
         uint8_t* done = nullptr; float* term = nullptr; uint8_t* mask = nullptr; int32_t* place = nullptr;
         float* h_term = nullptr;       // pinned host copy of `term` for steps where many envs finish
+        int8_t* obs8 = nullptr; float* ts = nullptr;          // compact format (oc_*_host_i8)
+        int8_t* term8 = nullptr; float* term_ts = nullptr;
     } hp;
 };
 
@@ -331,7 +341,8 @@ extern "C" int oc_destroy(oc_env* h) {
     if (h->blob) cudaFree(h->blob);
     if (h->ts) cudaFree(h->ts);
     for (void* q : {(void*)h->hp.actions, (void*)h->hp.obs, (void*)h->hp.rew32, (void*)h->hp.rew64, (void*)h->hp.done,
-                    (void*)h->hp.term, (void*)h->hp.mask, (void*)h->hp.place})
+                    (void*)h->hp.term, (void*)h->hp.mask, (void*)h->hp.place, (void*)h->hp.obs8, (void*)h->hp.ts,
+                    (void*)h->hp.term8, (void*)h->hp.term_ts})
         if (q) cudaFree(q);
     if (h->hp.h_term) cudaFreeHost(h->hp.h_term);
     delete h;
@@ -497,12 +508,30 @@ static int ensure_dev(T*& ptr, size_t count) {
     return OC_OK;
 }
 
-extern "C" int oc_reset_host(oc_env* h, const uint8_t* mask, const int32_t* placements, float* obs, void* stream) {
+// device-side repack of float rows into the compact integer format (also usable on its own)
+extern "C" int oc_pack_obs_i8(oc_env* h, const float* obs, int8_t* obs_i8, float* timestep, void* stream) {
+    if (!h || !obs || !obs_i8) return fail(OC_ERR_INVALID, "null argument");
+    if (reinterpret_cast<uintptr_t>(obs_i8) & 3) return fail(OC_ERR_INVALID, "obs_i8 must be 4-byte aligned");
+    if (int dc = check_device(h)) return dc;
+    const OcParams& p = h->p;
+    if (p.off_ts != p.F - 1) return fail(OC_ERR_INVALID, "timestep is not the last key of the row");
+    const uint64_t nbytes = (uint64_t)p.E * p.A * (p.F - 1);
+    if ((uint64_t)p.E * p.A * p.F >= (1ull << 32)) return fail(OC_ERR_INVALID, "batch too large for the 32-bit pack index");
+    const uint32_t nwords = (uint32_t)std::max<uint64_t>((nbytes + 3) / 4, (uint64_t)p.E);
+    oc_pack_i8_kernel<<<(nwords + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p, obs, obs_i8, timestep, nwords);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    return OC_OK;
+}
+
+// i8 = compact format: obs / term_obs are int8 [E, A, F-1] and the clocks go to ts / term_ts (f32 [E])
+static int reset_host_impl(oc_env* h, const uint8_t* mask, const int32_t* placements, void* obs, float* ts,
+                           bool i8, void* stream) {
     if (!h) return fail(OC_ERR_INVALID, "null handle");
     if (int dc = check_device(h)) return dc;
     const OcParams& p = h->p;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t E = (size_t)p.E, row = (size_t)p.row_bytes;
+    const size_t E = (size_t)p.E, row = (size_t)p.row_bytes, row8 = (size_t)p.A * (p.F - 1);
     int rc;
     if (mask) {
         if ((rc = ensure_dev(h->hp.mask, E))) return rc;
@@ -513,52 +542,101 @@ extern "C" int oc_reset_host(oc_env* h, const uint8_t* mask, const int32_t* plac
         CUDA_TRY(cudaMemcpyAsync(h->hp.place, placements, E * p.nrandom * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     }
     if (obs && (rc = ensure_dev(h->hp.obs, E * row))) return rc;
+    if (obs && i8 && ((rc = ensure_dev(h->hp.obs8, E * row8 + 4)) || (rc = ensure_dev(h->hp.ts, E)))) return rc;
     if ((rc = oc_reset(h, mask ? h->hp.mask : nullptr, (placements && p.nrandom > 0) ? h->hp.place : nullptr,
                        obs ? h->hp.obs : nullptr, stream))) return rc;
-    if (obs) CUDA_TRY(cudaMemcpyAsync(obs, h->hp.obs, E * row * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (obs && i8) {
+        if ((rc = oc_pack_obs_i8(h, h->hp.obs, h->hp.obs8, h->hp.ts, stream))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(obs, h->hp.obs8, E * row8, cudaMemcpyDeviceToHost, st));
+        if (ts) CUDA_TRY(cudaMemcpyAsync(ts, h->hp.ts, E * sizeof(float), cudaMemcpyDeviceToHost, st));
+    } else if (obs) {
+        CUDA_TRY(cudaMemcpyAsync(obs, h->hp.obs, E * row * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
     return OC_OK;
 }
 
-extern "C" int oc_step_host(oc_env* h, const int32_t* actions, float* obs, float* rew_f32, double* rew_f64,
-                            uint8_t* done, float* term_obs, uint32_t flags, void* stream) {
+static int step_host_impl(oc_env* h, const int32_t* actions, void* obs, float* ts, float* rew_f32, double* rew_f64,
+                          uint8_t* done, void* term_obs, float* term_ts, bool i8, uint32_t flags, void* stream) {
     if (!h || !actions || !obs || !done) return fail(OC_ERR_INVALID, "null argument");
     if (int dc = check_device(h)) return dc;
     const OcParams& p = h->p;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t E = (size_t)p.E, A = (size_t)p.A, row = (size_t)p.row_bytes;
+    const size_t E = (size_t)p.E, A = (size_t)p.A, row = (size_t)p.row_bytes, row8 = A * (size_t)(p.F - 1);
     int rc;
     if ((rc = ensure_dev(h->hp.actions, E * A * 2)) || (rc = ensure_dev(h->hp.obs, E * row)) ||
         (rc = ensure_dev(h->hp.done, E))) return rc;
+    if (i8 && ((rc = ensure_dev(h->hp.obs8, E * row8 + 4)) || (rc = ensure_dev(h->hp.ts, E)))) return rc;
     if (rew_f32 && (rc = ensure_dev(h->hp.rew32, E * A))) return rc;
     if (rew_f64 && (rc = ensure_dev(h->hp.rew64, E))) return rc;
     const bool want_term = term_obs != nullptr && (flags & OC_FLAG_AUTO_RESET);
-    if (want_term && (rc = ensure_dev(h->hp.term, E * row))) return rc;
+    if (want_term && !h->hp.term) {                    // rows of envs that never finished stay zero
+        if ((rc = ensure_dev(h->hp.term, E * row))) return rc;
+        CUDA_TRY(cudaMemsetAsync(h->hp.term, 0, E * row * sizeof(float), st));
+    }
+    if (want_term && i8 && ((rc = ensure_dev(h->hp.term8, E * row8 + 4)) || (rc = ensure_dev(h->hp.term_ts, E)))) return rc;
     CUDA_TRY(cudaMemcpyAsync(h->hp.actions, actions, E * A * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     if ((rc = oc_step(h, h->hp.actions, h->hp.obs, rew_f32 ? h->hp.rew32 : nullptr, rew_f64 ? h->hp.rew64 : nullptr,
                       h->hp.done, want_term ? h->hp.term : nullptr, flags, stream))) return rc;
     CUDA_TRY(cudaMemcpyAsync(done, h->hp.done, E, cudaMemcpyDeviceToHost, st));
     if (rew_f32) CUDA_TRY(cudaMemcpyAsync(rew_f32, h->hp.rew32, E * A * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (rew_f64) CUDA_TRY(cudaMemcpyAsync(rew_f64, h->hp.rew64, E * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(obs, h->hp.obs, E * row * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (i8) {
+        if ((rc = oc_pack_obs_i8(h, h->hp.obs, h->hp.obs8, h->hp.ts, stream))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(obs, h->hp.obs8, E * row8, cudaMemcpyDeviceToHost, st));
+        if (ts) CUDA_TRY(cudaMemcpyAsync(ts, h->hp.ts, E * sizeof(float), cudaMemcpyDeviceToHost, st));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(obs, h->hp.obs, E * row * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
     if (want_term) {                                   // only the rows of envs that just finished reach the caller's buffer
         size_t nfin = 0;
         for (size_t e = 0; e < E; ++e) nfin += done[e] != 0;
-        if (nfin > 0 && nfin <= 64) {
+        if (nfin == 0) return OC_OK;
+        if (i8 && (rc = oc_pack_obs_i8(h, h->hp.term, h->hp.term8, h->hp.term_ts, stream))) return rc;
+        const uint8_t* src = i8 ? (const uint8_t*)h->hp.term8 : (const uint8_t*)h->hp.term;
+        uint8_t* dst = (uint8_t*)term_obs;
+        const size_t rb = i8 ? row8 : row * sizeof(float);                // bytes of one env's rows
+        if (nfin <= 64) {
             for (size_t e = 0; e < E; ++e)
-                if (done[e]) CUDA_TRY(cudaMemcpyAsync(term_obs + e * row, h->hp.term + e * row, row * sizeof(float), cudaMemcpyDeviceToHost, st));
+                if (done[e]) {
+                    CUDA_TRY(cudaMemcpyAsync(dst + e * rb, src + e * rb, rb, cudaMemcpyDeviceToHost, st));
+                    if (i8 && term_ts) CUDA_TRY(cudaMemcpyAsync(term_ts + e, h->hp.term_ts + e, sizeof(float), cudaMemcpyDeviceToHost, st));
+                }
             CUDA_TRY(cudaStreamSynchronize(st));
-        } else if (nfin > 0) {
-            if (!h->hp.h_term) {
-                cudaError_t ce = cudaHostAlloc((void**)&h->hp.h_term, E * row * sizeof(float), cudaHostAllocDefault);
+        } else {
+            if (!h->hp.h_term) {                       // sized for the float format; the compact one fits inside (+ clocks)
+                cudaError_t ce = cudaHostAlloc((void**)&h->hp.h_term, E * row * sizeof(float) + E * sizeof(float), cudaHostAllocDefault);
                 if (ce != cudaSuccess) { h->hp.h_term = nullptr; return fail(OC_ERR_ALLOC, std::string("cudaHostAlloc: ") + cudaGetErrorString(ce)); }
             }
-            CUDA_TRY(cudaMemcpyAsync(h->hp.h_term, h->hp.term, E * row * sizeof(float), cudaMemcpyDeviceToHost, st));
+            uint8_t* hb = (uint8_t*)h->hp.h_term;
+            float* hts = (float*)(hb + E * row * sizeof(float));
+            CUDA_TRY(cudaMemcpyAsync(hb, src, E * rb, cudaMemcpyDeviceToHost, st));
+            if (i8 && term_ts) CUDA_TRY(cudaMemcpyAsync(hts, h->hp.term_ts, E * sizeof(float), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
             for (size_t e = 0; e < E; ++e)
-                if (done[e]) memcpy(term_obs + e * row, h->hp.h_term + e * row, row * sizeof(float));
+                if (done[e]) {
+                    memcpy(dst + e * rb, hb + e * rb, rb);
+                    if (i8 && term_ts) term_ts[e] = hts[e];
+                }
         }
     }
     return OC_OK;
+}
+
+extern "C" int oc_reset_host(oc_env* h, const uint8_t* mask, const int32_t* placements, float* obs, void* stream) {
+    return reset_host_impl(h, mask, placements, obs, nullptr, false, stream);
+}
+extern "C" int oc_step_host(oc_env* h, const int32_t* actions, float* obs, float* rew_f32, double* rew_f64,
+                            uint8_t* done, float* term_obs, uint32_t flags, void* stream) {
+    return step_host_impl(h, actions, obs, nullptr, rew_f32, rew_f64, done, term_obs, nullptr, false, flags, stream);
+}
+extern "C" int oc_reset_host_i8(oc_env* h, const uint8_t* mask, const int32_t* placements, int8_t* obs_i8,
+                                float* timestep, void* stream) {
+    return reset_host_impl(h, mask, placements, obs_i8, timestep, true, stream);
+}
+extern "C" int oc_step_host_i8(oc_env* h, const int32_t* actions, int8_t* obs_i8, float* timestep, float* rew_f32,
+                               double* rew_f64, uint8_t* done, int8_t* term_obs_i8, float* term_timestep,
+                               uint32_t flags, void* stream) {
+    return step_host_impl(h, actions, obs_i8, timestep, rew_f32, rew_f64, done, term_obs_i8, term_timestep, true, flags, stream);
 }

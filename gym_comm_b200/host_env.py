@@ -33,18 +33,26 @@ class OvercookedHostVecEnv:
     next episode and ``infos[e]["terminal_observation"]`` the last one of the finished episode (a view of
     ``env.terminal_obs[e]``; with very large batches read ``env.terminal_obs`` and ``done`` directly instead
     of walking the list).
+    ``obs_format="i8"`` switches the observation buffers to the compact integer format of
+    `oc_step_host_i8`: ``obs`` is int8 [E, A, F-1] (every key but the clock -- the reference builds these
+    keys as integer arrays, overcooked_env.py:145-157) and the clock is ``env.timestep`` f32 [E] (after a
+    finished episode: ``infos[e]["terminal_timestep"]``); 4x fewer bytes cross PCIe per step.
+    ``obs_float()`` rebuilds the float rows, ``obs_dict()`` gives the reference's per-key view in both formats.
     The returned arrays (and the `infos` list) are the env's own pinned buffers, overwritten by the next
     call (copy them to keep them, as SB3's rollout buffer does) and invalid after `close()`.
     """
 
     def __init__(self, arglist, num_envs: int = 1, device_index: int = 0, seed: int = 0, auto_reset: bool = True,
                  terminal_observations: bool = True, level_text: Optional[str] = None, subtasks=None,
-                 lib: Optional[_cabi.OcLibrary] = None):
+                 lib: Optional[_cabi.OcLibrary] = None, obs_format: str = "f32"):
         self.arglist = normalize(arglist)
         a = self.arglist
         self.lib = lib if lib is not None else _cabi.default_library()
         if self.lib.prefix != "oc_":
             raise RuntimeError("OvercookedHostVecEnv needs liboc_b200.so (CUDA); there is no CPU backend")
+        if obs_format not in ("f32", "i8"):
+            raise ValueError("obs_format must be 'f32' or 'i8'")
+        self.obs_format = obs_format
         self.device_index = int(device_index)
         self.num_envs, self.num_agents = int(num_envs), int(a.num_agents)
         self.auto_reset = bool(auto_reset)
@@ -66,11 +74,17 @@ class OvercookedHostVecEnv:
         self.obs_layout = {k: slice(off[i], off[i] + size[i]) for i, k in enumerate(_cabi.OBS_KEYS)}
         self.observation_space, self.action_space = make_spaces(self.level, a.num_communication)
         E, A, F = self.num_envs, self.num_agents, self.obs_width
-        self.obs = self.pinned_array((E, A, F), np.float32)
+        i8 = obs_format == "i8"
+        if i8 and self.obs_layout["timestep"] != slice(F - 1, F):
+            raise RuntimeError("the compact format expects `timestep` to be the last key of a row")
+        odt, Fo = (np.int8, F - 1) if i8 else (np.float32, F)
+        self.obs = self.pinned_array((E, A, Fo), odt)
+        self.timestep = self.pinned_array((E,), np.float32) if i8 else None
         self.rewards = self.pinned_array((E, A), np.float32)
         self.dones = self.pinned_array((E,), np.uint8)
         self.actions = self.pinned_array((E, A, 2), np.int32)
-        self.terminal_obs = self.pinned_array((E, A, F), np.float32) if (terminal_observations and auto_reset) else None
+        self.terminal_obs = self.pinned_array((E, A, Fo), odt) if (terminal_observations and auto_reset) else None
+        self.terminal_timestep = self.pinned_array((E,), np.float32) if (i8 and self.terminal_obs is not None) else None
         self._infos = [{} for _ in range(E)]
         self._touched = ()
 
@@ -102,8 +116,12 @@ class OvercookedHostVecEnv:
         if placements is not None:
             self._check(placements, (self.num_envs, self.level.num_random), np.int32, "placements")
         self.lib.check(self.lib.set_device(self.device_index), "oc_set_device")
-        self.lib.check(self.lib.reset_host(self._handle, self._p(mask), self._p(placements), self._p(self.obs), None),
-                       "oc_reset_host")
+        if self.obs_format == "i8":
+            self.lib.check(self.lib.reset_host_i8(self._handle, self._p(mask), self._p(placements), self._p(self.obs),
+                                                  self._p(self.timestep), None), "oc_reset_host_i8")
+        else:
+            self.lib.check(self.lib.reset_host(self._handle, self._p(mask), self._p(placements), self._p(self.obs), None),
+                           "oc_reset_host")
         return self.obs
 
     def step(self, actions: np.ndarray):
@@ -116,9 +134,15 @@ class OvercookedHostVecEnv:
             a = self.actions
         flags = _cabi.OC_FLAG_AUTO_RESET if self.auto_reset else 0
         self.lib.check(self.lib.set_device(self.device_index), "oc_set_device")
-        self.lib.check(self.lib.step_host(self._handle, self._p(a), self._p(self.obs), self._p(self.rewards),
-                                          None, self._p(self.dones), self._p(self.terminal_obs), flags, None),
-                       "oc_step_host")
+        if self.obs_format == "i8":
+            self.lib.check(self.lib.step_host_i8(self._handle, self._p(a), self._p(self.obs), self._p(self.timestep),
+                                                 self._p(self.rewards), None, self._p(self.dones),
+                                                 self._p(self.terminal_obs), self._p(self.terminal_timestep), flags, None),
+                           "oc_step_host_i8")
+        else:
+            self.lib.check(self.lib.step_host(self._handle, self._p(a), self._p(self.obs), self._p(self.rewards),
+                                              None, self._p(self.dones), self._p(self.terminal_obs), flags, None),
+                           "oc_step_host")
         d = self.dones.view(np.bool_)
         # one dict per env, allocated once; only the entries of envs that finished are touched
         for e in self._touched:
@@ -127,6 +151,8 @@ class OvercookedHostVecEnv:
         term = self.terminal_obs
         for e in self._touched:                      # views into the pinned buffer (valid until env e finishes again)
             self._infos[e]["terminal_observation"] = term[e]
+            if self.terminal_timestep is not None:
+                self._infos[e]["terminal_timestep"] = self.terminal_timestep[e]
         return self.obs, self.rewards, d, self._infos
 
     # SB3 VecEnv duck type (the rest of the convention; every env shares one configuration)
@@ -147,10 +173,27 @@ class OvercookedHostVecEnv:
         n = self.num_envs if indices is None else len([indices] if isinstance(indices, int) else list(indices))
         return [False] * n
 
-    def obs_dict(self, obs: Optional[np.ndarray] = None) -> dict:
-        """Per-key zero-copy views of flat rows (the reference's Dict observation)."""
+    def obs_dict(self, obs: Optional[np.ndarray] = None, timestep: Optional[np.ndarray] = None) -> dict:
+        """Per-key zero-copy views of flat rows (the reference's Dict observation).  Compact format: the
+        integer keys are int8 views and `timestep` is the per-env clock broadcast to [E, A, 1]."""
         o = self.obs if obs is None else obs
-        return {k: o[..., s] for k, s in self.obs_layout.items()}
+        if self.obs_format != "i8":
+            return {k: o[..., s] for k, s in self.obs_layout.items()}
+        t = self.timestep if timestep is None else timestep
+        d = {k: o[..., s] for k, s in self.obs_layout.items() if k != "timestep"}
+        d["timestep"] = np.broadcast_to(np.asarray(t, np.float32).reshape(-1, 1, 1), o.shape[:-1] + (1,))
+        return d
+
+    def obs_float(self, obs: Optional[np.ndarray] = None, timestep: Optional[np.ndarray] = None) -> np.ndarray:
+        """The float32 rows [E, A, F] (a new array) -- what `obs_format="f32"` returns directly."""
+        o = self.obs if obs is None else obs
+        if self.obs_format != "i8":
+            return np.array(o, np.float32)
+        t = self.timestep if timestep is None else timestep
+        out = np.empty(o.shape[:-1] + (self.obs_width,), np.float32)
+        out[..., :-1] = o
+        out[..., -1] = np.asarray(t, np.float32).reshape(-1, 1)
+        return out
 
     def close(self):
         if self._closed:
@@ -166,6 +209,7 @@ class OvercookedHostVecEnv:
             self._handle = C.c_void_p()
             self._pinned = []
             self.obs = self.rewards = self.dones = self.actions = self.terminal_obs = None
+            self.timestep = self.terminal_timestep = None
 
     def __del__(self):
         try:

@@ -188,6 +188,21 @@ class OvercookedVecEnv:
         obs = self.obs if obs is None else obs
         return {k: obs[..., s] for k, s in self.obs_layout.items()}
 
+    def pack_obs_i8(self, obs: Optional[torch.Tensor] = None, out=None, timestep_out=None):
+        """Float rows [E, A, F] -> the compact integer format of `oc_pack_obs_i8` (include/overcooked_b200.h):
+        ``(int8 [E, A, F-1], f32 [E] clock)`` on the same device, e.g. before shipping a rollout to a host."""
+        obs = self.obs if obs is None else obs
+        E, A, F = self.num_envs, self.num_agents, self.obs_width
+        self._check_tensor(obs, (E, A, F), torch.float32, "obs")
+        out = torch.empty((E, A, F - 1), dtype=torch.int8, device=self.device) if out is None else out
+        ts = torch.empty((E,), dtype=torch.float32, device=self.device) if timestep_out is None else timestep_out
+        self._check_tensor(out, (E, A, F - 1), torch.int8, "out")
+        self._check_tensor(ts, (E,), torch.float32, "timestep_out")
+        with self._device_guard():
+            self.lib.check(self.lib.pack_obs_i8(self._handle, self._ptr(obs), self._ptr(out), self._ptr(ts), self._stream()),
+                           "oc_pack_obs_i8")
+        return out, ts
+
     def decode_state(self, st: Optional[torch.Tensor] = None):
         """Packed state -> readable numpy fields (layout: gym_comm_b200/csrc/oc_params.h)."""
         w = (self.get_state() if st is None else st).cpu().numpy().view(np.uint32)

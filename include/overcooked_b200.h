@@ -190,6 +190,22 @@ uint64_t oc_launch_count(const oc_env* env);
 int oc_reset_host(oc_env* env, const uint8_t* mask, const int32_t* placements, float* obs, void* stream);
 int oc_step_host(oc_env* env, const int32_t* actions, float* obs, float* rew_f32, double* rew_f64,
                  uint8_t* done, float* term_obs, uint32_t flags, void* stream);
+/* ---- Compact integer format.  Every key of an observation row except the clock holds small integers -- the
+ * reference builds them as int64 arrays (get_observation2, gym_comm/envs/overcooked_env.py:145-157; the spaces
+ * at :56-78 are Box(int64) / MultiBinary) and only SB3's preprocessing turns them into float32.  For a consumer
+ * on the far side of PCIe the same values travel as
+ *    obs_i8    int8[E, A, F-1]  the row with the `timestep` column (the last key, oc_obs_layout) cut out
+ *    timestep  f32[E]           float32(t / max_num_timesteps), identical for every agent of an env
+ * i.e. 4x fewer bytes than the float rows; `obs_i8.astype(float32)` with `timestep` appended IS the float row.
+ * oc_pack_obs_i8 converts float rows already on the DEVICE (all pointers device, obs_i8 4-byte aligned,
+ * timestep may be NULL); the _host_i8 entry points are oc_reset_host / oc_step_host with the observation
+ * buffers in this format (HOST pointers; term_timestep[e] is written only for envs that finished). */
+int oc_pack_obs_i8(oc_env* env, const float* obs, int8_t* obs_i8, float* timestep, void* stream);
+int oc_reset_host_i8(oc_env* env, const uint8_t* mask, const int32_t* placements, int8_t* obs_i8, float* timestep,
+                     void* stream);
+int oc_step_host_i8(oc_env* env, const int32_t* actions, int8_t* obs_i8, float* timestep, float* rew_f32,
+                    double* rew_f64, uint8_t* done, int8_t* term_obs_i8, float* term_timestep, uint32_t flags,
+                    void* stream);
 /* Page-locked host memory for those buffers (cudaHostAlloc / cudaFreeHost without linking the CUDA runtime). */
 int oc_host_alloc(uint64_t bytes, void** out);
 int oc_host_free(void* ptr);

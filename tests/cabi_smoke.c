@@ -90,9 +90,17 @@ int main(void) {
      * oc_host_alloc must agree with the device-pointer path run on a second handle */
     {
         cfg.seed = 11;
-        oc_env *ha = NULL, *hb = NULL;
+        oc_env *ha = NULL, *hb = NULL, *hc = NULL;     /* hc: the compact integer format (oc_step_host_i8) */
         CHECK(oc_create(&cfg, &ha));
         CHECK(oc_create(&cfg, &hb));
+        CHECK(oc_create(&cfg, &hc));
+        int8_t *p_o8, *p_t8; float *p_ts, *p_tts; uint8_t* p_done8;
+        CHECK(oc_host_alloc((size_t)E * A * (F - 1), (void**)&p_o8));
+        CHECK(oc_host_alloc((size_t)E * A * (F - 1), (void**)&p_t8));
+        CHECK(oc_host_alloc(E * sizeof(float), (void**)&p_ts));
+        CHECK(oc_host_alloc(E * sizeof(float), (void**)&p_tts));
+        CHECK(oc_host_alloc(E, (void**)&p_done8));
+        CHECK(oc_reset_host_i8(hc, NULL, NULL, p_o8, p_ts, NULL));
         int32_t* p_act; float *p_obs, *p_rew, *p_term; uint8_t* p_done;
         CHECK(oc_host_alloc(sizeof(h_act), (void**)&p_act));
         CHECK(oc_host_alloc(sizeof(h_obs), (void**)&p_obs));
@@ -113,6 +121,20 @@ int main(void) {
             if (memcmp(h_obs, p_obs, sizeof(h_obs)) != 0 || memcmp(h_done, p_done, E) != 0) {
                 fprintf(stderr, "oc_step_host differs from oc_step at t=%d\n", t); return 1;
             }
+            CHECK(oc_step_host_i8(hc, p_act, p_o8, p_ts, NULL, NULL, p_done8, p_t8, p_tts, OC_FLAG_AUTO_RESET, NULL));
+            if (memcmp(p_done8, p_done, E) != 0) { fprintf(stderr, "oc_step_host_i8: done differs at t=%d\n", t); return 1; }
+            for (int e = 0; e < E; ++e)
+                for (int k = 0; k < A; ++k) {
+                    const float* fr = p_obs + ((size_t)e * A + k) * F;
+                    const int8_t* br = p_o8 + ((size_t)e * A + k) * (F - 1);
+                    for (int c = 0; c < F - 1; ++c)
+                        if ((float)br[c] != fr[c]) { fprintf(stderr, "oc_step_host_i8 differs at t=%d env %d col %d\n", t, e, c); return 1; }
+                    if (p_ts[e] != fr[F - 1]) { fprintf(stderr, "oc_step_host_i8 clock differs at t=%d env %d\n", t, e); return 1; }
+                    if (p_done[e] && ((float)p_t8[((size_t)e * A + k) * (F - 1)] != p_term[((size_t)e * A + k) * F] ||
+                                      p_tts[e] != p_term[((size_t)e * A + k) * F + F - 1])) {
+                        fprintf(stderr, "oc_step_host_i8 terminal row differs at t=%d env %d\n", t, e); return 1;
+                    }
+                }
             for (int e = 0; e < E; ++e)
                 if (p_done[e]) {                      /* terminal observation: the clock feature of the last step = 49/50 or earlier */
                     const float ts = p_term[((size_t)e * A) * F + off[OC_OBS_TIMESTEP]];
@@ -123,7 +145,9 @@ int main(void) {
         if (term_rows != (long)E * 2) { fprintf(stderr, "expected %d terminal observations, got %ld\n", E * 2, term_rows); return 1; }
         CHECK(oc_host_free(p_act)); CHECK(oc_host_free(p_obs)); CHECK(oc_host_free(p_term));
         CHECK(oc_host_free(p_rew)); CHECK(oc_host_free(p_done));
-        CHECK(oc_destroy(ha)); CHECK(oc_destroy(hb));
+        CHECK(oc_host_free(p_o8)); CHECK(oc_host_free(p_t8)); CHECK(oc_host_free(p_ts)); CHECK(oc_host_free(p_tts));
+        CHECK(oc_host_free(p_done8));
+        CHECK(oc_destroy(ha)); CHECK(oc_destroy(hb)); CHECK(oc_destroy(hc));
         cfg.seed = 7;
     }
     /* error path: a level with two tomatoes is outside the supported domain */

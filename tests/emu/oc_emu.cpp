@@ -180,6 +180,13 @@ int emu_set_state(emu_env* h, const uint32_t* state, void*) {
         for (int pl = 0; pl < 4; ++pl) h->state[(size_t)pl * h->p.E + env] = reinterpret_cast<const uint4*>(state)[(size_t)env * 4 + pl];
     return OC_OK;
 }
+int emu_pack_obs_i8(emu_env* h, const float* obs, int8_t* obs_i8, float* timestep, void*) {   // oc_pack_i8_kernel, thread by thread
+    const OcParams& p = h->p;
+    const uint64_t nbytes = (uint64_t)p.E * p.A * (p.F - 1);
+    const uint32_t nwords = (uint32_t)std::max<uint64_t>((nbytes + 3) / 4, (uint64_t)p.E);
+    for (uint32_t w = 0; w < nwords; ++w) pack_i8_word(p, obs, obs_i8, timestep, w);
+    return OC_OK;
+}
 int emu_get_stats(emu_env* h, uint32_t* episodes, uint32_t* last_completed, void*) {
     for (int i = 0; i < h->p.E; ++i) {
         if (episodes) episodes[i] = h->state[i].y;

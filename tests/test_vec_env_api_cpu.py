@@ -126,3 +126,26 @@ def test_train_ppo_main_loop_on_the_emulated_env(flags):
                           env_factory=factory)
     assert len(hist) == 4 and hist[-1]["eval"] and hist[-1]["episodes"] == 8 * 2
     assert all(np.isfinite(v) for h in hist[:3] for v in h["ego_loss"].values())
+
+
+@pytest.mark.parametrize("E,C", [(5, 4), (67, 7), (33, 100)])
+def test_pack_obs_i8_is_the_float_row_without_the_clock(E, C):
+    """The compact integer format (oc_pack_obs_i8; the word-per-thread device function run thread by thread
+    on the CPU emulation): int8 [E, A, F-1] + f32 [E] rebuild the float rows exactly, for row widths where a
+    4-byte output word straddles rows (F-1 = 33, 39, 225) and a batch whose byte count is not a multiple of 4."""
+    ns = argparse.Namespace(level="open-divider_tomato", num_agents=2, max_num_timesteps=9, communication_on=True,
+                            num_communication=C, ego_led=False, fow_radius=2, ego_config=D, partner_config=D)
+    env = OvercookedVecEnv(ns, num_envs=E, device="cpu", lib=emu_library(), auto_reset=True)
+    gen = torch.Generator().manual_seed(E)
+    env.reset()
+    for t in range(14):
+        a = torch.stack([torch.randint(0, 4, (E, 2), generator=gen), torch.randint(0, C, (E, 2), generator=gen)], -1).to(torch.int32)
+        obs, _, _ = env.step(a)[:3]
+        guard = torch.full((E * 2 * (env.obs_width - 1) + 8,), 99, dtype=torch.int8)
+        out = guard[:E * 2 * (env.obs_width - 1)].view(E, 2, env.obs_width - 1)
+        i8, ts = env.pack_obs_i8(obs, out=out)
+        assert torch.all(guard[-8:] == 99)                                        # nothing written past the end
+        assert torch.equal(i8.to(torch.float32), obs[..., :-1])
+        assert torch.equal(ts, obs[:, 0, -1]) and torch.equal(ts, obs[:, 1, -1])
+    assert i8.min() < 0                                                           # signed deltas survive
+    env.close()
