@@ -374,11 +374,11 @@ def main():
     # Two observation formats: float32 rows [E,A,F] (what SB3 holds after preprocessing) and the compact integer
     # format (int8 [E,A,F-1] + f32 clock [E]: the same values, the integer keys as integers -- the reference's own
     # dict holds int64 arrays, overcooked_env.py:145-157).  `e2e` is the compact format; `e2e_f32` sits beside it.
-    def measure_e2e(fmt):
+    def measure_e2e(fmt, term=False):
         from gym_comm_b200.host_env import OvercookedHostVecEnv
         Ke = min(K, 200)
         henv = OvercookedHostVecEnv(ns, num_envs=E, device_index=local_rank, seed=1234 + rank, auto_reset=True,
-                                    terminal_observations=False, obs_format=fmt)
+                                    terminal_observations=term, obs_format=fmt)
         try:
             host_actions = []                              # the steps' inputs live in pinned host memory
             for i in range(8):
@@ -386,12 +386,26 @@ def main():
                 pa[...] = actions[i].cpu().numpy()
                 host_actions.append(pa)
             henv.reset()
+            if term:
+                # stagger the episode clocks (env e starts e % T steps late) so that the timed steps see the steady
+                # state of a long run: about E / T envs finish in every step and their terminal rows are delivered
+                import numpy as np
+                T = int(w["max_num_timesteps"])
+                mask = np.zeros(E, np.uint8)
+                for i in range(T):
+                    mask[:] = 0
+                    mask[i::T] = 1
+                    henv.step(host_actions[i % 8])
+                    henv.reset(mask=mask)
             for i in range(3):
                 henv.step(host_actions[i])
             barrier()
+            nfin = 0
             t0 = time.perf_counter()
             for i in range(Ke):
-                henv.step(host_actions[i % 8])             # returns with obs / reward / done valid on the host
+                d_ = henv.step(host_actions[i % 8])[2]     # returns with obs / reward / done valid on the host
+                if term:
+                    nfin += int(d_.sum())
             barrier()
             dt = time.perf_counter() - t0
             obs_bytes = henv.obs.nbytes + (henv.timestep.nbytes if henv.timestep is not None else 0)
@@ -405,12 +419,17 @@ def main():
                 "h2d_bytes_per_step": E * A * 2 * 4, "d2h_bytes_per_step": obs_bytes + E * A * 4 + E,
                 "steps": Ke, "obs_format": ("int8 [E,A,F-1] + f32 clock [E]" if fmt == "i8" else "f32 [E,A,F]"),
                 "api": "OvercookedHostVecEnv(obs_format=%r).step = C ABI %s, pinned numpy buffers, synchronised every step" % (fmt, entry),
-                "gpu_launches_per_step": 2 if fmt == "i8" else 1,
+                "gpu_launches_per_step": (2 if fmt == "i8" else 1) + (1 if term else 0),
+                "terminal_observations": bool(term), "finished_envs_per_step": (nfin / Ke if term else None),
                 "cpu_affinity": "nvml (GPU-local cores)" if affinity else "none"}
 
-    e2e = e2e_f32 = None
+    e2e = e2e_f32 = e2e_term = None
     if not args.no_e2e:
         e2e_f32 = measure_e2e("f32")
+        try:                                   # the full SB3 contract: infos[e]["terminal_observation"] for finished envs
+            e2e_term = measure_e2e("i8", term=True)
+        except Exception as ex:
+            e2e_term = {"error": repr(ex)}
         try:
             e2e = measure_e2e("i8")
         except Exception as ex:                # every rank takes the same path: the failure modes are build-level
@@ -435,7 +454,7 @@ def main():
                            mode_desc=desc[args.mode], cuda_graphs=primary["cuda_graphs"], rollout_ring_slots=R,
                            l2="inputs/outputs larger than L2: the obs ring (%d x %.1f MB) is rewritten round-robin and the action pool is %.1f GB; only the %.1f MB packed state stays L2-resident (by design)"
                               % (R, E * A * F * 4 / 1e6, P * E * A * 8 / 1e9, E * 64 / 1e6)),
-            "roofline": primary["roofline"], "cpu_baseline": cpu, "e2e": e2e, "e2e_f32": e2e_f32,
+            "roofline": primary["roofline"], "cpu_baseline": cpu, "e2e": e2e, "e2e_f32": e2e_f32, "e2e_terminal_obs": e2e_term,
             "gpu_launches": primary["gpu_launches"], "clocks": primary["clocks"],
         }
         if secondary is not None:

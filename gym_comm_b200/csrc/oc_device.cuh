@@ -869,4 +869,26 @@ __device__ __forceinline__ void pack_i8_word(const OcParams& p, const float* __r
     else for (uint32_t k = 0; k < n; ++k) out[j0 + k] = (int8_t)(word >> (8u * k));
 }
 
+// ---- terminal rows of the host path: of the E rows in `term` only those of envs that just finished are
+// wanted on the host.  Finished env number i (env index idx[i]) is copied to slot i of a dense buffer, as
+// float rows (out_f32 [n, A*F]) or in the compact format (out_i8 [n, A*(F-1)] + out_ts [n]); thread `tid` of
+// `nthreads` cooperating on one row.
+__device__ __forceinline__ void gather_term_row(const OcParams& p, const float* __restrict__ term, int e, int i,
+                                                float* __restrict__ out_f32, int8_t* __restrict__ out_i8,
+                                                float* __restrict__ out_ts, int tid, int nthreads) {
+    const float* src = term + (size_t)e * p.row_bytes;
+    if (out_f32 != nullptr) {
+        float* dst = out_f32 + (size_t)i * p.row_bytes;
+        for (int j = tid; j < p.row_bytes; j += nthreads) dst[j] = src[j];
+    } else {
+        const int Fm = p.F - 1, n8 = p.A * Fm;
+        int8_t* dst = out_i8 + (size_t)i * n8;
+        for (int j = tid; j < n8; j += nthreads) {
+            const int k = j / Fm, c = j - k * Fm;
+            dst[j] = (int8_t)(int)src[k * p.F + c + (c >= p.off_ts ? 1 : 0)];
+        }
+        if (tid == 0) out_ts[i] = src[p.off_ts];
+    }
+}
+
 }  // namespace ock

@@ -166,6 +166,14 @@ oc_pack_i8_kernel(const __grid_constant__ OcParams p, const float* __restrict__ 
     if (w < nwords) pack_i8_word(p, obs, out, ts, w);
 }
 
+// rows of the n finished envs idx[0..n) -> dense [n, ...] buffer; one 128-thread CTA per row
+__global__ void __launch_bounds__(128)
+oc_gather_term_kernel(const __grid_constant__ OcParams p, const float* __restrict__ term, const int32_t* __restrict__ idx,
+                      int n, float* __restrict__ out_f32, int8_t* __restrict__ out_i8, float* __restrict__ out_ts) {
+    for (int i = blockIdx.x; i < n; i += gridDim.x)
+        gather_term_row(p, term, idx[i], i, out_f32, out_i8, out_ts, (int)threadIdx.x, (int)blockDim.x);
+}
+
 // =============================================================================================
 // host side
 // =============================================================================================
@@ -196,9 +204,10 @@ struct oc_env {
     struct HostPath {
         int32_t* actions = nullptr; float* obs = nullptr; float* rew32 = nullptr; double* rew64 = nullptr;
         uint8_t* done = nullptr; float* term = nullptr; uint8_t* mask = nullptr; int32_t* place = nullptr;
-        float* h_term = nullptr;       // pinned host copy of `term` for steps where many envs finish
         int8_t* obs8 = nullptr; float* ts = nullptr;          // compact format (oc_*_host_i8)
-        int8_t* term8 = nullptr; float* term_ts = nullptr;
+        // terminal rows: indices of the finished envs (host -> device), their rows gathered densely (device -> host)
+        int32_t* idx = nullptr; float* gather = nullptr; float* gather_ts = nullptr;
+        int32_t* h_idx = nullptr; float* h_gather = nullptr; float* h_gather_ts = nullptr;   // pinned
     } hp;
 };
 
@@ -342,9 +351,10 @@ extern "C" int oc_destroy(oc_env* h) {
     if (h->ts) cudaFree(h->ts);
     for (void* q : {(void*)h->hp.actions, (void*)h->hp.obs, (void*)h->hp.rew32, (void*)h->hp.rew64, (void*)h->hp.done,
                     (void*)h->hp.term, (void*)h->hp.mask, (void*)h->hp.place, (void*)h->hp.obs8, (void*)h->hp.ts,
-                    (void*)h->hp.term8, (void*)h->hp.term_ts})
+                    (void*)h->hp.idx, (void*)h->hp.gather, (void*)h->hp.gather_ts})
         if (q) cudaFree(q);
-    if (h->hp.h_term) cudaFreeHost(h->hp.h_term);
+    for (void* q : {(void*)h->hp.h_idx, (void*)h->hp.h_gather, (void*)h->hp.h_gather_ts})
+        if (q) cudaFreeHost(q);
     delete h;
     return OC_OK;
 }
@@ -508,6 +518,14 @@ static int ensure_dev(T*& ptr, size_t count) {
     return OC_OK;
 }
 
+template <typename T>
+static int ensure_host(T*& ptr, size_t count) {
+    if (ptr) return OC_OK;
+    cudaError_t ce = cudaHostAlloc((void**)&ptr, count * sizeof(T), cudaHostAllocDefault);
+    if (ce != cudaSuccess) { ptr = nullptr; return fail(OC_ERR_ALLOC, std::string("cudaHostAlloc (host path staging): ") + cudaGetErrorString(ce)); }
+    return OC_OK;
+}
+
 // device-side repack of float rows into the compact integer format (also usable on its own)
 extern "C" int oc_pack_obs_i8(oc_env* h, const float* obs, int8_t* obs_i8, float* timestep, void* stream) {
     if (!h || !obs || !obs_i8) return fail(OC_ERR_INVALID, "null argument");
@@ -574,7 +592,6 @@ static int step_host_impl(oc_env* h, const int32_t* actions, void* obs, float* t
         if ((rc = ensure_dev(h->hp.term, E * row))) return rc;
         CUDA_TRY(cudaMemsetAsync(h->hp.term, 0, E * row * sizeof(float), st));
     }
-    if (want_term && i8 && ((rc = ensure_dev(h->hp.term8, E * row8 + 4)) || (rc = ensure_dev(h->hp.term_ts, E)))) return rc;
     CUDA_TRY(cudaMemcpyAsync(h->hp.actions, actions, E * A * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     if ((rc = oc_step(h, h->hp.actions, h->hp.obs, rew_f32 ? h->hp.rew32 : nullptr, rew_f64 ? h->hp.rew64 : nullptr,
                       h->hp.done, want_term ? h->hp.term : nullptr, flags, stream))) return rc;
@@ -590,35 +607,39 @@ static int step_host_impl(oc_env* h, const int32_t* actions, void* obs, float* t
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     if (want_term) {                                   // only the rows of envs that just finished reach the caller's buffer
-        size_t nfin = 0;
-        for (size_t e = 0; e < E; ++e) nfin += done[e] != 0;
+        if ((rc = ensure_host(h->hp.h_idx, E))) return rc;
+        size_t nfin = 0, e = 0;
+        for (; e + 8 <= E; e += 8) {                   // finished envs are rare: skip eight clear flags at a time
+            uint64_t w8;
+            memcpy(&w8, done + e, 8);
+            if (w8 == 0) continue;
+            for (size_t k = e; k < e + 8; ++k)
+                if (done[k]) h->hp.h_idx[nfin++] = (int32_t)k;
+        }
+        for (; e < E; ++e)
+            if (done[e]) h->hp.h_idx[nfin++] = (int32_t)e;
         if (nfin == 0) return OC_OK;
-        if (i8 && (rc = oc_pack_obs_i8(h, h->hp.term, h->hp.term8, h->hp.term_ts, stream))) return rc;
-        const uint8_t* src = i8 ? (const uint8_t*)h->hp.term8 : (const uint8_t*)h->hp.term;
-        uint8_t* dst = (uint8_t*)term_obs;
+        // gather them on the device into a dense [nfin, row] buffer (the compact format is packed on the way), one
+        // copy to pinned host memory, then row-wise into the caller's (possibly pageable) buffer.  The staging
+        // buffers are sized for the worst case: lock-step envs all hit the time limit in the same step.
+        if ((rc = ensure_dev(h->hp.idx, E)) || (rc = ensure_dev(h->hp.gather, E * row)) || (rc = ensure_host(h->hp.h_gather, E * row))) return rc;
+        if (i8 && ((rc = ensure_dev(h->hp.gather_ts, E)) || (rc = ensure_host(h->hp.h_gather_ts, E)))) return rc;
         const size_t rb = i8 ? row8 : row * sizeof(float);                // bytes of one env's rows
-        if (nfin <= 64) {
-            for (size_t e = 0; e < E; ++e)
-                if (done[e]) {
-                    CUDA_TRY(cudaMemcpyAsync(dst + e * rb, src + e * rb, rb, cudaMemcpyDeviceToHost, st));
-                    if (i8 && term_ts) CUDA_TRY(cudaMemcpyAsync(term_ts + e, h->hp.term_ts + e, sizeof(float), cudaMemcpyDeviceToHost, st));
-                }
-            CUDA_TRY(cudaStreamSynchronize(st));
-        } else {
-            if (!h->hp.h_term) {                       // sized for the float format; the compact one fits inside (+ clocks)
-                cudaError_t ce = cudaHostAlloc((void**)&h->hp.h_term, E * row * sizeof(float) + E * sizeof(float), cudaHostAllocDefault);
-                if (ce != cudaSuccess) { h->hp.h_term = nullptr; return fail(OC_ERR_ALLOC, std::string("cudaHostAlloc: ") + cudaGetErrorString(ce)); }
-            }
-            uint8_t* hb = (uint8_t*)h->hp.h_term;
-            float* hts = (float*)(hb + E * row * sizeof(float));
-            CUDA_TRY(cudaMemcpyAsync(hb, src, E * rb, cudaMemcpyDeviceToHost, st));
-            if (i8 && term_ts) CUDA_TRY(cudaMemcpyAsync(hts, h->hp.term_ts, E * sizeof(float), cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
-            for (size_t e = 0; e < E; ++e)
-                if (done[e]) {
-                    memcpy(dst + e * rb, hb + e * rb, rb);
-                    if (i8 && term_ts) term_ts[e] = hts[e];
-                }
+        CUDA_TRY(cudaMemcpyAsync(h->hp.idx, h->hp.h_idx, nfin * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        const int grid = (int)std::min<size_t>(nfin, 148 * 16);
+        oc_gather_term_kernel<<<grid, 128, 0, st>>>(p, h->hp.term, h->hp.idx, (int)nfin, i8 ? nullptr : h->hp.gather,
+                                                    i8 ? (int8_t*)h->hp.gather : nullptr, h->hp.gather_ts);
+        CUDA_TRY(cudaGetLastError());
+        h->launches += 1;
+        CUDA_TRY(cudaMemcpyAsync(h->hp.h_gather, h->hp.gather, nfin * rb, cudaMemcpyDeviceToHost, st));
+        if (i8) CUDA_TRY(cudaMemcpyAsync(h->hp.h_gather_ts, h->hp.gather_ts, nfin * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        const uint8_t* hb = (const uint8_t*)h->hp.h_gather;
+        uint8_t* dst = (uint8_t*)term_obs;
+        for (size_t i = 0; i < nfin; ++i) {
+            const size_t e = (size_t)h->hp.h_idx[i];
+            memcpy(dst + e * rb, hb + i * rb, rb);
+            if (i8 && term_ts) term_ts[e] = h->hp.h_gather_ts[i];
         }
     }
     return OC_OK;

@@ -187,6 +187,11 @@ int emu_pack_obs_i8(emu_env* h, const float* obs, int8_t* obs_i8, float* timeste
     for (uint32_t w = 0; w < nwords; ++w) pack_i8_word(p, obs, obs_i8, timestep, w);
     return OC_OK;
 }
+int emu_gather_term(emu_env* h, const float* term, const int32_t* idx, int n, float* out_f32, int8_t* out_i8, float* out_ts) {
+    for (int i = 0; i < n; ++i)                       // oc_gather_term_kernel: one 128-thread CTA per finished env
+        for (int tid = 0; tid < 128; ++tid) gather_term_row(h->p, term, idx[i], i, out_f32, out_i8, out_ts, tid, 128);
+    return OC_OK;
+}
 int emu_get_stats(emu_env* h, uint32_t* episodes, uint32_t* last_completed, void*) {
     for (int i = 0; i < h->p.E; ++i) {
         if (episodes) episodes[i] = h->state[i].y;

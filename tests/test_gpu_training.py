@@ -75,6 +75,19 @@ def test_short_training_run_improves_return():
     assert hist[-1]["ep_rew_mean"] > hist[0]["ep_rew_mean"], (hist[0]["ep_rew_mean"], hist[-1]["ep_rew_mean"])
 
 
+def test_recurrent_learner_runs_off_the_gpu_env():
+    """The LSTM learner (the reference's RecurrentPPO, trainer.py:92-121) for ego and partner on the GPU env:
+    a few iterations plus the deterministic evaluation, finite losses, episodes counted."""
+    import train_ppo
+    hist = train_ppo.main(["--envs", "1024", "--n-steps", "32", "--iters", "6", "--log-every", "3", "--batch-size", "8192",
+                           "--max-num-timesteps", "60", "--recurrent", "--lstm-hidden", "64", "--eval-steps", "61",
+                           "--device", DEV])
+    assert len(hist) == 3 and hist[-1]["eval"] and hist[-1]["episodes"] >= 1024
+    for h in hist[:2]:
+        assert all(np.isfinite(v) for v in h["ego_loss"].values())
+        assert h["episodes"] > 0 and h["partner_updates"] >= 1
+
+
 def test_sb3_vecenv_adapter():
     from gym_comm_b200.pantheon import SB3VecEnvAdapter
     E, T = 16, 12

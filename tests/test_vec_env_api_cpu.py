@@ -149,3 +149,28 @@ def test_pack_obs_i8_is_the_float_row_without_the_clock(E, C):
         assert torch.equal(ts, obs[:, 0, -1]) and torch.equal(ts, obs[:, 1, -1])
     assert i8.min() < 0                                                           # signed deltas survive
     env.close()
+
+
+def test_terminal_row_gather_on_the_emulation():
+    """The device function behind the host path's terminal observations (oc_gather_term_kernel): rows of the
+    finished envs land densely, in index order, as float rows or in the compact format."""
+    import ctypes as C
+    E, Cn = 37, 5
+    ns = argparse.Namespace(level="open-divider_tomato", num_agents=2, max_num_timesteps=9, communication_on=True,
+                            num_communication=Cn, ego_led=False, fow_radius=2, ego_config=D, partner_config=D)
+    env = OvercookedVecEnv(ns, num_envs=E, device="cpu", lib=emu_library(), auto_reset=True)
+    F = env.obs_width
+    rng = np.random.default_rng(0)
+    term = np.ascontiguousarray(rng.integers(-9, 10, (E, 2, F)).astype(np.float32))
+    term[..., -1] = rng.random((E, 1)).astype(np.float32)
+    idx = np.array([0, 3, 4, 17, 36], np.int32)
+    f = emu_library().lib.emu_gather_term
+    f.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3
+    out = np.full((len(idx) + 1, 2, F), 7, np.float32)
+    f(env._handle, term.ctypes.data, idx.ctypes.data, len(idx), out.ctypes.data, None, None)
+    assert np.array_equal(out[:-1], term[idx]) and np.all(out[-1] == 7)
+    o8, ts = np.full((len(idx) + 1, 2, F - 1), 7, np.int8), np.zeros(len(idx), np.float32)
+    f(env._handle, term.ctypes.data, idx.ctypes.data, len(idx), None, o8.ctypes.data, ts.ctypes.data)
+    assert np.array_equal(o8[:-1], term[idx][..., :-1].astype(np.int8)) and np.all(o8[-1] == 7)
+    assert np.array_equal(ts, term[idx][:, 0, -1])
+    env.close()
