@@ -104,3 +104,83 @@ def replay_golden(meta, g, lib, device, num_envs=3):
             ep += 1
             check_obs(env.reset(placements=placements(ep)), g["reset_obs"][ep], ("reset", ep))
     env.close()
+
+
+class EmuHostLibrary:
+    """TEST ONLY.  Stands where `liboc_b200.so` stands for `OvercookedHostVecEnv`, so that the Python side of
+    the host-buffer path (buffers, formats, infos, terminal observations) can run in the GPU-less container:
+    the host-buffer entry points are re-expressed over the CPU emulation of the device functions
+    (emu_step, emu_pack_obs_i8, emu_gather_term -- the same sequence oc_step_host_i8 issues).  The real entry
+    points are covered on the GPU by tests/test_gpu_host_env.py and tests/cabi_smoke.c."""
+    prefix = "oc_"          # what OvercookedHostVecEnv checks for
+
+    def __init__(self):
+        import ctypes as C
+        self.C = C
+        self.emu = emu_library()
+        self.create, self.destroy = self.emu.create, self.emu.destroy
+        self.obs_width, self.obs_layout = self.emu.obs_width, self.emu.obs_layout
+        self._gather = self.emu.lib.emu_gather_term
+        self._gather.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3
+        self._bufs, self._dims = {}, {}
+
+    def check(self, rc, what):
+        assert rc == 0, (what, rc)
+
+    def set_device(self, index):
+        return 0
+
+    def host_alloc(self, n, ref):
+        buf = (self.C.c_uint8 * max(int(n), 1))()
+        addr = self.C.addressof(buf)
+        self._bufs[addr] = buf
+        ref._obj.value = addr
+        return 0
+
+    def host_free(self, ptr):
+        self._bufs.pop(ptr.value, None)
+        return 0
+
+    def _shape(self, h, E_bytes_hint=None):
+        return self._dims[h.value]
+
+    def bind(self, env):
+        """Remember (E, A, F) of a handle (the C library knows them from oc_config)."""
+        self._dims[env._handle.value] = (env.num_envs, env.num_agents, env.obs_width)
+
+    @staticmethod
+    def _a(ptr, shape, dtype):
+        import ctypes as C
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        return np.frombuffer((C.c_uint8 * n).from_address(ptr.value), dtype=dtype).reshape(shape)
+
+    def reset_host(self, h, mask, placements, obs, stream):
+        return self.emu.reset(h, mask, placements, obs, None)
+
+    def step_host(self, h, actions, obs, rew, rew64, done, term, flags, stream):
+        return self.emu.step(h, actions, obs, rew, rew64, done, term, flags, None)
+
+    def reset_host_i8(self, h, mask, placements, obs8, ts, stream):
+        E, A, F = self._dims[h.value]
+        f = np.zeros((E, A, F), np.float32)
+        rc = self.emu.reset(h, mask, placements, self.C.c_void_p(f.ctypes.data), None)
+        return rc or self.emu.pack_obs_i8(h, self.C.c_void_p(f.ctypes.data), obs8, ts, None)
+
+    def step_host_i8(self, h, actions, obs8, ts, rew, rew64, done, term8, term_ts, flags, stream):
+        C = self.C
+        E, A, F = self._dims[h.value]
+        f = np.zeros((E, A, F), np.float32)
+        t = np.zeros((E, A, F), np.float32)
+        rc = self.emu.step(h, actions, C.c_void_p(f.ctypes.data), rew, rew64, done,
+                           C.c_void_p(t.ctypes.data) if term8 is not None else None, flags, None)
+        rc = rc or self.emu.pack_obs_i8(h, C.c_void_p(f.ctypes.data), obs8, ts, None)
+        if rc or term8 is None:
+            return rc
+        idx = np.flatnonzero(self._a(done, (E,), np.uint8)).astype(np.int32)
+        if idx.size:
+            g8, gts = np.zeros((idx.size, A, F - 1), np.int8), np.zeros(idx.size, np.float32)
+            self._gather(h, t.ctypes.data, idx.ctypes.data, idx.size, None, g8.ctypes.data, gts.ctypes.data)
+            self._a(term8, (E, A, F - 1), np.int8)[idx] = g8
+            if term_ts is not None:
+                self._a(term_ts, (E,), np.float32)[idx] = gts
+        return 0
