@@ -55,6 +55,24 @@ class BatchedOnPolicyAgent:
         self.model.buffer.add_reward(reward)
 
 
+class BatchedStaticPolicyAgent:
+    """`StaticPolicyAgent` (pantheonrl/common/agents.py:55-80) over E envs: acts from a fixed policy, never
+    learns.  Like the reference it SAMPLES from the policy (`action_from_policy` calls `policy.forward`);
+    `deterministic=True` takes the argmax instead.  `update` only tracks episode starts, which a recurrent
+    policy needs to reset its LSTM state."""
+
+    def __init__(self, model, deterministic: bool = False):
+        self.model = model
+        self.deterministic = bool(deterministic)
+        self._starts = torch.ones(model.buffer.num_envs, device=model.device)
+
+    def get_action(self, obs: torch.Tensor, record: bool = True) -> torch.Tensor:
+        return self.model.act(obs, self._starts, deterministic=self.deterministic)[0]
+
+    def update(self, reward: torch.Tensor, done: torch.Tensor) -> None:
+        self._starts = done.to(torch.float32)
+
+
 class PantheonVecEnv:
     """Ego-centric batched env: `reset() -> ego_obs [E, F]`, `step(ego_actions [E, 2]) ->
     (ego_obs, reward [E], done [E] u8)`; the partner acts and learns inside `step`."""
@@ -85,6 +103,7 @@ class PantheonVecEnv:
         self.finished_return_sum = torch.zeros((), device=self.device)
         self.finished_length_sum = torch.zeros((), device=self.device)
         self.finished_success = torch.zeros((), device=self.device)
+        self.finished_return_sq = torch.zeros((), device=self.device, dtype=torch.float64)
 
     def add_partner_agent(self, agent: BatchedOnPolicyAgent):
         self.partner = agent
@@ -114,6 +133,7 @@ class PantheonVecEnv:
         self.finished_episodes += d.sum()
         self.finished_return_sum += (self.ep_return * d).sum()
         self.finished_length_sum += (self.ep_length * d).sum()
+        self.finished_return_sq += (self.ep_return.double() ** 2 * d).sum()
         self.finished_success += (d & (self.ep_length < T)).sum()             # ended by delivery, not by the clock
         self.ep_return = torch.where(d, torch.zeros_like(self.ep_return), self.ep_return)
         self.ep_length = torch.where(d, torch.zeros_like(self.ep_length), self.ep_length)
@@ -122,11 +142,14 @@ class PantheonVecEnv:
     def pop_episode_stats(self):
         """Host read (one sync) of the episode statistics accumulated since the last call."""
         n = float(self.finished_episodes.item())
+        mean = float(self.finished_return_sum.item()) / max(n, 1.0)
         out = dict(episodes=n,
-                   ep_rew_mean=float(self.finished_return_sum.item()) / max(n, 1.0),
+                   ep_rew_mean=mean,
+                   ep_rew_std=max(float(self.finished_return_sq.item()) / max(n, 1.0) - mean * mean, 0.0) ** 0.5,
                    ep_len_mean=float(self.finished_length_sum.item()) / max(n, 1.0),
                    delivered_frac=float(self.finished_success.item()) / max(n, 1.0))
-        for t in (self.finished_episodes, self.finished_return_sum, self.finished_length_sum, self.finished_success):
+        for t in (self.finished_episodes, self.finished_return_sum, self.finished_length_sum, self.finished_success,
+                  self.finished_return_sq):
             t.zero_()
         return out
 

@@ -318,3 +318,28 @@ class RecurrentPPO:
         self.n_updates += 1
         k = max(stats.pop("n"), 1)
         return {a: v / k for a, v in stats.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+# Saving / loading a learner's policy -- the counterpart of `ego.save(path)` / `PPO.load(path)`
+# (trainer.py:129-133, tester.py:64-70).  One file per agent, self-describing (kind + sizes).
+# ------------------------------------------------------------------------------------------------
+def save_learner(learner, path: str) -> None:
+    pol = learner.policy
+    recurrent = isinstance(pol, RecurrentActorCritic)
+    first = pol.lstm_pi.weight_ih if recurrent else pol.pi[0].weight
+    meta = dict(kind="lstm" if recurrent else "mlp", obs_dim=int(first.shape[1]), num_nav=int(pol.num_nav),
+                num_comm=int(pol.num_comm), lstm_hidden=int(pol.lstm_hidden) if recurrent else 0)
+    torch.save({"meta": meta, "policy": pol.state_dict()}, path)
+
+
+def load_learner(path: str, num_envs: int, device, cfg: PPOConfig = None):
+    """-> PPO or RecurrentPPO for `num_envs` envs with the saved weights (optimizer state is not kept)."""
+    blob = torch.load(path, map_location=device, weights_only=True)
+    m = blob["meta"]
+    if m["kind"] == "lstm":
+        learner = RecurrentPPO(m["obs_dim"], m["num_nav"], m["num_comm"], num_envs, device, cfg, lstm_hidden=m["lstm_hidden"])
+    else:
+        learner = PPO(m["obs_dim"], m["num_nav"], m["num_comm"], num_envs, device, cfg)
+    learner.policy.load_state_dict(blob["policy"])
+    return learner

@@ -174,3 +174,57 @@ def test_terminal_row_gather_on_the_emulation():
     assert np.array_equal(o8[:-1], term[idx][..., :-1].astype(np.int8)) and np.all(o8[-1] == 7)
     assert np.array_equal(ts, term[idx][:, 0, -1])
     env.close()
+
+
+@pytest.mark.parametrize("flags", [[], ["--recurrent", "--lstm-hidden", "8"]])
+def test_saved_policies_play_through_test_policy(tmp_path, flags):
+    """train_ppo --save-dir -> test_policy --ego-load / --alt-load (trainer.py:129-133 -> tester.py:64-128) on the
+    emulated env: the loaded learners are the saved ones, the requested number of games is played, and the
+    statistics line is consistent."""
+    import test_policy
+    import train_ppo
+    from gym_comm_b200.ppo import load_learner
+
+    def factory(ns, args):
+        return OvercookedVecEnv(ns, num_envs=args.envs, device="cpu", seed=args.seed, auto_reset=True, lib=emu_library())
+    d = str(tmp_path / "model")
+    train_ppo.main(["--envs", "8", "--n-steps", "5", "--iters", "2", "--log-every", "1", "--batch-size", "20",
+                    "--max-num-timesteps", "6", "--epochs", "1", "--device", "cpu", "--save-dir", d] + flags, env_factory=factory)
+    a, b = load_learner(d + "/ppo_ego.pt", 4, "cpu"), load_learner(d + "/ppo_ego.pt", 4, "cpu")
+    assert type(a).__name__ == ("RecurrentPPO" if flags else "PPO")
+    for x, y in zip(a.policy.state_dict().values(), b.policy.state_dict().values()):
+        assert torch.equal(x, y)
+    out = test_policy.main(["--max-num-timesteps", "6", "--ego-load", d + "/ppo_ego.pt", "--alt-load", d + "/ppo_partner1.pt",
+                            "-t", "20", "--envs", "4", "-d", "cpu"], env_factory=factory)
+    assert out["episodes"] >= 20 and out["env_steps"] % 4 == 0
+    assert out["ep_len_mean"] <= 6 and 0.0 <= out["delivered_frac"] <= 1.0
+    assert np.isfinite(out["average_reward"]) and out["standard_deviation"] >= 0.0
+    with pytest.raises(ValueError):                                         # a policy of another message width is refused
+        test_policy.main(["--max-num-timesteps", "6", "--num-communication", "3", "--ego-load", d + "/ppo_ego.pt",
+                          "--alt-load", d + "/ppo_partner1.pt", "-t", "4", "--envs", "4", "-d", "cpu"], env_factory=factory)
+
+
+def test_episode_statistics_match_a_manual_tally():
+    """pop_episode_stats (count, mean / std of the episode return, mean length) against per-episode sums kept by
+    hand, with a static random partner (`BatchedStaticPolicyAgent`, never learning)."""
+    from gym_comm_b200.pantheon import BatchedStaticPolicyAgent
+    from gym_comm_b200.ppo import PPO, PPOConfig
+    E = 6
+    env = make(E=E, T=7, auto_reset=True)
+    partner = BatchedStaticPolicyAgent(PPO(env.obs_width, 4, 4, E, "cpu", PPOConfig(n_steps=4, batch_size=8), seed=5))
+    penv = PantheonVecEnv(env, partner)
+    gen = torch.Generator().manual_seed(1)
+    penv.reset()
+    run, rets, lens = np.zeros(E), [], []
+    for t in range(30):
+        a = torch.stack([torch.randint(0, 4, (E,), generator=gen), torch.randint(0, 4, (E,), generator=gen)], -1).to(torch.int32)
+        _, r, d = penv.step(a)
+        run += r.numpy()
+        for e in np.flatnonzero(d.numpy()):
+            rets.append(run[e]); lens.append(7); run[e] = 0.0
+    st = penv.pop_episode_stats()
+    assert st["episodes"] == len(rets) == E * 4
+    assert abs(st["ep_rew_mean"] - np.mean(rets)) < 1e-4 and abs(st["ep_rew_std"] - np.std(rets)) < 1e-3
+    assert st["ep_len_mean"] == 7 and penv.pop_episode_stats()["episodes"] == 0
+    assert partner.model.n_updates == 0                                      # a static agent never trains
+    env.close()

@@ -10,6 +10,7 @@ step, no host sync inside a rollout).  Prints one JSON line per log interval.
 """
 import argparse
 import json
+import os
 import sys
 import time
 
@@ -17,7 +18,7 @@ import torch
 
 from gym_comm_b200 import OvercookedVecEnv, create_arglist, namespace_from_dict
 from gym_comm_b200.pantheon import BatchedOnPolicyAgent, PantheonVecEnv, collect_and_train
-from gym_comm_b200.ppo import PPO, PPOConfig, RecurrentPPO
+from gym_comm_b200.ppo import PPO, PPOConfig, RecurrentPPO, save_learner
 
 
 def main(argv=None, env_factory=None):
@@ -43,7 +44,9 @@ def main(argv=None, env_factory=None):
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--device", default="cuda:0")
     ap.add_argument("--eval-steps", type=int, default=0, help="after training: deterministic evaluation for this many steps")
-    ap.add_argument("--save", default=None, help="path to save the two policies (torch.save)")
+    ap.add_argument("--save-dir", default=None,
+                    help="directory for the two policies, `ppo_ego.pt` and `ppo_partner1.pt` (trainer.py:129-133); "
+                         "test_policy.py --ego-load / --alt-load reads them")
     args = ap.parse_args(argv)
 
     if args.json_path:
@@ -109,9 +112,10 @@ def main(argv=None, env_factory=None):
         ev = penv.pop_episode_stats()
         print(json.dumps(dict(eval=True, steps=args.eval_steps, **ev)), flush=True)
         history.append(dict(eval=True, **ev))
-    if args.save:
-        torch.save({"ego": ego.policy.state_dict(), "partner": partner.model.policy.state_dict(),
-                    "config": vars(ns)}, args.save)
+    if args.save_dir:
+        os.makedirs(args.save_dir, exist_ok=True)
+        save_learner(ego, os.path.join(args.save_dir, "ppo_ego.pt"))
+        save_learner(partner.model, os.path.join(args.save_dir, "ppo_partner1.pt"))
     env.close()
     return history
 
