@@ -140,16 +140,19 @@ class PantheonVecEnv:
         return self._obs[:, 0], rew[:, 0] * self.reward_scale, done
 
     def pop_episode_stats(self):
-        """Host read (one sync) of the episode statistics accumulated since the last call."""
-        n = float(self.finished_episodes.item())
-        mean = float(self.finished_return_sum.item()) / max(n, 1.0)
-        out = dict(episodes=n,
-                   ep_rew_mean=mean,
-                   ep_rew_std=max(float(self.finished_return_sq.item()) / max(n, 1.0) - mean * mean, 0.0) ** 0.5,
-                   ep_len_mean=float(self.finished_length_sum.item()) / max(n, 1.0),
-                   delivered_frac=float(self.finished_success.item()) / max(n, 1.0))
-        for t in (self.finished_episodes, self.finished_return_sum, self.finished_length_sum, self.finished_success,
-                  self.finished_return_sq):
+        """Host read (one sync) of the episode statistics accumulated since the last call; summed over the
+        ranks of a data-parallel job (every rank must call it)."""
+        acc = (self.finished_episodes, self.finished_return_sum, self.finished_length_sum, self.finished_success,
+               self.finished_return_sq)
+        v = torch.stack([t.to(torch.float64) for t in acc])
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(v)
+        n, rsum, lsum, succ, rsq = v.tolist()
+        mean = rsum / max(n, 1.0)
+        out = dict(episodes=n, ep_rew_mean=mean, ep_rew_std=max(rsq / max(n, 1.0) - mean * mean, 0.0) ** 0.5,
+                   ep_len_mean=lsum / max(n, 1.0), delivered_frac=succ / max(n, 1.0))
+        for t in acc:
             t.zero_()
         return out
 

@@ -31,6 +31,48 @@ def _mlp(inp: int, hidden: Tuple[int, ...]) -> nn.Sequential:
     return nn.Sequential(*layers)
 
 
+# ---- data-parallel learners ("the only collective in the whole system would be an NCCL all-reduce
+# of PPO gradients").  One process per GPU, each with its own env shard and rollout buffer; the policies are a few
+# hundred KB, so every minibatch ends in ONE all-reduce over a flat gradient buffer.  No-ops without a process group.
+def _world() -> int:
+    import torch.distributed as dist
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+
+def broadcast_parameters(module: nn.Module, src: int = 0) -> None:
+    """Every rank starts from rank `src`'s weights."""
+    if _world() == 1:
+        return
+    import torch.distributed as dist
+    with torch.no_grad():
+        flat = torch.cat([p.reshape(-1) for p in module.parameters()])
+        dist.broadcast(flat, src)
+        o = 0
+        for p in module.parameters():
+            p.copy_(flat[o:o + p.numel()].view_as(p))
+            o += p.numel()
+
+
+def average_gradients(module: nn.Module) -> None:
+    """Mean of the ranks' gradients, in place (call between backward() and the optimizer step)."""
+    w = _world()
+    if w == 1:
+        return
+    import torch.distributed as dist
+    ps = list(module.parameters())
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in ps])
+    dist.all_reduce(flat)
+    flat /= w
+    o = 0
+    for p in ps:
+        g = flat[o:o + p.numel()].view_as(p)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        o += p.numel()
+
+
 class ActorCritic(nn.Module):
     """obs [.., F] -> logits over nav (4) and message (C), value."""
 
@@ -156,6 +198,7 @@ class PPO:
         with torch.random.fork_rng(devices=[]):
             torch.manual_seed(int(torch.randint(0, 2 ** 31 - 1, (1,), generator=gen)))
             self.policy = ActorCritic(obs_dim, num_nav, num_comm).to(self.device)
+        broadcast_parameters(self.policy)
         self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.learning_rate, eps=1e-5)
         self.buffer = RolloutBuffer(self.cfg.n_steps, num_envs, obs_dim, self.device, self.cfg.gamma, self.cfg.gae_lambda)
         self.n_updates = 0
@@ -190,6 +233,7 @@ class PPO:
                 loss = pg + c.vf_coef * vf - c.ent_coef * ent.mean()
                 self.optimizer.zero_grad(set_to_none=True)
                 loss.backward()
+                average_gradients(self.policy)
                 nn.utils.clip_grad_norm_(self.policy.parameters(), c.max_grad_norm)
                 self.optimizer.step()
                 with torch.no_grad():
@@ -203,7 +247,7 @@ class PPO:
 
 
 # ------------------------------------------------------------------------------------------------
-# Recurrent learner: what the reference actually trains (`RecurrentPPO("MultiInputLstmPolicy", ...)`,
+# Recurrent learner: what the reference actually trains (`RecurrentPPO("MultiInputPolicy", ...)`,
 # trainer.py:92-121; sb3_contrib/ppo_recurrent): separate LSTMs for actor and critic in front of the
 # 2 x 64 towers, hidden state reset at episode starts, back-propagation through the whole rollout.
 # ------------------------------------------------------------------------------------------------
@@ -254,6 +298,7 @@ class RecurrentPPO:
         with torch.random.fork_rng(devices=[]):
             torch.manual_seed(int(torch.randint(0, 2 ** 31 - 1, (1,), generator=gen)))
             self.policy = RecurrentActorCritic(obs_dim, num_nav, num_comm, lstm_hidden).to(self.device)
+        broadcast_parameters(self.policy)
         self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.learning_rate, eps=1e-5)
         self.buffer = RolloutBuffer(self.cfg.n_steps, num_envs, obs_dim, self.device, self.cfg.gamma, self.cfg.gae_lambda)
         self.state = self.policy.initial_state(num_envs, self.device)
@@ -308,6 +353,7 @@ class RecurrentPPO:
                 loss = pg + c.vf_coef * vf - c.ent_coef * ent.mean()
                 self.optimizer.zero_grad(set_to_none=True)
                 loss.backward()
+                average_gradients(self.policy)
                 nn.utils.clip_grad_norm_(self.policy.parameters(), c.max_grad_norm)
                 self.optimizer.step()
                 with torch.no_grad():

@@ -3,6 +3,7 @@
 
     python train_ppo.py --json-path cfg.json            # same JSON schema as the reference trainer
     python train_ppo.py                                 # open-divider_tomato, 65 536 envs: delivers 100 % after ~45 s
+    torchrun --nproc-per-node 8 train_ppo.py            # data parallel: --envs per GPU, gradients all-reduced (NCCL)
 
 Ego PPO + partner PPO (the partner records and trains inside `env.step`, like PantheonRL's
 OnPolicyAgent), both on the device; the Overcooked env is `OvercookedVecEnv` (one CUDA launch per
@@ -15,20 +16,23 @@ import sys
 import time
 
 import torch
+import torch.distributed as dist
 
 from gym_comm_b200 import OvercookedVecEnv, create_arglist, namespace_from_dict
 from gym_comm_b200.pantheon import BatchedOnPolicyAgent, PantheonVecEnv, collect_and_train
 from gym_comm_b200.ppo import PPO, PPOConfig, RecurrentPPO, save_learner
+from gym_comm_b200.sharding import rank_world, shard_seed
 
 
-def main(argv=None, env_factory=None):
-    """`env_factory(ns, args)` lets the CPU tests put the emulated env under the same training loop."""
+def main(argv=None, env_factory=None, learners_out=None):
+    """`env_factory(ns, args)` lets the CPU tests put the emulated env under the same training loop;
+    `learners_out` (a list) receives the ego and the partner learner."""
     ap = argparse.ArgumentParser()
     ap.add_argument("--json-path", default=None, help="env config JSON (reference trainer.py --json-path)")
     ap.add_argument("--level", default="open-divider_tomato")
     ap.add_argument("--max-num-timesteps", type=int, default=200)
     ap.add_argument("--num-communication", type=int, default=10)
-    ap.add_argument("--envs", type=int, default=65536)
+    ap.add_argument("--envs", type=int, default=65536, help="envs per process (per GPU under torchrun)")
     ap.add_argument("--n-steps", type=int, default=32)
     ap.add_argument("--iters", type=int, default=60)
     ap.add_argument("--batch-size", type=int, default=65536)
@@ -54,9 +58,20 @@ def main(argv=None, env_factory=None):
     else:
         ns = namespace_from_dict(dict(level=args.level, num_agents=2, max_num_timesteps=args.max_num_timesteps,
                                       communication_on=True, num_communication=args.num_communication))
-    torch.manual_seed(args.seed)
+    # one process per GPU under torchrun: every rank owns `--envs` envs (its own shard seed) and its own rollout
+    # buffers; the learners start from the same weights and average their gradients (ppo.average_gradients)
+    rank, world, local_rank = rank_world()
+    if world > 1:
+        if args.device.startswith("cuda"):
+            args.device = "cuda:%d" % local_rank
+            torch.cuda.set_device(local_rank)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl" if args.device.startswith("cuda") else "gloo")
+    env_seed = shard_seed(args.seed, rank) if world > 1 else args.seed
+    torch.manual_seed(args.seed + rank)                   # action sampling differs per shard
+    args.env_seed = env_seed
     env = env_factory(ns, args) if env_factory is not None else \
-        OvercookedVecEnv(ns, num_envs=args.envs, device=args.device, seed=args.seed, auto_reset=True)
+        OvercookedVecEnv(ns, num_envs=args.envs, device=args.device, seed=env_seed, auto_reset=True)
     h = getattr(ns, "hyperparams", {}) or {}
     cfg = PPOConfig.from_hyperparams(h, n_steps=args.n_steps, batch_size=args.batch_size, n_epochs=args.epochs)
     if "clip_range" not in h:
@@ -83,14 +98,15 @@ def main(argv=None, env_factory=None):
     history = []
     for it in range(1, args.iters + 1):
         obs, starts, stats = collect_and_train(penv, ego, obs, starts)
-        steps += args.n_steps * args.envs
+        steps += args.n_steps * args.envs * world
         if it % args.log_every == 0 or it == args.iters:
             ep = penv.pop_episode_stats()
             dt = time.time() - t0
-            line = dict(iter=it, env_steps=steps, agent_steps_per_s=2 * steps / dt, wall_s=dt, **ep,
+            line = dict(iter=it, env_steps=steps, agent_steps_per_s=2 * steps / dt, wall_s=dt, world=world, **ep,
                         ego_loss=stats, partner_updates=partner.iteration)
             history.append(line)
-            print(json.dumps(line), flush=True)
+            if rank == 0:
+                print(json.dumps(line), flush=True)
     if args.eval_steps > 0:
         # tester.py-style evaluation (tester.py:72-106): deterministic (argmax) actions, no learning
         obs = penv.reset()
@@ -110,12 +126,15 @@ def main(argv=None, env_factory=None):
             obs, _, d = penv.step(ego.act(obs, ego_starts, deterministic=True)[0].to(torch.int32))
             ego_starts = d.to(torch.float32)
         ev = penv.pop_episode_stats()
-        print(json.dumps(dict(eval=True, steps=args.eval_steps, **ev)), flush=True)
+        if rank == 0:
+            print(json.dumps(dict(eval=True, steps=args.eval_steps, **ev)), flush=True)
         history.append(dict(eval=True, **ev))
-    if args.save_dir:
+    if args.save_dir and rank == 0:                        # the ranks' weights are identical
         os.makedirs(args.save_dir, exist_ok=True)
         save_learner(ego, os.path.join(args.save_dir, "ppo_ego.pt"))
         save_learner(partner.model, os.path.join(args.save_dir, "ppo_partner1.pt"))
+    if learners_out is not None:
+        learners_out += [ego, partner.model]
     env.close()
     return history
 
