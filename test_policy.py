@@ -24,14 +24,14 @@ from gym_comm_b200.ppo import load_learner
 
 def main(argv=None, env_factory=None):
     """`env_factory(ns, args)` lets the CPU tests put the emulated env under the same loop."""
-    ap = argparse.ArgumentParser("Overcooked 2 - Tester Argument parser")
+    ap = argparse.ArgumentParser(description="play saved ego / partner policies on the batched GPU env")
     ap.add_argument("--json-path", "-j", default=None, help="env config JSON (tester.py --json-path)")
     ap.add_argument("--level", default="open-divider_tomato", help="used when no --json-path is given")
     ap.add_argument("--max-num-timesteps", type=int, default=200)
     ap.add_argument("--num-communication", type=int, default=10)
-    ap.add_argument("--ego-load", required=True, help="file to load the ego agent from")
-    ap.add_argument("--alt-load", required=True, help="file to load the partner agent from")
-    ap.add_argument("--total-episodes", "-t", type=int, default=100, help="number of episodes to run")
+    ap.add_argument("--ego-load", required=True, help="ego policy file written by train_ppo.py --save-dir (ppo_ego.pt)")
+    ap.add_argument("--alt-load", required=True, help="partner policy file (ppo_partner1.pt)")
+    ap.add_argument("--total-episodes", "-t", type=int, default=100, help="stop after this many finished games")
     ap.add_argument("--envs", type=int, default=0, help="games played at once (default: min(total episodes, 65536))")
     ap.add_argument("--device", "-d", default="cuda:0")
     ap.add_argument("--deterministic", action="store_true")
