@@ -144,14 +144,21 @@ class PantheonVecEnv:
         ranks of a data-parallel job (every rank must call it)."""
         acc = (self.finished_episodes, self.finished_return_sum, self.finished_length_sum, self.finished_success,
                self.finished_return_sq)
-        v = torch.stack([t.to(torch.float64) for t in acc])
+        # what the reference's EpisodeRecorder logs at every reset (episode_recorder.py:29): completed subtasks of the
+        # last finished episode, kept per env on the device (oc_get_stats); here its mean over the envs that have
+        # finished at least one episode
+        st = self.env.stats()
+        has = st["episodes"] > 0
+        v = torch.stack([t.to(torch.float64) for t in acc] +
+                        [(st["num_completed_subtasks"] * has).sum().to(torch.float64), has.sum().to(torch.float64)])
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(v)
-        n, rsum, lsum, succ, rsq = v.tolist()
+        n, rsum, lsum, succ, rsq, csum, cn = v.tolist()
         mean = rsum / max(n, 1.0)
         out = dict(episodes=n, ep_rew_mean=mean, ep_rew_std=max(rsq / max(n, 1.0) - mean * mean, 0.0) ** 0.5,
-                   ep_len_mean=lsum / max(n, 1.0), delivered_frac=succ / max(n, 1.0))
+                   ep_len_mean=lsum / max(n, 1.0), delivered_frac=succ / max(n, 1.0),
+                   num_completed_subtasks=csum / max(cn, 1.0))
         for t in acc:
             t.zero_()
         return out

@@ -225,6 +225,8 @@ def test_episode_statistics_match_a_manual_tally():
     st = penv.pop_episode_stats()
     assert st["episodes"] == len(rets) == E * 4
     assert abs(st["ep_rew_mean"] - np.mean(rets)) < 1e-4 and abs(st["ep_rew_std"] - np.std(rets)) < 1e-3
+    last = env.stats()["num_completed_subtasks"].double().mean().item()       # every env has finished episodes by now
+    assert st["num_completed_subtasks"] == pytest.approx(last) and 0.0 <= last <= 3.0
     assert st["ep_len_mean"] == 7 and penv.pop_episode_stats()["episodes"] == 0
     assert partner.model.n_updates == 0                                      # a static agent never trains
     env.close()
