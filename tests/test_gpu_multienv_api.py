@@ -1,117 +1,21 @@
 """GPU: the reference-shaped single-env surface (`OvercookedMultiEnv.multi_step / multi_reset /
 get_observation2`, gym_comm/envs/overcooked_env.py:105-297) against golden traces of the live
-reference: 11-key dict observations, Python-float reward with the reference's f64 value, done."""
-import numpy as np
+reference (cases in tests/multienv_cases.py), through the CUDA library."""
 import pytest
 
-from gym_comm_b200.vec_env import OvercookedMultiEnv
-from tests.golden_util import load_golden
-from tests.parity_util import namespace_from_meta
+from tests import multienv_cases as cases
 
 pytestmark = pytest.mark.gpu
-KEYS = ["agent1_comm", "agent1_location", "agent2_comm", "agent2_location", "agent_is_holding",
-        "completed_subtasks", "is_hidden", "object_encodings_x", "object_encodings_y", "state_encodings", "timestep"]
 
 
-def _split_golden(meta, flat):
-    C, S = meta["num_communication"], len(meta["subtasks"])
-    sizes = [C, 2, C, 2, 2, S, 4, 4, 4, 4, 1]
-    out, o = {}, 0
-    for k, n in zip(KEYS, sizes):
-        out[k] = flat[o:o + n]
-        o += n
-    return out
-
-
-@pytest.mark.parametrize("name", ["tomato_a9_script", "cramped_allergic", "open_tl"])
+@pytest.mark.parametrize("name", cases.TRACES)
 def test_multi_step_matches_reference_trace(name):
-    meta, g = load_golden(name)
-    env = OvercookedMultiEnv(namespace_from_meta(meta), level_text=meta["level_text"], subtasks=meta["subtasks"])
-    W = len(meta["level_text"].split("\n")[0])
-
-    def placements(ep):
-        pl = g["placements"][ep]
-        return None if pl.shape[0] == 0 else [int(x + y * W) for x, y in pl]
-
-    def check(obs_pair, want_rows):
-        for k in range(2):
-            want = _split_golden(meta, want_rows[k])
-            assert set(obs_pair[k].keys()) == set(KEYS)
-            for key in KEYS:
-                got = np.asarray(obs_pair[k][key], dtype=np.float64)
-                assert np.array_equal(got, want[key]), (name, key, got, want[key])      # timestep too: exact f64
-
-    ep = 0
-    check(env.multi_reset(placements(0)), g["reset_obs"][0])
-    assert env.action_space.nvec.tolist() == [4, meta["num_communication"]]
-    for i in range(min(len(g["navs"]), 300)):
-        a0 = (int(g["navs"][i][0]), int(g["comms"][i][0]))
-        a1 = (int(g["navs"][i][1]), int(g["comms"][i][1]))
-        (o0, o1), (r0, r1), done, info = env.multi_step(a0, a1)
-        assert isinstance(r0, float) and r0 == r1 == g["reward"][i], (i, r0, g["reward"][i])
-        assert done is bool(g["done"][i]) and info == {}
-        check((o0, o1), g["obs"][i])
-        if done:
-            ep += 1
-            check(env.multi_reset(placements(ep)), g["reset_obs"][ep])
-    env.close()
+    cases.run_multi_step_matches_reference_trace(name)
 
 
 def test_known_answer_survey_a7():
-    """SURVEY A.7 known answer: fresh open-divider_tomato, one multi_step, observer 0, radius 2."""
-    import argparse
-    d = dict(CAN_MOVE=True, ALLERGIC=False, BLIND=False)
-    ns = argparse.Namespace(level="open-divider_tomato", num_agents=2, max_num_timesteps=500, communication_on=True,
-                            num_communication=5, ego_led=False, fow_radius=2, ego_config=d, partner_config=d)
-    env = OvercookedMultiEnv(ns)
-    (o0, _), (r, _), done, _ = env.multi_step((3, 2), (0, 4))
-    assert r == -8.206896551724139 and done is False
-    assert o0["object_encodings_x"].tolist() == [2, 3, 0, 2] and o0["object_encodings_y"].tolist() == [-1, 0, 0, 5]
-    assert o0["is_hidden"].tolist() == [1, 1, 0, 1] and o0["state_encodings"].tolist() == [0, 0, 0, 0]
-    assert o0["agent1_location"].tolist() == [3, 1] and o0["agent2_location"].tolist() == [4, 2]
-    assert o0["agent1_comm"].tolist() == [0, 0, 1, 0, 0] and o0["agent2_comm"].tolist() == [0, 0, 0, 0, 1]
-    assert o0["completed_subtasks"].tolist() == [0, 0, 0] and o0["agent_is_holding"].tolist() == [False, False]
-    assert float(o0["timestep"][0]) == 0.002
-    env.close()
+    cases.run_known_answer_survey_a7()
 
 
 def test_multiagentenv_step_reset_with_partner():
-    """`step(action)` / `reset()` with an embedded partner, as trainer.py drives the env
-    (pantheonrl/common/multiagentenv.py:172-243)."""
-    import argparse
-
-    class Partner:
-        def __init__(self):
-            self.seen, self.updates = [], []
-
-        def get_action(self, obs):
-            self.seen.append(obs.obs)
-            return (0, 3)
-
-        def update(self, reward, done):
-            self.updates.append((reward, done))
-
-    d = dict(CAN_MOVE=True, ALLERGIC=False, BLIND=False)
-    ns = argparse.Namespace(level="open-divider_tomato", num_agents=2, max_num_timesteps=5, communication_on=True,
-                            num_communication=5, ego_led=False, fow_radius=2, ego_config=d, partner_config=d)
-    env = OvercookedMultiEnv(ns)
-    twin = OvercookedMultiEnv(ns)
-    p = Partner()
-    env.add_partner_agent(p)
-    ego_obs = env.reset()
-    o_twin = twin.multi_reset()
-    assert all(np.array_equal(ego_obs[k], o_twin[0][k]) for k in KEYS)
-    prev = ego_obs
-    for t in range(5):
-        obs, r, done, info = env.step((3, 1))
-        (t0, t1), (tr, _), tdone, _ = twin.multi_step((3, 1), (0, 3))
-        assert r == tr and done is tdone and info["_partnerid"] == [0]
-        if not done:
-            assert all(np.array_equal(obs[k], t0[k]) for k in KEYS)
-            prev = obs
-        else:
-            assert all(np.array_equal(obs[k], prev[k]) for k in KEYS)     # previous ego obs on done
-    assert done and len(p.seen) == 5
-    assert p.updates[0] == (0.0, False) and len(p.updates) == 6 and p.updates[-1][1] is True
-    env.close()
-    twin.close()
+    cases.run_multiagentenv_step_reset_with_partner()
