@@ -28,6 +28,17 @@ for c in [dict(level="random-open-divider_salad_small_cramped", num_agents=2, ma
             env.step(a, term_obs_out=term, want_f64=True)
         obs = torch.zeros((8, E, A, F)); rew = torch.zeros((8, E, A)); done = torch.zeros((8, E), dtype=torch.uint8); acts = torch.zeros((8,E,A,2), dtype=torch.int32)
         env.rollout(8, obs_out=obs, rew_out=rew, done_out=done, actions_out=acts)
+        # compact format + terminal-row gather: exactly-sized buffers so that any overrun trips ASan
+        i8, ts = env.pack_obs_i8(obs[-1].contiguous())
+        assert torch.equal(i8.float(), obs[-1][..., :-1])
+        import ctypes as C
+        idx = np.arange(0, E, 2, dtype=np.int32)
+        g32 = np.zeros((len(idx), A, F), np.float32); g8 = np.zeros((len(idx), A, F - 1), np.int8); gts = np.zeros(len(idx), np.float32)
+        gt = lib.lib.emu_gather_term
+        gt.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3
+        gt(env._handle, term.data_ptr(), idx.ctypes.data, len(idx), g32.ctypes.data, None, None)
+        gt(env._handle, term.data_ptr(), idx.ctypes.data, len(idx), None, g8.ctypes.data, gts.ctypes.data)
+        assert np.array_equal(g32, term.numpy()[idx]) and np.array_equal(g8, term.numpy()[idx][..., :-1].astype(np.int8))
         env.reset(mask=done[-1].contiguous()); env.set_state(env.get_state()); env.close()
     print(c['level'], 'ok', flush=True)
 print('ASAN RUN CLEAN')
