@@ -21,9 +21,17 @@ using namespace ock;
 // kernels
 // =============================================================================================
 
+// A/B knob (compile time): -DOC_STEP_MIN_CTAS=n adds a minimum-CTAs-per-SM hint to the step kernel, i.e. a register
+// cap of 65536 / (256 n); unset = ptxas' own choice (see profiles/r1_ptxas_sass.txt for what it picks)
+#ifdef OC_STEP_MIN_CTAS
+#define OC_STEP_BOUNDS __launch_bounds__(256, OC_STEP_MIN_CTAS)
+#else
+#define OC_STEP_BOUNDS __launch_bounds__(256)
+#endif
+
 // dynamic shared memory: [table blob][per warp: nb env rows (float or biased-byte format)]
 template <int A, int NOBJ, int NF, int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void OC_STEP_BOUNDS
 oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
                const int32_t* __restrict__ actions, float* __restrict__ obs,
                float* __restrict__ rew32, double* __restrict__ rew64, uint8_t* __restrict__ done_out,
