@@ -116,9 +116,11 @@ _default = None
 
 
 def default_library() -> OcLibrary:
+    """The in-tree CUDA library.  `OC_B200_LIB=<path>` loads another BUILD of the same sources instead (A/B of
+    compile-time knobs such as -DOC_STEP_MIN_CTAS, tools/ab_step_bounds.sh); it is still the CUDA library."""
     global _default
     if _default is None:
-        _default = OcLibrary()
+        _default = OcLibrary(os.environ.get("OC_B200_LIB") or DEFAULT_LIB)
     return _default
 
 
