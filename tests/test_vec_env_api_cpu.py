@@ -121,7 +121,7 @@ def test_train_ppo_main_loop_on_the_emulated_env(flags):
 
     def factory(ns, args):
         return OvercookedVecEnv(ns, num_envs=args.envs, device="cpu", seed=args.seed, auto_reset=True, lib=emu_library())
-    hist = train_ppo.main(["--envs", "8", "--n-steps", "5", "--iters", "3", "--log-every", "1", "--batch-size", "20",
+    hist = train_ppo.main(["--envs", "8", "--n-steps", "5", "--total-timesteps", "81", "--log-every", "1", "--batch-size", "20",
                            "--max-num-timesteps", "4", "--epochs", "1", "--eval-steps", "9", "--device", "cpu"] + flags,
                           env_factory=factory)
     assert len(hist) == 4 and hist[-1]["eval"] and hist[-1]["episodes"] == 8 * 2

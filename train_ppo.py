@@ -35,6 +35,9 @@ def main(argv=None, env_factory=None, learners_out=None):
     ap.add_argument("--envs", type=int, default=65536, help="envs per process (per GPU under torchrun)")
     ap.add_argument("--n-steps", type=int, default=32)
     ap.add_argument("--iters", type=int, default=60)
+    ap.add_argument("--total-timesteps", type=int, default=0,
+                    help="train for this many ego env-steps summed over all envs (SB3's `learn(total_timesteps)`, "
+                         "trainer.py:121) instead of --iters; the JSON's own total_timesteps is not applied automatically")
     ap.add_argument("--batch-size", type=int, default=65536)
     ap.add_argument("--epochs", type=int, default=4)
     ap.add_argument("--clip-range", type=float, default=0.2)
@@ -91,6 +94,9 @@ def main(argv=None, env_factory=None, learners_out=None):
     partner = BatchedOnPolicyAgent(make_learner(args.seed + 1))
     penv = PantheonVecEnv(env, partner, reward_scale=args.reward_scale)
 
+    if args.total_timesteps > 0:                            # whole rollouts, like OnPolicyAlgorithm.learn
+        per_iter = args.n_steps * args.envs * world
+        args.iters = max(1, -(-args.total_timesteps // per_iter))
     obs = penv.reset()
     starts = torch.ones(args.envs, device=env.device)
     t0 = time.time()
