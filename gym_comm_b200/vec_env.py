@@ -354,6 +354,47 @@ class OvercookedMultiEnv:
     def getDummyEnv(self, player_num: int):
         return self
 
+    # partner selection (multiagentenv.py:103-147); one partner slot, as in every 2-player PantheonRL env
+    def set_partnerid(self, agent_id: int, player_num: int = 1) -> None:
+        if player_num != 1:
+            raise ValueError("Ego agent is not set by the environment")
+        partners = self.__dict__.get("partners", [])
+        assert 0 <= agent_id < len(partners)
+        self.partnerid = int(agent_id)
+
+    def resample_random(self) -> None:
+        self.partnerid = int(np.random.randint(len(self.partners)))
+
+    def resample_round_robin(self) -> None:
+        self.partnerid = (self.partnerid + 1) % len(self.partners)
+
+    def set_resample_policy(self, resample_policy: str) -> None:
+        """"default" / "robin" (round robin, the 2-player default) or "random"."""
+        if resample_policy in ("default", "robin"):
+            self.resample_partner = self.resample_round_robin
+        elif resample_policy == "random":
+            self.resample_partner = self.resample_random
+        else:
+            raise ValueError("Invalid resampling policy: %s" % resample_policy)      # PlayerException (:145-147)
+
+    # SimultaneousEnv.n_step / n_reset (multiagentenv.py:395-409): both players move on every step
+    def n_step(self, actions):
+        (obs0, obs1), r, d, i = self.multi_step(actions[0], actions[1])
+        return (0, 1), (self.Observation(obs0), self.Observation(obs1)), r, d, i
+
+    def n_reset(self):
+        obs0, obs1 = self.multi_reset()
+        return (0, 1), (self.Observation(obs0), self.Observation(obs1))
+
+    def cost_fn(self):
+        return 1                                                                      # overcooked_env.py:204-205
+
+    def render(self, mode="human", close=False):
+        """Prints the board like `print(str(self.base_env))` (overcooked_env.py:299-300; the reference then calls a
+        `get_observation` that does not exist and raises) followed by the ego observation."""
+        print(self.vec.render(0))
+        print(self.get_observation2(self.ego_agent_idx))
+
     def set_ego_extractor(self, ego_extractor) -> None:
         self.ego_extractor = ego_extractor
 
@@ -361,7 +402,7 @@ class OvercookedMultiEnv:
         """MultiAgentEnv.reset (:217-243): round-robin partner resampling, first ego observation."""
         partners = self.__dict__.get("partners", [])
         if partners:
-            self.partnerid = (self.partnerid + 1) % len(partners)                # resample_round_robin (:124-131)
+            self.__dict__.get("resample_partner", self.resample_round_robin)()   # (:228-229), round robin by default
         self._obs = self.multi_reset(placements)
         self._should_update, self._total_rews = False, [0.0, 0.0]
         self._old_ego_obs = self._obs[0]

@@ -117,3 +117,60 @@ def run_multiagentenv_step_reset_with_partner(**envkw):
     assert p.updates[0] == (0.0, False) and len(p.updates) == 6 and p.updates[-1][1] is True
     env.close()
     twin.close()
+
+
+def run_partner_selection_and_n_step(**envkw):
+    """set_partnerid / resample policies (multiagentenv.py:103-147), n_step / n_reset (:395-409), cost_fn, render."""
+    import argparse
+    import contextlib
+    import io
+
+    class Const:
+        def __init__(self, a):
+            self.a, self.calls = a, 0
+
+        def get_action(self, obs):
+            self.calls += 1
+            return self.a
+
+        def update(self, reward, done):
+            pass
+
+    d = dict(CAN_MOVE=True, ALLERGIC=False, BLIND=False)
+    ns = argparse.Namespace(level="open-divider_tomato", num_agents=2, max_num_timesteps=3, communication_on=True,
+                            num_communication=5, ego_led=False, fow_radius=2, ego_config=d, partner_config=d)
+    env = OvercookedMultiEnv(ns, **envkw)
+    a, b, c = Const((0, 1)), Const((1, 2)), Const((2, 3))
+    for p in (a, b, c):
+        env.add_partner_agent(p)
+    env.reset()                                            # round robin: 0 -> 1
+    _, _, _, info = env.step((3, 0))
+    assert info["_partnerid"] == [1] and (a.calls, b.calls, c.calls) == (0, 1, 0)
+    env.set_partnerid(2)
+    assert env.step((3, 0))[3]["_partnerid"] == [2] and c.calls == 1
+    env.reset()                                            # 2 -> 0
+    assert env.step((3, 0))[3]["_partnerid"] == [0]
+    env.set_resample_policy("random")
+    np.random.seed(0)
+    seen = set()
+    for _ in range(12):
+        env.reset()
+        seen.add(env.partnerid)
+    assert seen == {0, 1, 2}
+    env.set_resample_policy("default")
+    try:
+        env.set_resample_policy("nope")
+        raise AssertionError("invalid policy accepted")
+    except ValueError:
+        pass
+    who, obs = env.n_reset()
+    assert who == (0, 1) and float(obs[0].obs["timestep"][0]) == 0.0 and obs[1].action_mask is None
+    who, obs, rews, done, info = env.n_step([(3, 0), (0, 1)])
+    assert who == (0, 1) and rews[0] == rews[1] and done is False and info == {}
+    assert obs[0].obs["agent1_location"].tolist() == [3, 1] and obs[1].obs["agent2_comm"].tolist() == [0, 1, 0, 0, 0]
+    assert env.cost_fn() == 1
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out):
+        env.render()
+    assert "agent1_location" in out.getvalue() and len(out.getvalue().splitlines()) >= 7
+    env.close()

@@ -22,3 +22,7 @@ def test_known_answer_survey_a7():
 
 def test_multiagentenv_step_reset_with_partner():
     cases.run_multiagentenv_step_reset_with_partner(**_kw())
+
+
+def test_partner_selection_and_n_step():
+    cases.run_partner_selection_and_n_step(**_kw())
