@@ -418,6 +418,9 @@ def main():
         return {"value": float(E) * A * Ke * world / float(tm.item()), "unit": "agent-steps/s",
                 "h2d_bytes_per_step": E * A * 2 * 4, "d2h_bytes_per_step": obs_bytes + E * A * 4 + E,
                 "steps": Ke, "obs_format": ("int8 [E,A,F-1] + f32 clock [E]" if fmt == "i8" else "f32 [E,A,F]"),
+                "lossless": True,       # i8: the integer keys as the integers the reference's get_observation2 builds
+                                        # (int64 arrays), the clock still f32 -- value-identical to the float rows
+                                        # (tests/test_gpu_host_env.py, tests/cabi_smoke.c); nothing is quantised
                 "api": "OvercookedHostVecEnv(obs_format=%r).step = C ABI %s, pinned numpy buffers, synchronised every step" % (fmt, entry),
                 "gpu_launches_per_step": (2 if fmt == "i8" else 1) + (1 if term else 0),
                 "terminal_observations": bool(term), "finished_envs_per_step": (nfin / Ke if term else None),
