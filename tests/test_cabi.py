@@ -77,3 +77,22 @@ def test_emulation_backend_is_refused_outside_tests(monkeypatch):
     ns = argparse.Namespace(level="open-divider_tomato", num_agents=2, max_num_timesteps=100)
     with pytest.raises(RuntimeError):
         OvercookedVecEnv(ns, num_envs=4, device="cpu", lib=emu)
+
+
+def test_header_is_plain_c_and_cxx(tmp_path):
+    """include/overcooked_b200.h stands alone: C99 and C++17 translation units that include nothing else compile, and
+    a C program can name every entry point with the documented signature (pointer types, no torch / CUDA headers)."""
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    c = tmp_path / "t.c"
+    c.write_text('#include "overcooked_b200.h"\n'
+                 "int use(oc_env* e, const int32_t* a, int8_t* o8, float* ts, float* r, uint8_t* d, void* s) {\n"
+                 "    oc_config cfg; (void)cfg;\n"
+                 "    int (*step)(oc_env*, const int32_t*, float*, float*, double*, uint8_t*, float*, uint32_t, void*) = oc_step; (void)step;\n"
+                 "    int (*pack)(oc_env*, const float*, int8_t*, float*, void*) = oc_pack_obs_i8; (void)pack;\n"
+                 "    return oc_step_host_i8(e, a, o8, ts, r, 0, d, 0, 0, OC_FLAG_AUTO_RESET, s) + oc_reset_host_i8(e, 0, 0, o8, ts, s);\n"
+                 "}\n")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I" + inc, "-c", str(c), "-o", str(tmp_path / "t.o")])
+    cxx = tmp_path / "t.cpp"
+    cxx.write_text('#include "overcooked_b200.h"\nint v() { return OC_ABI_VERSION + (int)sizeof(oc_config); }\n')
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-I" + inc, "-c", str(cxx), "-o", str(tmp_path / "t2.o")])
