@@ -4,7 +4,7 @@
 episode's total reward, then the average and the standard deviation).
 
     python train_ppo.py --save-dir model/tomato
-    python test_policy.py -j env_args.json --ego-load model/tomato/ppo_ego.pt --alt-load model/tomato/ppo_partner1.pt -t 10000
+    python evaluate_policy.py -j env_args.json --ego-load model/tomato/ppo_ego.pt --alt-load model/tomato/ppo_partner1.pt -t 10000
 
 The games run `--envs` at a time on the device (`OvercookedVecEnv` + `PantheonVecEnv` with a
 `BatchedStaticPolicyAgent` partner).  Like the reference's `StaticPolicyAgent` both agents sample from their

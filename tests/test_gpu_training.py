@@ -88,14 +88,14 @@ def test_recurrent_learner_runs_off_the_gpu_env():
         assert h["episodes"] > 0 and h["partner_updates"] >= 1
 
 
-def test_saved_policies_are_evaluated_by_test_policy(tmp_path):
-    """train_ppo --save-dir -> test_policy (trainer.py:129-133 -> tester.py:64-128) on the GPU env."""
-    import test_policy
+def test_saved_policies_are_evaluated_by_evaluate_policy(tmp_path):
+    """train_ppo --save-dir -> evaluate_policy (trainer.py:129-133 -> tester.py:64-128) on the GPU env."""
+    import evaluate_policy
     import train_ppo
     d = str(tmp_path / "model")
     train_ppo.main(["--envs", "1024", "--n-steps", "32", "--iters", "4", "--log-every", "4", "--batch-size", "8192",
                     "--max-num-timesteps", "50", "--device", DEV, "--save-dir", d])
-    out = test_policy.main(["--max-num-timesteps", "50", "--ego-load", d + "/ppo_ego.pt", "--alt-load", d + "/ppo_partner1.pt",
+    out = evaluate_policy.main(["--max-num-timesteps", "50", "--ego-load", d + "/ppo_ego.pt", "--alt-load", d + "/ppo_partner1.pt",
                             "-t", "3000", "--envs", "1024", "-d", DEV])
     assert out["episodes"] >= 3000 and out["ep_len_mean"] <= 50
     assert np.isfinite(out["average_reward"]) and out["standard_deviation"] > 0.0

@@ -177,11 +177,11 @@ def test_terminal_row_gather_on_the_emulation():
 
 
 @pytest.mark.parametrize("flags", [[], ["--recurrent", "--lstm-hidden", "8"]])
-def test_saved_policies_play_through_test_policy(tmp_path, flags):
-    """train_ppo --save-dir -> test_policy --ego-load / --alt-load (trainer.py:129-133 -> tester.py:64-128) on the
+def test_saved_policies_play_through_evaluate_policy(tmp_path, flags):
+    """train_ppo --save-dir -> evaluate_policy --ego-load / --alt-load (trainer.py:129-133 -> tester.py:64-128) on the
     emulated env: the loaded learners are the saved ones, the requested number of games is played, and the
     statistics line is consistent."""
-    import test_policy
+    import evaluate_policy
     import train_ppo
     from gym_comm_b200.ppo import load_learner
 
@@ -194,13 +194,13 @@ def test_saved_policies_play_through_test_policy(tmp_path, flags):
     assert type(a).__name__ == ("RecurrentPPO" if flags else "PPO")
     for x, y in zip(a.policy.state_dict().values(), b.policy.state_dict().values()):
         assert torch.equal(x, y)
-    out = test_policy.main(["--max-num-timesteps", "6", "--ego-load", d + "/ppo_ego.pt", "--alt-load", d + "/ppo_partner1.pt",
+    out = evaluate_policy.main(["--max-num-timesteps", "6", "--ego-load", d + "/ppo_ego.pt", "--alt-load", d + "/ppo_partner1.pt",
                             "-t", "20", "--envs", "4", "-d", "cpu"], env_factory=factory)
     assert out["episodes"] >= 20 and out["env_steps"] % 4 == 0
     assert out["ep_len_mean"] <= 6 and 0.0 <= out["delivered_frac"] <= 1.0
     assert np.isfinite(out["average_reward"]) and out["standard_deviation"] >= 0.0
     with pytest.raises(ValueError):                                         # a policy of another message width is refused
-        test_policy.main(["--max-num-timesteps", "6", "--num-communication", "3", "--ego-load", d + "/ppo_ego.pt",
+        evaluate_policy.main(["--max-num-timesteps", "6", "--num-communication", "3", "--ego-load", d + "/ppo_ego.pt",
                           "--alt-load", d + "/ppo_partner1.pt", "-t", "4", "--envs", "4", "-d", "cpu"], env_factory=factory)
 
 

@@ -53,7 +53,7 @@ def main(argv=None, env_factory=None, learners_out=None):
     ap.add_argument("--eval-steps", type=int, default=0, help="after training: deterministic evaluation for this many steps")
     ap.add_argument("--save-dir", default=None,
                     help="directory for the two policies, `ppo_ego.pt` and `ppo_partner1.pt` (trainer.py:129-133); "
-                         "test_policy.py --ego-load / --alt-load reads them")
+                         "evaluate_policy.py --ego-load / --alt-load reads them")
     args = ap.parse_args(argv)
 
     if args.json_path:
