@@ -230,3 +230,36 @@ def test_episode_statistics_match_a_manual_tally():
     assert st["ep_len_mean"] == 7 and penv.pop_episode_stats()["episodes"] == 0
     assert partner.model.n_updates == 0                                      # a static agent never trains
     env.close()
+
+
+@pytest.mark.parametrize("level,A", [("open-divider_tomato", 2), ("random-open-divider_salad_small_cramped", 2), ("partial-divider_salad", 3)])
+def test_state_injection_continues_identically(level, A):
+    """Mid-game states exported from one env and injected into a fresh handle (oc_get_state / oc_set_state): both
+    continue with identical observations, rewards, dones and episode counters under the same actions, across
+    auto-resets (random placements included: they are keyed by env index and episode number, both in the state)."""
+    E, C, T = 45, 4, 13
+    ns = argparse.Namespace(level=level, num_agents=A, max_num_timesteps=T, communication_on=True, num_communication=C,
+                            ego_led=False, fow_radius=2, ego_config=D, partner_config=D)
+    a_env = OvercookedVecEnv(ns, num_envs=E, device="cpu", seed=9, auto_reset=True, lib=emu_library())
+    gen = torch.Generator().manual_seed(2)
+
+    def act():
+        return torch.stack([torch.randint(0, 4, (E, A), generator=gen), torch.randint(0, C, (E, A), generator=gen)], -1).to(torch.int32)
+    a_env.reset()
+    for _ in range(T + 5):                                  # past the first auto-reset
+        a_env.step(act())
+    st = a_env.get_state()
+    b_env = OvercookedVecEnv(ns, num_envs=E, device="cpu", seed=9, auto_reset=True, lib=emu_library())
+    b_env.set_state(st)
+    assert torch.equal(b_env.get_state(), st)
+    for t in range(2 * T):
+        a = act()
+        oa, ra, da = (x.clone() for x in a_env.step(a, want_f64=True))
+        r64 = a_env.rewards64.clone()
+        ob, rb, db = b_env.step(a, want_f64=True)
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db) and torch.equal(r64, b_env.rewards64), t
+    sa, sb = a_env.stats(), b_env.stats()
+    assert torch.equal(sa["episodes"], sb["episodes"]) and torch.equal(sa["num_completed_subtasks"], sb["num_completed_subtasks"])
+    assert torch.equal(a_env.get_state(), b_env.get_state())
+    a_env.close()
+    b_env.close()
