@@ -52,3 +52,37 @@ def test_config_compiles_and_steps_like_the_oracle(path):
         assert np.array_equal(env.rewards64.numpy(), orr) and np.array_equal(done.numpy(), od), t
     env.close()
     ora.close()
+
+
+REF_JSON = [p for p in FILES if p.startswith(REF)]
+
+
+@pytest.mark.skipif(not REF_JSON, reason="needs /root/reference")
+def test_namespace_equals_the_reference_parser_where_it_can_parse():
+    """For the config files the reference's own `arglist.create_arglist` (arglist.py:96-121) accepts, our parser
+    yields the same Namespace values for every key the env reads; the files it rejects fail there with a KeyError on
+    `ego_config` / `partner_config` -- those are the ones that get our defaults."""
+    import contextlib
+    import importlib.util
+    import io
+    spec = importlib.util.spec_from_file_location("_ref_arglist", os.path.join(REF, "arglist.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    parsed, rejected = 0, 0
+    for path in REF_JSON:
+        ours = create_arglist(path)
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                theirs = ref.create_arglist(path)
+        except KeyError as ex:
+            assert ex.args[0] in ("ego_config", "partner_config"), (path, ex)
+            rejected += 1
+            continue
+        parsed += 1
+        for key in ("level", "num_agents", "max_num_timesteps", "hyperparams", "communication_on", "num_communication",
+                    "ego_led", "fow_radius", "total_timesteps", "record_interval", "wandb", "max_num_subtasks", "seed"):
+            assert getattr(ours, key) == getattr(theirs, key), (path, key)
+        for side in ("ego_config", "partner_config"):              # the reference keeps exactly the file's keys
+            given = getattr(theirs, side)
+            assert {k: getattr(ours, side)[k] for k in given} == given, (path, side)
+    assert parsed >= 7 and parsed + rejected == len(REF_JSON)
