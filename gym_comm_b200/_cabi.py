@@ -9,11 +9,14 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-OC_ABI_VERSION = 1
+OC_ABI_VERSION = 2
 OC_MAX_AGENTS, OC_MAX_OBJECTS, OC_MAX_SUBTASKS, OC_MAX_CELLS = 4, 6, 32, 128
 OC_STATE_WORDS = 16
 OC_NUM_OBS_KEYS = 11
 OC_FLAG_AUTO_RESET = 1
+OC_FLAG_ACTIONS_U8 = 2
+OC_FLAG_REWARD_PER_ENV = 4
+OC_FLAG_NO_SYNC = 8
 OBS_KEYS = ("agent1_comm", "agent1_location", "agent2_comm", "agent2_location", "agent_is_holding",
             "completed_subtasks", "is_hidden", "object_encodings_x", "object_encodings_y",
             "state_encodings", "timestep")
@@ -21,7 +24,9 @@ OBS_KEYS = ("agent1_comm", "agent1_location", "agent2_comm", "agent2_location", 
 EXPORTS = ("oc_abi_version", "oc_last_error", "oc_create", "oc_destroy", "oc_obs_width", "oc_obs_layout",
            "oc_reset", "oc_step", "oc_rollout", "oc_replay", "oc_get_state", "oc_set_state", "oc_get_stats",
            "oc_launch_count", "oc_reset_host", "oc_step_host", "oc_pack_obs_i8", "oc_reset_host_i8",
-           "oc_step_host_i8", "oc_host_alloc", "oc_host_free", "oc_set_device")
+           "oc_step_host_i8", "oc_host_alloc", "oc_host_free", "oc_set_device", "oc_reset_i8", "oc_step_i8",
+           "oc_host_block_layout", "oc_reset_host_block", "oc_step_host_block", "oc_sync", "oc_get_state_host",
+           "oc_set_state_host", "oc_compact_supported")
 
 
 class OcConfig(C.Structure):
@@ -58,53 +63,70 @@ class OcConfig(C.Structure):
 DEFAULT_LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liboc_b200.so")
 
 
-class OcLibrary:
-    """Loaded shared object + typed entry points.  ``prefix`` exists so the test-only CPU
-    emulation of the device code (tests/emu, prefix ``emu_``) can be driven by the same host
-    code; the product always uses the default arguments."""
+class OcHostBlock(C.Structure):
+    """oc_host_block: byte offsets of the sections of the one-block host path."""
+    _fields_ = [("obs_i8", C.c_uint64), ("timestep", C.c_uint64), ("reward", C.c_uint64), ("done", C.c_uint64),
+                ("total_bytes", C.c_uint64)]
 
-    def __init__(self, path: str = DEFAULT_LIB, prefix: str = "oc_"):
+
+def _signatures():
+    vp, i32, u32 = C.c_void_p, C.c_int32, C.c_uint32
+    return {
+        "oc_last_error": (C.c_char_p, []),
+        "oc_create": (C.c_int, [C.POINTER(OcConfig), C.POINTER(vp)]),
+        "oc_destroy": (C.c_int, [vp]),
+        "oc_obs_width": (C.c_int, [vp]),
+        "oc_obs_layout": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32)]),
+        "oc_reset": (C.c_int, [vp, vp, vp, vp, vp]),
+        "oc_step": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, u32, vp]),
+        "oc_reset_i8": (C.c_int, [vp, vp, vp, vp, vp, vp]),
+        "oc_step_i8": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, u32, vp]),
+        "oc_rollout": (C.c_int, [vp, i32, vp, vp, vp, vp, vp]),
+        "oc_replay": (C.c_int, [vp, i32, vp, vp, vp, vp, vp]),
+        "oc_get_state": (C.c_int, [vp, vp, vp]),
+        "oc_set_state": (C.c_int, [vp, vp, vp]),
+        "oc_get_stats": (C.c_int, [vp, vp, vp, vp]),
+        "oc_pack_obs_i8": (C.c_int, [vp, vp, vp, vp, vp]),
+        "oc_reset_host": (C.c_int, [vp, vp, vp, vp, vp]),
+        "oc_step_host": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, u32, vp]),
+        "oc_reset_host_i8": (C.c_int, [vp, vp, vp, vp, vp, vp]),
+        "oc_step_host_i8": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, u32, vp]),
+        "oc_host_block_layout": (C.c_int, [vp, C.POINTER(OcHostBlock)]),
+        "oc_reset_host_block": (C.c_int, [vp, vp, vp, vp, vp]),
+        "oc_step_host_block": (C.c_int, [vp, vp, vp, vp, vp, u32, vp]),
+        "oc_sync": (C.c_int, [vp, vp]),
+        "oc_get_state_host": (C.c_int, [vp, vp, vp]),
+        "oc_set_state_host": (C.c_int, [vp, vp, vp]),
+        "oc_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(vp)]),
+        "oc_host_free": (C.c_int, [vp]),
+        "oc_set_device": (C.c_int, [C.c_int]),
+        "oc_abi_version": (C.c_int, []),
+        "oc_launch_count": (C.c_uint64, [vp]),
+        "oc_compact_supported": (C.c_int, [vp]),
+    }
+
+
+SIGNATURES = _signatures()      # (restype, argtypes) of every export of include/overcooked_b200.h
+
+
+class OcLibrary:
+    """`liboc_b200.so` (hand-written sm_100a CUDA) + typed entry points.  This is the only backend the package
+    has: there is no CPU implementation to select."""
+
+    def __init__(self, path: str = DEFAULT_LIB):
         if not os.path.exists(path):
             raise RuntimeError(
                 "%s not found: the CUDA extension is not built. Run `python -c 'import __graft_entry__ as g; "
                 "g.build()'` (nvcc, sm_100a). There is no CPU fallback." % path)
         self.path = path
-        self.prefix = prefix
         self.lib = C.CDLL(path)
-        vp, i32, u32 = C.c_void_p, C.c_int32, C.c_uint32
-
-        def fn(name, restype, argtypes):
-            f = getattr(self.lib, prefix + name)
-            f.restype = restype
-            f.argtypes = argtypes
-            return f
-
-        self.last_error = fn("last_error", C.c_char_p, [])
-        self.create = fn("create", C.c_int, [C.POINTER(OcConfig), C.POINTER(vp)])
-        self.destroy = fn("destroy", C.c_int, [vp])
-        self.obs_width = fn("obs_width", C.c_int, [vp])
-        self.obs_layout = fn("obs_layout", C.c_int, [vp, C.POINTER(i32), C.POINTER(i32)])
-        self.reset = fn("reset", C.c_int, [vp, vp, vp, vp, vp])
-        self.step = fn("step", C.c_int, [vp, vp, vp, vp, vp, vp, vp, u32, vp])
-        self.rollout = fn("rollout", C.c_int, [vp, i32, vp, vp, vp, vp, vp])
-        if prefix == "oc_":
-            self.replay = fn("replay", C.c_int, [vp, i32, vp, vp, vp, vp, vp])
-        self.get_state = fn("get_state", C.c_int, [vp, vp, vp])
-        self.set_state = fn("set_state", C.c_int, [vp, vp, vp])
-        self.get_stats = fn("get_stats", C.c_int, [vp, vp, vp, vp])
-        self.pack_obs_i8 = fn("pack_obs_i8", C.c_int, [vp, vp, vp, vp, vp])
-        if prefix == "oc_":
-            self.reset_host = fn("reset_host", C.c_int, [vp, vp, vp, vp, vp])
-            self.step_host = fn("step_host", C.c_int, [vp, vp, vp, vp, vp, vp, vp, u32, vp])
-            self.reset_host_i8 = fn("reset_host_i8", C.c_int, [vp, vp, vp, vp, vp, vp])
-            self.step_host_i8 = fn("step_host_i8", C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, u32, vp])
-            self.host_alloc = fn("host_alloc", C.c_int, [C.c_uint64, C.POINTER(vp)])
-            self.host_free = fn("host_free", C.c_int, [vp])
-            self.set_device = fn("set_device", C.c_int, [C.c_int])
-            self.abi_version = fn("abi_version", C.c_int, [])
-            self.launch_count = fn("launch_count", C.c_uint64, [vp])
-            if self.abi_version() != OC_ABI_VERSION:
-                raise RuntimeError("liboc_b200.so ABI version %d != %d" % (self.abi_version(), OC_ABI_VERSION))
+        for name in EXPORTS:                       # self.step = oc_step, self.reset_host_i8 = oc_reset_host_i8, ...
+            f = getattr(self.lib, name)
+            f.restype, f.argtypes = SIGNATURES[name]
+            setattr(self, name[3:], f)
+        if self.abi_version() != OC_ABI_VERSION:
+            raise RuntimeError("liboc_b200.so ABI version %d != %d (rebuild: __graft_entry__.build())" %
+                               (self.abi_version(), OC_ABI_VERSION))
 
     def check(self, rc: int, what: str):
         if rc != 0:
@@ -117,7 +139,7 @@ _default = None
 
 def default_library() -> OcLibrary:
     """The in-tree CUDA library.  `OC_B200_LIB=<path>` loads another BUILD of the same sources instead (A/B of
-    compile-time knobs such as -DOC_STEP_MIN_CTAS, tools/ab_step_bounds.sh); it is still the CUDA library."""
+    compile-time knobs, e.g. the -DOC_PHASE_PROBE build of tools/probe_step.py); it is still the CUDA library."""
     global _default
     if _default is None:
         _default = OcLibrary(os.environ.get("OC_B200_LIB") or DEFAULT_LIB)

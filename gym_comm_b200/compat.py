@@ -12,12 +12,15 @@ called (this image has neither gym nor pantheonrl; the build container tests it 
 from __future__ import annotations
 
 
-def gym_env_class():
+def gym_env_class(b200_env_cls=None):
     """-> a `SimultaneousEnv` subclass with the constructor of `gym_comm.envs.OvercookedMultiEnv`
-    (gym_comm/envs/overcooked_env.py:16-18) whose `multi_step` / `multi_reset` go to the B200 env."""
+    (gym_comm/envs/overcooked_env.py:16-18) whose `multi_step` / `multi_reset` go to the B200 env
+    (`b200_env_cls`: the class to wrap, default `gym_comm_b200.OvercookedMultiEnv`)."""
     from pantheonrl.common.multiagentenv import SimultaneousEnv       # the reference's own base class
 
-    from .vec_env import OvercookedMultiEnv as _B200Env
+    if b200_env_cls is None:
+        from .vec_env import OvercookedMultiEnv as b200_env_cls
+    _B200Env = b200_env_cls
 
     class GymOvercookedMultiEnv(SimultaneousEnv):
         def __init__(self, arglist, ego_agent_idx: int = 0, baselines: bool = False, **backend):

@@ -249,7 +249,7 @@ __device__ __forceinline__ Info env_step(Env<A, NOBJ>& e, const OcParams& p, con
         const uint32_t c1 = (p.comm_on && !p.ego_led) ? (uint32_t)comm1 : OCK_COMM_NONE;
         e.comm = (c0 & 0xFFFFu) | (c1 << 16);
     }
-    e.w0 += 1;   // t += 1 (t lives in the low 16 bits)
+    if ((e.w0 & 0xFFFFu) != 0xFFFFu) e.w0 += 1;   // t += 1 (t lives in the low 16 bits and saturates instead of carrying into the stamp)
     const uint32_t t = e.w0 & 0xFFFFu;
 
     // ---- collisions, on the ORIGINAL actions for every pair (:543-613)
@@ -341,7 +341,7 @@ __device__ __forceinline__ Info env_step(Env<A, NOBJ>& e, const OcParams& p, con
     // ---- done + sparse reward through the signature -> subtask-mask table
     const Info in = gather_info<A, NOBJ, NF>(e, p, tb);
     const uint32_t dl = in.deliv & p.deliver_mask;
-    done = (p.T != 0 && t >= (uint32_t)p.T) || (dl == p.deliver_mask);       // :243-270
+    done = (t >= (uint32_t)p.T) || (dl == p.deliver_mask);                   // :243-270 (T >= 1: oc_create rejects 0)
     const uint32_t nw = in.pres & ~e.countbits & p.nondeliver_mask;          // count rose (:409-415)
     const int sparse = 3 * __popc(dl) + __popc(nw);
     e.countbits = in.pres & p.nondeliver_mask;
@@ -496,24 +496,26 @@ __device__ __forceinline__ void build_rows_f32(const Env<A, NOBJ>& e, const OcPa
     }
 }
 
-// one observer's row as biased bytes (r = F bytes, 0x80-filled)
-template <int A, int NOBJ, int NF>
+// one observer's row as bytes: value + BIAS.  BIAS = 128 with 0x80-filled rows of F bytes (expanded to floats on
+// the way out); BIAS = 0 with zero-filled rows of F - 1 bytes = the compact integer format itself (int8, the
+// `timestep` column -- the last key -- cut out)
+template <int A, int NOBJ, int NF, uint32_t BIAS = 128u>
 __device__ __forceinline__ void build_row_u8_one(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
                                                  const Info& in, int k, uint8_t* __restrict__ r) {
     const uint32_t xy0 = tb.xy16[e.acell[0]], xy1 = tb.xy16[e.acell[1]];
     const uint32_t c0 = e.comm & 0xFFFFu, c1 = e.comm >> 16;
     const float fow = (float)p.fow;
     const bool blind = p.blind[k] != 0;
-    if (c0 != OCK_COMM_NONE) r[p.off_a1comm + c0] = OCK_BIAS + 1;
-    if (c1 != OCK_COMM_NONE) r[p.off_a2comm + c1] = OCK_BIAS + 1;
+    if (c0 != OCK_COMM_NONE) r[p.off_a1comm + c0] = BIAS + 1;
+    if (c1 != OCK_COMM_NONE) r[p.off_a2comm + c1] = BIAS + 1;
     if (!blind) {
-        r[p.off_a1loc] = OCK_BIAS + (xy0 & 0xFF);  r[p.off_a1loc + 1] = OCK_BIAS + (xy0 >> 8);
-        r[p.off_a2loc] = OCK_BIAS + (xy1 & 0xFF);  r[p.off_a2loc + 1] = OCK_BIAS + (xy1 >> 8);
+        r[p.off_a1loc] = BIAS + (xy0 & 0xFF);  r[p.off_a1loc + 1] = BIAS + (xy0 >> 8);
+        r[p.off_a2loc] = BIAS + (xy1 & 0xFF);  r[p.off_a2loc + 1] = BIAS + (xy1 >> 8);
     }
-    if (!p.ego_blind && ((in.holdmask >> k) & 1u)) r[p.off_hold] = OCK_BIAS + 1;
+    if (!p.ego_blind && ((in.holdmask >> k) & 1u)) r[p.off_hold] = BIAS + 1;
     if (blind) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) r[p.off_hidden + c] = OCK_BIAS + 1;
+        for (int c = 0; c < 4; ++c) r[p.off_hidden + c] = BIAS + 1;
     } else {
         const float2 me = tb.xyf[e.acell[k]];
 #pragma unroll
@@ -523,14 +525,14 @@ __device__ __forceinline__ void build_row_u8_one(const Env<A, NOBJ>& e, const Oc
             if (obj_alive(w)) {
                 float hid, ex, ey, st;
                 channel_features(tb, w, me, fow, c, hid, ex, ey, st);
-                r[p.off_hidden + c] = (uint8_t)(OCK_BIAS + (int)hid);
-                r[p.off_encx + c] = (uint8_t)(OCK_BIAS + (int)ex);
-                r[p.off_ency + c] = (uint8_t)(OCK_BIAS + (int)ey);
-                if (c < 3) r[p.off_state + c] = (uint8_t)(OCK_BIAS + (int)st);
+                r[p.off_hidden + c] = (uint8_t)(BIAS + (int)hid);
+                r[p.off_encx + c] = (uint8_t)(BIAS + (int)ex);
+                r[p.off_ency + c] = (uint8_t)(BIAS + (int)ey);
+                if (c < 3) r[p.off_state + c] = (uint8_t)(BIAS + (int)st);
             }
         }
     }
-    for (uint32_t m = e.completed; m != 0; m &= m - 1) r[p.off_completed + (__ffs((int)m) - 1)] = OCK_BIAS + 1;
+    for (uint32_t m = e.completed; m != 0; m &= m - 1) r[p.off_completed + (__ffs((int)m) - 1)] = BIAS + 1;
 }
 
 template <int A, int NOBJ, int NF>
@@ -538,6 +540,14 @@ __device__ __forceinline__ void build_rows_u8(const Env<A, NOBJ>& e, const OcPar
                                               const Info& in, uint8_t* __restrict__ row /* 0x80-filled */) {
 #pragma unroll
     for (int k = 0; k < A; ++k) build_row_u8_one<A, NOBJ, NF>(e, p, tb, in, k, row + k * p.F);
+}
+
+// compact integer rows: int8 [A, F-1] per env, zero-filled on entry
+template <int A, int NOBJ, int NF>
+__device__ __forceinline__ void build_rows_i8(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
+                                              const Info& in, uint8_t* __restrict__ row /* zero-filled */) {
+#pragma unroll
+    for (int k = 0; k < A; ++k) build_row_u8_one<A, NOBJ, NF, 0u>(e, p, tb, in, k, row + k * (p.F - 1));
 }
 
 // warp-cooperative fill of the warp's 32 rows with the "all features 0.0" pattern
@@ -561,6 +571,24 @@ __device__ __forceinline__ void tma_store(void* gdst, const void* ssrc, uint32_t
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(s), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// ---- TMA bulk LOAD of a contiguous global region into shared memory, completion on an mbarrier (one thread issues,
+// everybody waits on the barrier's phase bit): the table blob arrives while the threads are busy with other things
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");     // visible to the async proxy
+}
+__device__ __forceinline__ void tma_load(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar), d = (uint32_t)__cvta_generic_to_shared(sdst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("{\n\t.reg .pred p;\n\tOCK_MBAR_WAIT:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@!p bra OCK_MBAR_WAIT;\n\t}" :: "r"(b), "r"(parity) : "memory");
 }
 #endif
 // rows may be overwritten again once the copy engine has READ them
@@ -659,7 +687,8 @@ __device__ __forceinline__ void warp_expand_rows(const OcParams& p, const uint8_
 template <int A, int NOBJ>
 __device__ __forceinline__ float timestep_of(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb) {
     const uint32_t t = e.w0 & 0xFFFFu;
-    return (p.o_ts >= 0) ? tb.ts[t] : (float)__ddiv_rn((double)t, (double)p.T);
+    // the table holds t = 0..T; an env stepped past done without a reset (auto-reset off) reports t / T > 1 like the reference
+    return (p.o_ts >= 0 && t <= (uint32_t)p.T) ? tb.ts[t] : (float)__ddiv_rn((double)t, (double)p.T);
 }
 
 template <int A, int NOBJ, int NF, bool ROWF>
@@ -754,6 +783,66 @@ __device__ __forceinline__ void warp_terminal_obs(const Env<A, NOBJ>& e, const I
     }
 }
 
+// =============================================================================================
+// Compact integer format produced by the step / reset kernels themselves (kernel MODE 3): int8 [E, A, F-1]
+// rows + the f32 clock [E] -- what a consumer on the far side of PCIe gets (oc_step_host_i8 /
+// oc_step_host_block).  A warp's 32 rows are 32 * A * (F-1) contiguous bytes in shared memory (a quarter of
+// the float rows, so four times the warps fit on an SM) and leave through ONE bulk copy; the destination may
+// be device memory or page-locked host memory (the copy engine then writes across PCIe while the kernel runs).
+// p.row_bytes = A * (F-1) = bytes of one env's rows, p.row_stride == p.row_bytes (contiguous).
+// =============================================================================================
+__device__ __forceinline__ void warp_store_packed(const OcParams& p, const uint8_t* __restrict__ wrows,
+                                                  uint8_t* __restrict__ out /* warp's first env row */, int nvalid, int lane) {
+    const int total = nvalid * p.row_bytes;                      // bytes; rows are contiguous
+#ifndef OCK_HOST_EMU
+    if (p.use_tma && (total & 15) == 0) {                        // every full warp: 32 * row_bytes is a multiple of 32
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tma_store(out, wrows, (uint32_t)total);
+        return;
+    }
+#endif
+    const int nw = total >> 2;                                   // ragged last warp: word copy + byte tail
+    const uint32_t* i32 = reinterpret_cast<const uint32_t*>(wrows);
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(out);            // out = base + env0 * row_bytes with env0 % 32 == 0: 4-byte aligned
+    for (int idx = lane; idx < nw; idx += 32) o32[idx] = i32[idx];
+    for (int idx = (nw << 2) + lane; idx < total; idx += 32) out[idx] = wrows[idx];
+}
+
+template <int A, int NOBJ, int NF>
+__device__ __forceinline__ void emit_obs_packed(const Env<A, NOBJ>& e, const Info& in, bool valid, const OcParams& p,
+                                                const Tables& tb, uint8_t* wrows, int lane,
+                                                uint8_t* __restrict__ out_env0, float* __restrict__ ts_env0, int nvalid,
+                                                bool clean_on_entry = false) {
+    const float ts = valid ? timestep_of<A, NOBJ>(e, p, tb) : 0.0f;
+    if (!clean_on_entry) {
+        rows_wait_read(p);
+        warp_clear_rows<true>(wrows, p.warp_row_bytes, lane);
+        __syncwarp();
+    }
+    if (valid) build_rows_i8<A, NOBJ, NF>(e, p, tb, in, wrows + (size_t)lane * p.row_stride);
+    __syncwarp();
+    if (nvalid > 0) warp_store_packed(p, wrows, out_env0, nvalid, lane);
+    if (valid && ts_env0 != nullptr) ts_env0[lane] = ts;         // 128 contiguous bytes per warp
+}
+
+// terminal rows of the envs of this warp that just finished, compact format; rare path
+template <int A, int NOBJ, int NF>
+__device__ __forceinline__ void warp_terminal_obs_packed(const Env<A, NOBJ>& e, const Info& in, bool fin, const OcParams& p,
+                                                         const Tables& tb, uint8_t* wrows, int lane,
+                                                         uint8_t* __restrict__ term_row, float* __restrict__ term_ts) {
+    rows_wait_read(p);
+    warp_clear_rows<true>(wrows, p.warp_row_bytes, lane);
+    __syncwarp();
+    if (fin) {
+        uint8_t* myrow = wrows + (size_t)lane * p.row_stride;
+        build_rows_i8<A, NOBJ, NF>(e, p, tb, in, myrow);
+        for (int j = 0; j < p.row_bytes; ++j) { term_row[j] = myrow[j]; myrow[j] = 0; }
+        if (term_ts != nullptr) *term_ts = timestep_of<A, NOBJ>(e, p, tb);
+    }
+    __syncwarp();
+}
+
 // terminal bookkeeping + in-place reset of one finished env (SB3 VecEnv auto-reset contract)
 template <int A, int NOBJ>
 __device__ __forceinline__ void finish_episode(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb, uint32_t env_id) {
@@ -767,7 +856,8 @@ template <int A, int NOBJ, int NF>
 __device__ __forceinline__ Info step_logic(Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
                                            const int (&nav)[A], int comm0, int comm1, uint32_t env,
                                            float* __restrict__ rew32, double* __restrict__ rew64,
-                                           uint8_t* __restrict__ done_out, bool& done) {
+                                           uint8_t* __restrict__ done_out, bool& done,
+                                           bool rew_per_env = false /* rew32 is f32 [E], not [E, A] */) {
     double reward;
     // out-of-range message index -> zero vector (the reference raises IndexError)
     const int c0 = ((uint32_t)comm0 < (uint32_t)p.C) ? comm0 : (int)OCK_COMM_NONE;
@@ -776,8 +866,11 @@ __device__ __forceinline__ Info step_logic(Env<A, NOBJ>& e, const OcParams& p, c
     if (rew64 != nullptr) rew64[env] = reward;
     if (rew32 != nullptr) {
         const float r = (float)reward;
+        if (rew_per_env) rew32[env] = r;
+        else {
 #pragma unroll
-        for (int k = 0; k < A; ++k) rew32[(size_t)env * A + k] = r;
+            for (int k = 0; k < A; ++k) rew32[(size_t)env * A + k] = r;
+        }
     }
     done_out[env] = done ? 1 : 0;
     return in;
@@ -842,6 +935,37 @@ __device__ __forceinline__ void reset_logic(Env<A, NOBJ>& e, const OcParams& p, 
         e.episodes += 1;
         env_reset<A, NOBJ>(e, p, tb, pl, env);
     }
+}
+
+// ---- oc_set_state: one 16-byte plane of an imported env, sanitised (agent cells and live object cells clamped to the
+// grid, holders to {0..A-1, none}, empty slots -> the canonical dead word, subtask bits and message indices cut to
+// the configured S and C): whatever the words are, the kernels stay inside their tables and rows
+__device__ __forceinline__ uint32_t sanitize_object_word(const OcParams& p, uint32_t o) {
+    if ((o & 0xFu) == 0u) return OCK_DEAD;
+    uint32_t holder = (o >> 8) & 7u, cell = (o >> 16) & 0xFFu;
+    if (holder >= (uint32_t)p.A) holder = OCK_HOLDER_NONE;
+    cell = min(cell, (uint32_t)p.ncell - 1u);
+    return (o & 0xFF0000FFu) | (holder << 8) | (cell << 16);
+}
+__device__ __forceinline__ uint4 sanitize_state_plane(const OcParams& p, int plane, uint4 v) {
+    if (plane == 0) {                                    // completed / count bits index the observation row
+        const uint32_t smask = p.S >= 32 ? 0xFFFFFFFFu : ((1u << p.S) - 1u);
+        v.z &= smask; v.w &= smask;
+    } else if (plane == 1) {
+        uint32_t cells = 0;
+        for (int k = 0; k < 4; ++k) cells |= min((v.x >> (8 * k)) & 0xFFu, (uint32_t)p.ncell - 1u) << (8 * k);
+        v.x = cells;
+    } else if (plane == 2) {
+        v.x = sanitize_object_word(p, v.x); v.y = sanitize_object_word(p, v.y);
+        v.z = sanitize_object_word(p, v.z); v.w = sanitize_object_word(p, v.w);
+    } else if (plane == 3) {
+        v.x = sanitize_object_word(p, v.x); v.y = sanitize_object_word(p, v.y);
+        uint32_t c0 = v.z & 0xFFFFu, c1 = v.z >> 16;     // message indices write one-hots into the row
+        if (c0 >= (uint32_t)p.C) c0 = OCK_COMM_NONE;
+        if (c1 >= (uint32_t)p.C) c1 = OCK_COMM_NONE;
+        v.z = c0 | (c1 << 16);
+    }
+    return v;
 }
 
 // ---- compact integer format (oc_pack_obs_i8): every key of a row except the clock is a small

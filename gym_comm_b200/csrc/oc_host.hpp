@@ -62,6 +62,19 @@ static inline void bfs_path_dist(const oc_config* c, std::vector<uint8_t>& pd) {
 }
 
 
+// the compact-row variant of a compiled parameter block (kernel MODE 3): one env's rows are the A * (F-1) int8
+// values of the compact integer format, contiguous, all 32 envs of a warp in one pass, one bulk copy per warp
+static inline void make_compact_params(OcParams& p) {
+    p.rowf = 0;
+    p.row_bytes = p.A * (p.F - 1);
+    p.row_stride = p.row_bytes;
+    p.nb = 32; p.nb_shift = 5; p.obs_passes = 1; p.nbuf = 1;
+    p.buf_bytes = (int)align_up((size_t)32 * p.row_bytes, 16);
+    p.warp_row_bytes = p.buf_bytes;
+    p.use_tma = 1;
+    if (const char* t = getenv("OC_TMA")) p.use_tma = atoi(t) != 0 ? 1 : 0;
+}
+
 // returns OC_OK or OC_ERR_INVALID (message in err)
 static inline int compile_config(const oc_config* c, HostImage& h, std::string& err) {
 #define OC_BAD(msg) do { err = (msg); return OC_ERR_INVALID; } while (0)

@@ -21,66 +21,159 @@ using namespace ock;
 // kernels
 // =============================================================================================
 
-// A/B knob (compile time): -DOC_STEP_MIN_CTAS=n adds a minimum-CTAs-per-SM hint to the step kernel, i.e. a register
-// cap of 65536 / (256 n); unset = ptxas' own choice (see profiles/r1_ptxas_sass.txt for what it picks)
+// Launch bounds of the step kernel: the float-row instantiations are limited by shared memory to 2-3 CTAs per SM, so
+// they may use up to 128 registers (no spills); the byte-row and compact-row ones want many resident warps (64 registers).
+// A/B knob (compile time): -DOC_STEP_MIN_CTAS=n forces one value for all of them.
 #ifdef OC_STEP_MIN_CTAS
-#define OC_STEP_BOUNDS __launch_bounds__(256, OC_STEP_MIN_CTAS)
+#define OC_STEP_BOUNDS(MODE) __launch_bounds__(256, OC_STEP_MIN_CTAS)
 #else
-#define OC_STEP_BOUNDS __launch_bounds__(256)
+#define OC_STEP_BOUNDS(MODE) __launch_bounds__(256, ((MODE) == 1 || (MODE) == 2) ? 2 : 4)
 #endif
 
-// dynamic shared memory: [table blob][per warp: nb env rows (float or biased-byte format)]
+// Phase probe (tools/probe_step.py, -DOC_PHASE_PROBE builds only; never in the shipped library): lane 0 of every
+// warp stamps %clock64 at the phase boundaries of the step kernel and %globaltimer at entry / exit.
+#ifdef OC_PHASE_PROBE
+__device__ unsigned long long* g_probe = nullptr;
+__device__ __forceinline__ unsigned long long probe_clock(uint32_t dep) {
+    __shared__ uint32_t scratch[32];
+    unsigned long long c;
+    // the store cannot issue before `dep` has arrived; the clock read issues after it (in-order issue)
+    asm volatile("st.shared.u32 [%1], %2;\n\tmov.u64 %0, %%clock64;"
+                 : "=l"(c) : "r"((uint32_t)__cvta_generic_to_shared(scratch + (threadIdx.x >> 5))), "r"(dep) : "memory");
+    return c;
+}
+__device__ __forceinline__ unsigned long long probe_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
+    return t;
+}
+#define OC_PROBE(k, dep) do { if (lane == 0) pr[k] = probe_clock(dep); } while (0)
+#else
+#define OC_PROBE(k, dep) do { } while (0)
+#endif
+
+// One oc_step launch.  MODE 0-2: float rows [E, A, F] to `obs`; MODE 3: compact rows int8 [E, A, F-1] to `obs`
+// and the clock f32 [E] to `ts`.  Any output pointer may be device memory or page-locked host memory.
+struct StepIO {
+    const void* actions;      // int32 [E, A, 2], or u8 [E, A, 2] with OC_FLAG_ACTIONS_U8
+    void* obs;
+    float* ts;                // MODE 3 only
+    float* rew32;             // f32 [E, A], or f32 [E] with OC_FLAG_REWARD_PER_ENV
+    double* rew64;            // f64 [E]
+    uint8_t* done;
+    void* term_obs;           // like obs: rows of envs that finished (auto-reset on)
+    float* term_ts;           // MODE 3 only
+    uint32_t flags;
+    int32_t env_lo, env_hi;   // this launch steps envs [env_lo, env_hi); env_lo is a multiple of 32
+};
+
+// dynamic shared memory: [table blob][per warp: nb env rows (float / biased-byte / compact int8 format)]
 template <int A, int NOBJ, int NF, int MODE>
-__global__ void OC_STEP_BOUNDS
-oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
-               const int32_t* __restrict__ actions, float* __restrict__ obs,
-               float* __restrict__ rew32, double* __restrict__ rew64, uint8_t* __restrict__ done_out,
-               float* __restrict__ term_obs, uint32_t flags) {
+__global__ void OC_STEP_BOUNDS(MODE)
+oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, const __grid_constant__ StepIO io) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#ifdef OC_PHASE_PROBE
+    unsigned long long pr[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const unsigned long long g0 = probe_gtime();
+#endif
+    OC_PROBE(0, 0u);
 
-    // Programmatic dependent launch: let the NEXT launch in the stream start its own prologue as
-    // soon as every CTA of this grid is running; do our prologue (tables, row clear) before
-    // waiting for the previous grid -- only what follows the wait touches its outputs (state,
-    // actions).  Both instructions are no-ops when the launch carries no PDL attribute.
+    // Prologue.  (1) One thread hands the table blob to the copy engine (TMA bulk load, completion on an mbarrier): the
+    // tables are constant, so this does not wait for the previous grid, and nobody stalls on it until the dynamics
+    // need them.  (2) Programmatic dependent launch: the NEXT launch may start as soon as every CTA of this grid is
+    // running; everything below the wait may touch what the previous grid wrote (state, actions).  Both
+    // griddepcontrol instructions are no-ops when the launch carries no PDL attribute.  (3) Inside the loop, the
+    // first chunk issues its state / action loads BEFORE the rows are cleared, so the clear (82 KB of shared-memory
+    // stores per CTA at cfg2) runs under the latency of those loads instead of in front of them.
+    __shared__ __align__(8) uint64_t tbar;
+    if (threadIdx.x == 0) {
+        mbar_init(&tbar, 1);
+        tma_load(smem, p.blob, (uint32_t)p.blob_bytes, &tbar);
+    }
     asm volatile("griddepcontrol.launch_dependents;");
-    load_tables(p, smem);
     uint8_t* wrows = smem + p.blob_bytes + (size_t)warp * p.warp_row_bytes;
-    warp_clear_rows<MODE != 0>(wrows, p.warp_row_bytes, lane);
+    OC_PROBE(1, 0u);
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    __syncthreads();
+    OC_PROBE(2, 0u);
     const Tables tb = make_tables(p, smem);
+    const uint32_t flags = io.flags;
 
     // the grid is sized to ONE resident wave (148 SMs x CTAs that fit); with more envs than that
     // each CTA walks several chunks so the tables are loaded once per CTA, not once per chunk
     bool first = true;                              // rows still clear from the prologue
-    for (int base = blockIdx.x * blockDim.x; base < p.E; base += gridDim.x * blockDim.x) {
+    for (int base = io.env_lo + blockIdx.x * blockDim.x; base < io.env_hi; base += gridDim.x * blockDim.x) {
         const int env = base + threadIdx.x;
-        const bool valid = env < p.E;
+        const bool valid = env < io.env_hi;
         Env<A, NOBJ> e;
         Info in;
         bool done = false;
-        if (valid) {                                    // dynamics: no row access, may overlap the previous chunk's TMA read
-            int nav[A], comm[A];
-            load_env<A, NOBJ>(e, state, p.E, env);
-            const int2* a2 = reinterpret_cast<const int2*>(actions) + (size_t)env * A;
+        uint4 s0, s1, s2, s3;
+        int nav[A], comm[A];
+        if (valid) {                                    // raw loads: state planes + this env's actions
+            s0 = state[env]; s1 = state[p.E + env]; s2 = state[2 * p.E + env]; s3 = state[3 * p.E + env];
+            if (flags & OC_FLAG_ACTIONS_U8) {
+                const uchar2* a2 = reinterpret_cast<const uchar2*>(io.actions) + (size_t)env * A;
 #pragma unroll
-            for (int k = 0; k < A; ++k) { const int2 v = __ldg(a2 + k); nav[k] = v.x & 3; comm[k] = v.y; }
-            in = step_logic<A, NOBJ, NF>(e, p, tb, nav, comm[0], comm[1], (uint32_t)env, rew32, rew64, done_out, done);
+                for (int k = 0; k < A; ++k) { const uchar2 v = __ldg(a2 + k); nav[k] = v.x & 3; comm[k] = v.y; }
+            } else {
+                const int2* a2 = reinterpret_cast<const int2*>(io.actions) + (size_t)env * A;
+#pragma unroll
+                for (int k = 0; k < A; ++k) { const int2 v = __ldg(a2 + k); nav[k] = v.x & 3; comm[k] = v.y; }
+            }
+        }
+        if (first) {
+            warp_clear_rows<MODE != 0>(wrows, p.warp_row_bytes, lane);
+            __syncthreads();                            // mbarrier initialised by thread 0 -> visible to everyone
+            OC_PROBE(3, 0u);
+            mbar_wait(&tbar, 0);                        // tables have landed
+        }
+        if (valid) {                                    // dynamics: no row access, may overlap the previous chunk's TMA read
+            unpack_env<A, NOBJ>(e, s0, s1, s2, s3);
+            OC_PROBE(4, e.w0 + e.comm + e.obj[0] + e.acell[0] + (uint32_t)nav[A - 1]);
+            in = step_logic<A, NOBJ, NF>(e, p, tb, nav, comm[0], comm[1], (uint32_t)env, io.rew32, io.rew64, io.done, done,
+                                         (flags & OC_FLAG_REWARD_PER_ENV) != 0);
+            OC_PROBE(5, in.pres + in.holdmask + (uint32_t)done);
         }
         const bool fin = valid && done && (flags & OC_FLAG_AUTO_RESET);
-        if (term_obs != nullptr && __any_sync(0xFFFFFFFFu, fin))      // rare: some env of this warp finished
-            warp_terminal_obs<A, NOBJ, NF, MODE>(e, in, fin, p, tb, wrows, lane, term_obs + (size_t)env * p.row_bytes);
+        if (io.term_obs != nullptr && __any_sync(0xFFFFFFFFu, fin)) {  // rare: some env of this warp finished
+            if (MODE == 3)
+                warp_terminal_obs_packed<A, NOBJ, NF>(e, in, fin, p, tb, wrows, lane,
+                                                      reinterpret_cast<uint8_t*>(io.term_obs) + (size_t)env * p.row_bytes,
+                                                      io.term_ts ? io.term_ts + env : nullptr);
+            else
+                warp_terminal_obs<A, NOBJ, NF, (MODE == 3 ? 0 : MODE)>(e, in, fin, p, tb, wrows, lane,
+                                                      reinterpret_cast<float*>(io.term_obs) + (size_t)env * p.row_bytes);
+        }
         if (fin) {
             finish_episode<A, NOBJ>(e, p, tb, (uint32_t)env);
             in = gather_info<A, NOBJ, NF>(e, p, tb);
         }
         if (valid) store_env<A, NOBJ>(e, state, p.E, env);
+        OC_PROBE(6, 0u);
         const int env0 = base + warp * 32;
-        emit_obs<A, NOBJ, NF, MODE>(e, in, valid, p, tb, wrows, lane, obs + (size_t)env0 * p.row_bytes, min(32, p.E - env0), first);
+        const int nvalid = max(0, min(32, io.env_hi - env0));
+        if (MODE == 3)
+            emit_obs_packed<A, NOBJ, NF>(e, in, valid, p, tb, wrows, lane,
+                                         reinterpret_cast<uint8_t*>(io.obs) + (size_t)env0 * p.row_bytes,
+                                         io.ts ? io.ts + env0 : nullptr, nvalid, first);
+        else
+            emit_obs<A, NOBJ, NF, (MODE == 3 ? 0 : MODE)>(e, in, valid, p, tb, wrows, lane,
+                                         reinterpret_cast<float*>(io.obs) + (size_t)env0 * p.row_bytes, nvalid, first);
+        OC_PROBE(7, 0u);
         first = false;
     }
     rows_wait_done(p);
+    OC_PROBE(8, 0u);
+#ifdef OC_PHASE_PROBE
+    if (lane == 0 && g_probe != nullptr) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        unsigned long long* o = g_probe + ((size_t)blockIdx.x * 8 + warp) * 16;
+        for (int k = 0; k < 9; ++k) o[k] = pr[k];
+        o[9] = g0; o[10] = probe_gtime(); o[11] = smid;
+    }
+#endif
 }
 
 // n_steps steps per launch, state in registers, Philox actions (SURVEY section 8d synthetic inputs)
@@ -118,11 +211,11 @@ oc_rollout_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
     rows_wait_done(p);
 }
 
-// reset (masked) + observation of every env
+// reset (masked) + observation of every env (MODE 3: compact rows to `obs`, clocks to `ts`)
 template <int A, int NOBJ, int NF, int MODE>
 __global__ void __launch_bounds__(256)
 oc_reset_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, const uint8_t* __restrict__ mask,
-                const int32_t* __restrict__ placements, float* __restrict__ obs, int initial) {
+                const int32_t* __restrict__ placements, void* __restrict__ obs, float* __restrict__ ts, int initial) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
@@ -140,8 +233,15 @@ oc_reset_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, c
         if (obs != nullptr) in = gather_info<A, NOBJ, NF>(e, p, tb);
     }
     const int env0 = blockIdx.x * blockDim.x + warp * 32;
-    if (obs != nullptr)
-        emit_obs<A, NOBJ, NF, MODE>(e, in, valid, p, tb, wrows, lane, obs + (size_t)env0 * p.row_bytes, min(32, p.E - env0));
+    const int nvalid = max(0, min(32, p.E - env0));
+    if (obs != nullptr) {
+        if (MODE == 3)
+            emit_obs_packed<A, NOBJ, NF>(e, in, valid, p, tb, wrows, lane,
+                                         reinterpret_cast<uint8_t*>(obs) + (size_t)env0 * p.row_bytes, ts ? ts + env0 : nullptr, nvalid);
+        else
+            emit_obs<A, NOBJ, NF, (MODE == 3 ? 0 : MODE)>(e, in, valid, p, tb, wrows, lane,
+                                                          reinterpret_cast<float*>(obs) + (size_t)env0 * p.row_bytes, nvalid);
+    }
     rows_wait_done(p);
 }
 
@@ -152,11 +252,16 @@ __global__ void oc_state_export_kernel(const uint4* __restrict__ planes, uint32_
     const int env = i >> 2, pl = i & 3;
     reinterpret_cast<uint4*>(rows)[(size_t)env * 4 + pl] = planes[(size_t)pl * E + env];
 }
-__global__ void oc_state_import_kernel(uint4* __restrict__ planes, const uint32_t* __restrict__ rows, int E) {
+// imported state is sanitised on the way in (a checkpoint of another level must not drive the table look-ups out
+// of the CTA's shared memory): agent cells and live object cells are clamped to the grid, holders to {agents, none},
+// empty slots become the canonical dead word
+__global__ void oc_state_import_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ planes,
+                                       const uint32_t* __restrict__ rows, int E) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= E * 4) return;
     const int env = i >> 2, pl = i & 3;
-    planes[(size_t)pl * E + env] = reinterpret_cast<const uint4*>(rows)[(size_t)env * 4 + pl];
+    const uint4 v = sanitize_state_plane(p, pl, reinterpret_cast<const uint4*>(rows)[(size_t)env * 4 + pl]);
+    planes[(size_t)pl * E + env] = v;
 }
 __global__ void oc_stats_kernel(const uint4* __restrict__ planes, uint32_t* __restrict__ episodes,
                                 uint32_t* __restrict__ last_completed, int E) {
@@ -182,6 +287,19 @@ oc_gather_term_kernel(const __grid_constant__ OcParams p, const float* __restric
         gather_term_row(p, term, idx[i], i, out_f32, out_i8, out_ts, (int)threadIdx.x, (int)blockDim.x);
 }
 
+// compact terminal rows of the n finished envs idx[0..n) -> dense [n, A*(F-1)] bytes + [n] clocks (staged host path
+// with pageable caller buffers; page-locked ones are written by the step kernel itself)
+__global__ void __launch_bounds__(128)
+oc_gather_term8_kernel(const uint8_t* __restrict__ term8, const float* __restrict__ term_ts, const int32_t* __restrict__ idx,
+                       int n, int row8, uint8_t* __restrict__ out8, float* __restrict__ out_ts) {
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint8_t* src = term8 + (size_t)idx[i] * row8;
+        uint8_t* dst = out8 + (size_t)i * row8;
+        for (int j = threadIdx.x; j < row8; j += blockDim.x) dst[j] = src[j];
+        if (threadIdx.x == 0) out_ts[i] = term_ts[idx[i]];
+    }
+}
+
 // =============================================================================================
 // host side
 // =============================================================================================
@@ -194,11 +312,21 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
             return fail(OC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
     } while (0)
 
-struct oc_env {
+// one kernel configuration of a handle: parameter block + CTA shape
+struct LaunchCfg {
     OcParams p;
+    int threads = 64;
+    size_t smem_bytes = 0;
+    int step_grid = 1;
+    bool ok = false;
+};
+
+struct oc_env {
+    OcParams p;               // float rows (kernel MODE 0-2); == f.p
     int device = 0;
     int threads = 64;
     size_t smem_bytes = 0;
+    LaunchCfg c;              // compact int8 rows (kernel MODE 3); c.ok false when the rows are too wide for one pass
     uint4* state = nullptr;
     uint8_t* blob = nullptr;
     float* ts = nullptr;
@@ -207,19 +335,24 @@ struct oc_env {
     int pdl = 1;
     int tma_rows_in_step = 1;
     int step_grid = 1;
+    int zero_copy = 1;        // OC_HOST_ZEROCOPY: page-locked caller buffers are read / written by the kernels directly where that pays
     int obs_off[OC_NUM_OBS_KEYS], obs_size[OC_NUM_OBS_KEYS];
-    // device-side staging of the host-buffer entry points (oc_step_host / oc_reset_host), allocated on first use
+    // device-side staging of the host-buffer entry points (oc_step_host* / oc_reset_host*), allocated on first use
     struct HostPath {
         int32_t* actions = nullptr; float* obs = nullptr; float* rew32 = nullptr; double* rew64 = nullptr;
         uint8_t* done = nullptr; float* term = nullptr; uint8_t* mask = nullptr; int32_t* place = nullptr;
         int8_t* obs8 = nullptr; float* ts = nullptr;          // compact format (oc_*_host_i8)
+        uint8_t* term8 = nullptr; float* term_ts = nullptr;   // compact terminal rows [E, A*(F-1)] + [E]
+        uint8_t* block = nullptr; uint8_t* actions8 = nullptr; // oc_*_host_block: one staging block, u8 actions
+        uint32_t* state_rows = nullptr;                        // oc_get_state_host / oc_set_state_host
         // terminal rows: indices of the finished envs (host -> device), their rows gathered densely (device -> host)
         int32_t* idx = nullptr; float* gather = nullptr; float* gather_ts = nullptr;
         int32_t* h_idx = nullptr; float* h_gather = nullptr; float* h_gather_ts = nullptr;   // pinned
     } hp;
 };
 
-// kernel template MODE: 0 byte rows, 1 float rows (all 32 envs of a warp in one pass), 2 float rows in passes
+// kernel template MODE: 0 byte rows, 1 float rows (all 32 envs of a warp in one pass), 2 float rows in passes,
+// 3 compact int8 rows (step / reset kernels only)
 static int row_mode(const OcParams& p) { return !p.rowf ? 0 : (p.obs_passes > 1 ? 2 : 1); }
 
 template <int N, int NFOOD> constexpr int shape_nobj(std::integer_sequence<int, N, NFOOD>) { return N; }
@@ -241,9 +374,47 @@ static int dispatch(int A, int NOBJ, int mode, F&& f) {
 #undef OC_CASE
     return fail(OC_ERR_INVALID, "unsupported (num_agents, num_objects)");
 }
+// the compact-row instantiations (MODE 3) exist for the step and reset kernels only
+template <typename F>
+static int dispatch_shape(int A, int NOBJ, F&& f) {
+#define OC_CASE(a, n, nfood)                                                                                            \
+    if (A == a && NOBJ == n) return f(std::integral_constant<int, a>(), std::integer_sequence<int, n, nfood>());
+    OC_CASE(2, 2, 1) OC_CASE(3, 2, 1) OC_CASE(4, 2, 1) OC_CASE(2, 4, 2) OC_CASE(3, 4, 2) OC_CASE(4, 4, 2)
+    OC_CASE(2, 6, 3) OC_CASE(3, 6, 3) OC_CASE(4, 6, 3)
+#undef OC_CASE
+    return fail(OC_ERR_INVALID, "unsupported (num_agents, num_objects)");
+}
 
 extern "C" int oc_abi_version(void) { return OC_ABI_VERSION; }
+#ifdef OC_PHASE_PROBE
+extern "C" int oc_debug_set_probe(unsigned long long* dev_buf) {      // [grid * 8 warps * 16] u64, or NULL
+    CUDA_TRY(cudaMemcpyToSymbol(g_probe, &dev_buf, sizeof(dev_buf)));
+    return OC_OK;
+}
+#endif
 extern "C" const char* oc_last_error(void) { return g_err.c_str(); }
+
+// CTA shape: the work is one warp per 32 envs; pick the CTA size whose resident wave covers the envs with the
+// smallest makespan, preferring fewer table copies on ties.  caps[t / 32] = resident CTAs of t threads per SM.
+static bool pick_cta(const OcParams& p, const int* caps, int num_sm, double want_warps, const char* tenv,
+                     int& best_t, int& best_cap) {
+    best_t = 0; best_cap = 1;
+    double best_cost = 1e30;
+    for (int t = 32; t <= 256; t += 32) {
+        if (tenv && atoi(tenv) != t) continue;
+        const int cap = caps[t / 32];
+        if (cap < 1) continue;
+        const long long ctas = ((long long)p.E + t - 1) / t;
+        const long long per_sm = (ctas + num_sm - 1) / num_sm;              // CTAs of work on the busiest SM
+        const double conc = (double)std::min<long long>(per_sm, cap) * (t / 32); // warps resident together
+        const double eff = std::min(1.0, conc / want_warps);
+        double cost = (double)per_sm * (t / 32) / eff + 1e-3 * (double)(256 - t) / 256.0;
+        // several waves through ONE resident CTA per SM: the SM idles while each new CTA loads its tables
+        if (per_sm > cap && cap < 2) cost *= 1.25;
+        if (cost < best_cost) { best_cost = cost; best_t = t; best_cap = cap; }
+    }
+    return best_t != 0;
+}
 
 extern "C" int oc_create(const oc_config* c, oc_env** out) {
     if (!c || !out) return fail(OC_ERR_INVALID, "null argument");
@@ -268,6 +439,7 @@ extern "C" int oc_create(const oc_config* c, oc_env** out) {
 
     if (const char* pe = getenv("OC_PDL")) h->pdl = atoi(pe) != 0;
     if (const char* te = getenv("OC_TMA")) h->tma_rows_in_step = atoi(te) != 0;
+    if (const char* ze = getenv("OC_HOST_ZEROCOPY")) h->zero_copy = atoi(ze) != 0;
     cudaDeviceProp prop;
     {
         cudaError_t cep = cudaGetDeviceProperties(&prop, dev);
@@ -275,14 +447,20 @@ extern "C" int oc_create(const oc_config* c, oc_env** out) {
     }
     const int num_sm = prop.multiProcessorCount;
     const size_t smem_cta_max = prop.sharedMemPerBlockOptin;
-    auto smem_for = [&](int threads) { return (size_t)p.blob_bytes + (size_t)(threads / 32) * (size_t)p.warp_row_bytes; };
+
+    // compact-row configuration (MODE 3): the same parameter block with byte rows of A * (F-1), contiguous, one pass
+    OcParams& p8 = h->c.p;
+    p8 = p;
+    make_compact_params(p8);
+    const bool want8 = p8.warp_row_bytes <= 64 * 1024 && p.off_ts == p.F - 1;
 
     // opt in to large dynamic shared memory for the instantiations we launch.  The attribute is per
     // function, not per handle, so it is always set to the device maximum: a second handle with a
     // smaller footprint must not lower it under the first one's feet.  Then ask the runtime how many
     // CTAs of each candidate size are resident per SM (shared memory AND registers).
-    const int smem_optin = (int)smem_cta_max;
-    int caps[9] = {0};
+    const int smem_optin = (int)smem_cta_max - 1024;      // the kernels keep a few static words (mbarrier)
+    auto smem_for = [&](const OcParams& q, int threads) { return (size_t)q.blob_bytes + (size_t)(threads / 32) * (size_t)q.warp_row_bytes; };
+    int caps[9] = {0}, caps8[9] = {0};
     int rc = dispatch(p.A, p.NOBJ, row_mode(p), [&](auto a, auto nobj, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = shape_nobj(nobj), FF = shape_nf(nobj);
         constexpr int RF = decltype(rf)::value;
@@ -290,40 +468,44 @@ extern "C" int oc_create(const oc_config* c, oc_env** out) {
         CUDA_TRY(cudaFuncSetAttribute(oc_rollout_kernel<AA, NN, FF, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
         CUDA_TRY(cudaFuncSetAttribute(oc_reset_kernel<AA, NN, FF, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
         for (int t = 32; t <= 256; t += 32) {
-            if (smem_for(t) > smem_cta_max) continue;
+            if (smem_for(p, t) > (size_t)smem_optin) continue;
             int cs = 0, cr = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cs, oc_step_kernel<AA, NN, FF, RF>, t, smem_for(t)));
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cr, oc_rollout_kernel<AA, NN, FF, RF>, t, smem_for(t)));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cs, oc_step_kernel<AA, NN, FF, RF>, t, smem_for(p, t)));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cr, oc_rollout_kernel<AA, NN, FF, RF>, t, smem_for(p, t)));
             caps[t / 32] = std::min(cs, cr);
+        }
+        return OC_OK;
+    });
+    if (rc == OC_OK && want8) rc = dispatch_shape(p.A, p.NOBJ, [&](auto a, auto nobj) -> int {
+        constexpr int AA = decltype(a)::value, NN = shape_nobj(nobj), FF = shape_nf(nobj);
+        CUDA_TRY(cudaFuncSetAttribute(oc_step_kernel<AA, NN, FF, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(oc_reset_kernel<AA, NN, FF, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+        for (int t = 32; t <= 256; t += 32) {
+            if (smem_for(p8, t) > (size_t)smem_optin) continue;
+            int cs = 0, cr = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cs, oc_step_kernel<AA, NN, FF, 3>, t, smem_for(p8, t)));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cr, oc_reset_kernel<AA, NN, FF, 3>, t, smem_for(p8, t)));
+            caps8[t / 32] = std::min(cs, cr);
         }
         return OC_OK;
     });
     if (rc != OC_OK) { std::string m = g_err; delete h; return fail(rc, m); }
 
-    // CTA shape: the work is one warp per 32 envs; pick the CTA size whose resident wave covers the
-    // envs with the smallest makespan, preferring fewer table copies on ties.
     const char* tenv = getenv("OC_BLOCK_THREADS");
     // resident warps per SM that hide the latencies: byte rows run LDS -> convert -> STG chains, float rows
     // leave through the copy engine, multi-pass float rows wait on it most of the time
     const double want_warps = !p.rowf ? 24.0 : (p.obs_passes > 1 ? 6.0 : 14.0);
-    int best_t = 0, best_cap = 1; double best_cost = 1e30;
-    for (int t = 32; t <= 256; t += 32) {
-        if (tenv && atoi(tenv) != t) continue;
-        const int cap = caps[t / 32];
-        if (cap < 1) continue;
-        const long long ctas = ((long long)p.E + t - 1) / t;
-        const long long per_sm = (ctas + num_sm - 1) / num_sm;              // CTAs of work on the busiest SM
-        const double conc = (double)std::min<long long>(per_sm, cap) * (t / 32); // warps resident together
-        const double eff = std::min(1.0, conc / want_warps);
-        double cost = (double)per_sm * (t / 32) / eff + 1e-3 * (double)(256 - t) / 256.0;
-        // several waves through ONE resident CTA per SM: the SM idles while each new CTA loads its tables
-        if (per_sm > cap && cap < 2) cost *= 1.25;
-        if (cost < best_cost) { best_cost = cost; best_t = t; best_cap = cap; }
-    }
-    if (best_t == 0) { delete h; return fail(OC_ERR_INVALID, "observation row too wide for shared memory"); }
+    int best_t = 0, best_cap = 1;
+    if (!pick_cta(p, caps, num_sm, want_warps, tenv, best_t, best_cap)) { delete h; return fail(OC_ERR_INVALID, "observation row too wide for shared memory"); }
     h->threads = best_t;
-    h->smem_bytes = smem_for(best_t);
+    h->smem_bytes = smem_for(p, best_t);
     h->step_grid = (int)std::min<long long>(((long long)p.E + best_t - 1) / best_t, (long long)num_sm * best_cap);
+    if (want8 && pick_cta(p8, caps8, num_sm, 32.0, getenv("OC_BLOCK_THREADS_I8"), best_t, best_cap)) {
+        h->c.threads = best_t;
+        h->c.smem_bytes = smem_for(p8, best_t);
+        h->c.step_grid = (int)std::min<long long>(((long long)p.E + best_t - 1) / best_t, (long long)num_sm * best_cap);
+        h->c.ok = true;
+    }
 
     cudaError_t ce;
     if ((ce = cudaMalloc(&h->state, (size_t)p.E * 64)) != cudaSuccess ||
@@ -336,12 +518,13 @@ extern "C" int oc_create(const oc_config* c, oc_env** out) {
         return fail(ce == cudaErrorMemoryAllocation ? OC_ERR_ALLOC : OC_ERR_CUDA, m);
     }
     p.blob = h->blob; p.ts_table = h->ts;
+    p8.blob = h->blob; p8.ts_table = h->ts;
 
     rc = dispatch(p.A, p.NOBJ, row_mode(p), [&](auto a, auto nobj, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = shape_nobj(nobj), FF = shape_nf(nobj);
         constexpr int RF = decltype(rf)::value;
         const int grid = (p.E + h->threads - 1) / h->threads;
-        oc_reset_kernel<AA, NN, FF, RF><<<grid, h->threads, h->smem_bytes, 0>>>(p, h->state, nullptr, nullptr, nullptr, 1);
+        oc_reset_kernel<AA, NN, FF, RF><<<grid, h->threads, h->smem_bytes, 0>>>(p, h->state, nullptr, nullptr, nullptr, nullptr, 1);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaDeviceSynchronize());
         return OC_OK;
@@ -359,7 +542,8 @@ extern "C" int oc_destroy(oc_env* h) {
     if (h->ts) cudaFree(h->ts);
     for (void* q : {(void*)h->hp.actions, (void*)h->hp.obs, (void*)h->hp.rew32, (void*)h->hp.rew64, (void*)h->hp.done,
                     (void*)h->hp.term, (void*)h->hp.mask, (void*)h->hp.place, (void*)h->hp.obs8, (void*)h->hp.ts,
-                    (void*)h->hp.idx, (void*)h->hp.gather, (void*)h->hp.gather_ts})
+                    (void*)h->hp.term8, (void*)h->hp.term_ts, (void*)h->hp.block, (void*)h->hp.actions8,
+                    (void*)h->hp.state_rows, (void*)h->hp.idx, (void*)h->hp.gather, (void*)h->hp.gather_ts})
         if (q) cudaFree(q);
     for (void* q : {(void*)h->hp.h_idx, (void*)h->hp.h_gather, (void*)h->hp.h_gather_ts})
         if (q) cudaFreeHost(q);
@@ -368,6 +552,8 @@ extern "C" int oc_destroy(oc_env* h) {
 }
 
 extern "C" int oc_obs_width(const oc_env* h) { return h ? h->p.F : OC_ERR_INVALID; }
+
+extern "C" int oc_compact_supported(const oc_env* h) { return (h && h->c.ok) ? 1 : 0; }
 
 extern "C" int oc_obs_layout(const oc_env* h, int32_t* offsets, int32_t* sizes) {
     if (!h || !offsets || !sizes) return fail(OC_ERR_INVALID, "null argument");
@@ -386,16 +572,25 @@ static int check_device(const oc_env* h) {
     return OC_OK;
 }
 
-extern "C" int oc_reset(oc_env* h, const uint8_t* mask, const int32_t* placements, float* obs, void* stream) {
-    if (!h) return fail(OC_ERR_INVALID, "null handle");
-    if (obs && misaligned16(obs)) return fail(OC_ERR_INVALID, "obs must be 16-byte aligned");
-    if (int dc = check_device(h)) return dc;
-    const OcParams& p = h->p;
-    int rc = dispatch(p.A, p.NOBJ, row_mode(p), [&](auto a, auto nobj, auto rf) -> int {
+// ---- launches ------------------------------------------------------------------------------------------------
+// compact = kernel MODE 3 (obs int8 [E, A, F-1] + ts f32 [E]); otherwise float rows
+static int launch_reset(oc_env* h, bool compact, const uint8_t* mask, const int32_t* placements, void* obs, float* ts,
+                        cudaStream_t st) {
+    const OcParams& p = compact ? h->c.p : h->p;
+    const int threads = compact ? h->c.threads : h->threads;
+    const size_t smem = compact ? h->c.smem_bytes : h->smem_bytes;
+    const int grid = (p.E + threads - 1) / threads;
+    int rc;
+    if (compact) rc = dispatch_shape(p.A, p.NOBJ, [&](auto a, auto nobj) -> int {
+        constexpr int AA = decltype(a)::value, NN = shape_nobj(nobj), FF = shape_nf(nobj);
+        oc_reset_kernel<AA, NN, FF, 3><<<grid, threads, smem, st>>>(p, h->state, mask, placements, obs, ts, 0);
+        CUDA_TRY(cudaGetLastError());
+        return OC_OK;
+    });
+    else rc = dispatch(p.A, p.NOBJ, row_mode(p), [&](auto a, auto nobj, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = shape_nobj(nobj), FF = shape_nf(nobj);
         constexpr int RF = decltype(rf)::value;
-        const int grid = (p.E + h->threads - 1) / h->threads;
-        oc_reset_kernel<AA, NN, FF, RF><<<grid, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(p, h->state, mask, placements, obs, 0);
+        oc_reset_kernel<AA, NN, FF, RF><<<grid, threads, smem, st>>>(p, h->state, mask, placements, obs, ts, 0);
         CUDA_TRY(cudaGetLastError());
         return OC_OK;
     });
@@ -403,32 +598,74 @@ extern "C" int oc_reset(oc_env* h, const uint8_t* mask, const int32_t* placement
     return rc;
 }
 
-extern "C" int oc_step(oc_env* h, const int32_t* actions, float* obs, float* rew_f32, double* rew_f64,
-                       uint8_t* done, float* term_obs, uint32_t flags, void* stream) {
-    if (!h || !actions || !obs || !done) return fail(OC_ERR_INVALID, "null argument");
-    if (misaligned16(obs) || (reinterpret_cast<uintptr_t>(actions) & 7)) return fail(OC_ERR_INVALID, "obs must be 16-byte and actions 8-byte aligned");
-    if (int dc = check_device(h)) return dc;
-    const OcParams& p = h->p;
-    int rc = dispatch(p.A, p.NOBJ, row_mode(p), [&](auto a, auto nobj, auto rf) -> int {
+static int launch_step(oc_env* h, bool compact, StepIO io, cudaStream_t st) {
+    const OcParams& p = compact ? h->c.p : h->p;
+    if (io.env_hi <= 0) { io.env_lo = 0; io.env_hi = p.E; }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(compact ? h->c.step_grid : h->step_grid);
+    cfg.blockDim = dim3(compact ? h->c.threads : h->threads);
+    cfg.dynamicSmemBytes = compact ? h->c.smem_bytes : h->smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = h->pdl ? 1 : 0;
+    OcParams ps = p;
+    if (!compact && ps.rowf && !ps.use_tma && h->tma_rows_in_step) ps.use_tma = 2;      // padded float rows: per-row bulk copies
+    int rc;
+    if (compact) rc = dispatch_shape(p.A, p.NOBJ, [&](auto a, auto nobj) -> int {
+        constexpr int AA = decltype(a)::value, NN = shape_nobj(nobj), FF = shape_nf(nobj);
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, oc_step_kernel<AA, NN, FF, 3>, ps, h->state, io));
+        return OC_OK;
+    });
+    else rc = dispatch(p.A, p.NOBJ, row_mode(p), [&](auto a, auto nobj, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = shape_nobj(nobj), FF = shape_nf(nobj);
         constexpr int RF = decltype(rf)::value;
-        const int grid = h->step_grid;
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(h->threads);
-        cfg.dynamicSmemBytes = h->smem_bytes; cfg.stream = (cudaStream_t)stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr; cfg.numAttrs = h->pdl ? 1 : 0;
-        OcParams ps = p;
-        if (ps.rowf && !ps.use_tma && h->tma_rows_in_step) ps.use_tma = 2;      // padded float rows: per-row bulk copies
-        CUDA_TRY(cudaLaunchKernelEx(&cfg, oc_step_kernel<AA, NN, FF, RF>, ps, h->state, actions, obs, rew_f32, rew_f64,
-                                    done, term_obs, flags));
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, oc_step_kernel<AA, NN, FF, RF>, ps, h->state, io));
         return OC_OK;
     });
     if (rc == OC_OK) h->launches += 1;
     return rc;
+}
+
+extern "C" int oc_reset(oc_env* h, const uint8_t* mask, const int32_t* placements, float* obs, void* stream) {
+    if (!h) return fail(OC_ERR_INVALID, "null handle");
+    if (obs && misaligned16(obs)) return fail(OC_ERR_INVALID, "obs must be 16-byte aligned");
+    if (int dc = check_device(h)) return dc;
+    return launch_reset(h, false, mask, placements, obs, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int oc_reset_i8(oc_env* h, const uint8_t* mask, const int32_t* placements, int8_t* obs_i8, float* timestep,
+                           void* stream) {
+    if (!h) return fail(OC_ERR_INVALID, "null handle");
+    if (!h->c.ok) return fail(OC_ERR_INVALID, "observation rows too wide for the compact format kernels; use oc_reset + oc_pack_obs_i8");
+    if (obs_i8 && misaligned16(obs_i8)) return fail(OC_ERR_INVALID, "obs_i8 must be 16-byte aligned");
+    if (int dc = check_device(h)) return dc;
+    return launch_reset(h, true, mask, placements, obs_i8, timestep, (cudaStream_t)stream);
+}
+
+extern "C" int oc_step(oc_env* h, const int32_t* actions, float* obs, float* rew_f32, double* rew_f64,
+                       uint8_t* done, float* term_obs, uint32_t flags, void* stream) {
+    if (!h || !actions || !obs || !done) return fail(OC_ERR_INVALID, "null argument");
+    if (misaligned16(obs) || (reinterpret_cast<uintptr_t>(actions) & 7)) return fail(OC_ERR_INVALID, "obs must be 16-byte and actions 8-byte aligned");
+    if (flags & ~OC_FLAG_AUTO_RESET) return fail(OC_ERR_INVALID, "oc_step takes OC_FLAG_AUTO_RESET only");
+    if (int dc = check_device(h)) return dc;
+    StepIO io{actions, obs, nullptr, rew_f32, rew_f64, done, term_obs, nullptr, flags, 0, h->p.E};
+    return launch_step(h, false, io, (cudaStream_t)stream);
+}
+
+extern "C" int oc_step_i8(oc_env* h, const void* actions, int8_t* obs_i8, float* timestep, float* rew_f32, double* rew_f64,
+                          uint8_t* done, int8_t* term_obs_i8, float* term_timestep, uint32_t flags, void* stream) {
+    if (!h || !actions || !obs_i8 || !done) return fail(OC_ERR_INVALID, "null argument");
+    if (!h->c.ok) return fail(OC_ERR_INVALID, "observation rows too wide for the compact format kernels; use oc_step + oc_pack_obs_i8");
+    if (misaligned16(obs_i8)) return fail(OC_ERR_INVALID, "obs_i8 must be 16-byte aligned");
+    if (!(flags & OC_FLAG_ACTIONS_U8) && (reinterpret_cast<uintptr_t>(actions) & 7)) return fail(OC_ERR_INVALID, "int32 actions must be 8-byte aligned");
+    if ((flags & OC_FLAG_ACTIONS_U8) && (reinterpret_cast<uintptr_t>(actions) & 1)) return fail(OC_ERR_INVALID, "u8 actions must be 2-byte aligned");
+    if (flags & ~(OC_FLAG_AUTO_RESET | OC_FLAG_ACTIONS_U8 | OC_FLAG_REWARD_PER_ENV)) return fail(OC_ERR_INVALID, "unknown flag");
+    if (int dc = check_device(h)) return dc;
+    StepIO io{actions, obs_i8, timestep, rew_f32, rew_f64, done, term_obs_i8, term_timestep, flags, 0, h->p.E};
+    return launch_step(h, true, io, (cudaStream_t)stream);
 }
 
 static int launch_rollout(oc_env* h, int32_t n_steps, float* obs, float* rew_f32, uint8_t* done,
@@ -481,7 +718,7 @@ extern "C" int oc_set_state(oc_env* h, const uint32_t* state, void* stream) {
     if (misaligned16(state)) return fail(OC_ERR_INVALID, "state must be 16-byte aligned");
     if (int dc = check_device(h)) return dc;
     const int n = h->p.E * 4;
-    oc_state_import_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->state, state, h->p.E);
+    oc_state_import_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->p, h->state, state, h->p.E);
     CUDA_TRY(cudaGetLastError());
     h->launches += 1;
     return OC_OK;
@@ -497,6 +734,12 @@ extern "C" int oc_get_stats(oc_env* h, uint32_t* episodes, uint32_t* last_comple
 }
 
 extern "C" uint64_t oc_launch_count(const oc_env* h) { return h ? h->launches : 0; }
+
+extern "C" int oc_sync(oc_env* h, void* stream) {
+    if (!h) return fail(OC_ERR_INVALID, "null handle");
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return OC_OK;
+}
 
 // ---- host-buffer entry points: what a caller without device memory of its own (numpy, SB3 on the CPU) binds
 
@@ -534,6 +777,39 @@ static int ensure_host(T*& ptr, size_t count) {
     return OC_OK;
 }
 
+// Page-locked host memory (oc_host_alloc / cudaHostAlloc / cudaHostRegister) is addressable from the device under
+// unified virtual addressing: returns the device alias of `ptr`, or nullptr for pageable memory.
+template <typename T>
+static T* device_alias(T* ptr) {
+    if (!ptr) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, (const void*)ptr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) return nullptr;
+    return (T*)at.devicePointer;
+}
+
+extern "C" int oc_get_state_host(oc_env* h, uint32_t* state, void* stream) {
+    if (!h || !state) return fail(OC_ERR_INVALID, "null argument");
+    int rc;
+    const size_t n = (size_t)h->p.E * OC_STATE_WORDS;
+    if ((rc = ensure_dev(h->hp.state_rows, n))) return rc;
+    if ((rc = oc_get_state(h, h->hp.state_rows, stream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(state, h->hp.state_rows, n * 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return OC_OK;
+}
+
+extern "C" int oc_set_state_host(oc_env* h, const uint32_t* state, void* stream) {
+    if (!h || !state) return fail(OC_ERR_INVALID, "null argument");
+    int rc;
+    const size_t n = (size_t)h->p.E * OC_STATE_WORDS;
+    if ((rc = ensure_dev(h->hp.state_rows, n))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h->hp.state_rows, state, n * 4, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    if ((rc = oc_set_state(h, h->hp.state_rows, stream))) return rc;
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return OC_OK;
+}
+
 // device-side repack of float rows into the compact integer format (also usable on its own)
 extern "C" int oc_pack_obs_i8(oc_env* h, const float* obs, int8_t* obs_i8, float* timestep, void* stream) {
     if (!h || !obs || !obs_i8) return fail(OC_ERR_INVALID, "null argument");
@@ -567,65 +843,100 @@ static int reset_host_impl(oc_env* h, const uint8_t* mask, const int32_t* placem
         if ((rc = ensure_dev(h->hp.place, E * p.nrandom))) return rc;
         CUDA_TRY(cudaMemcpyAsync(h->hp.place, placements, E * p.nrandom * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     }
-    if (obs && (rc = ensure_dev(h->hp.obs, E * row))) return rc;
-    if (obs && i8 && ((rc = ensure_dev(h->hp.obs8, E * row8 + 4)) || (rc = ensure_dev(h->hp.ts, E)))) return rc;
-    if ((rc = oc_reset(h, mask ? h->hp.mask : nullptr, (placements && p.nrandom > 0) ? h->hp.place : nullptr,
-                       obs ? h->hp.obs : nullptr, stream))) return rc;
+    const uint8_t* dmask = mask ? h->hp.mask : nullptr;
+    const int32_t* dplace = (placements && p.nrandom > 0) ? h->hp.place : nullptr;
     if (obs && i8) {
-        if ((rc = oc_pack_obs_i8(h, h->hp.obs, h->hp.obs8, h->hp.ts, stream))) return rc;
+        if ((rc = ensure_dev(h->hp.obs8, E * row8 + 16)) || (rc = ensure_dev(h->hp.ts, E))) return rc;
+        if (h->c.ok) {                                  // the reset kernel emits the compact rows itself
+            if ((rc = launch_reset(h, true, dmask, dplace, h->hp.obs8, h->hp.ts, st))) return rc;
+        } else {
+            if ((rc = ensure_dev(h->hp.obs, E * row))) return rc;
+            if ((rc = launch_reset(h, false, dmask, dplace, h->hp.obs, nullptr, st))) return rc;
+            if ((rc = oc_pack_obs_i8(h, h->hp.obs, h->hp.obs8, h->hp.ts, stream))) return rc;
+        }
         CUDA_TRY(cudaMemcpyAsync(obs, h->hp.obs8, E * row8, cudaMemcpyDeviceToHost, st));
         if (ts) CUDA_TRY(cudaMemcpyAsync(ts, h->hp.ts, E * sizeof(float), cudaMemcpyDeviceToHost, st));
-    } else if (obs) {
-        CUDA_TRY(cudaMemcpyAsync(obs, h->hp.obs, E * row * sizeof(float), cudaMemcpyDeviceToHost, st));
+    } else {
+        if (obs && (rc = ensure_dev(h->hp.obs, E * row))) return rc;
+        if ((rc = launch_reset(h, false, dmask, dplace, obs ? h->hp.obs : nullptr, nullptr, st))) return rc;
+        if (obs) CUDA_TRY(cudaMemcpyAsync(obs, h->hp.obs, E * row * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     return OC_OK;
 }
 
+// indices of the set flags of a host done buffer -> h_idx; finished envs are rare, eight clear flags are skipped at a time
+static size_t scan_done(const uint8_t* done, size_t E, int32_t* h_idx) {
+    size_t nfin = 0, e = 0;
+    for (; e + 8 <= E; e += 8) {
+        uint64_t w8;
+        memcpy(&w8, done + e, 8);
+        if (w8 == 0) continue;
+        for (size_t k = e; k < e + 8; ++k)
+            if (done[k]) h_idx[nfin++] = (int32_t)k;
+    }
+    for (; e < E; ++e)
+        if (done[e]) h_idx[nfin++] = (int32_t)e;
+    return nfin;
+}
+
 static int step_host_impl(oc_env* h, const int32_t* actions, void* obs, float* ts, float* rew_f32, double* rew_f64,
                           uint8_t* done, void* term_obs, float* term_ts, bool i8, uint32_t flags, void* stream) {
     if (!h || !actions || !obs || !done) return fail(OC_ERR_INVALID, "null argument");
+    if (flags & ~OC_FLAG_AUTO_RESET) return fail(OC_ERR_INVALID, "the host entry points take OC_FLAG_AUTO_RESET only");
     if (int dc = check_device(h)) return dc;
     const OcParams& p = h->p;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t E = (size_t)p.E, A = (size_t)p.A, row = (size_t)p.row_bytes, row8 = A * (size_t)(p.F - 1);
+    const bool direct8 = i8 && h->c.ok;                // the step kernel emits the compact rows itself (MODE 3)
     int rc;
-    if ((rc = ensure_dev(h->hp.actions, E * A * 2)) || (rc = ensure_dev(h->hp.obs, E * row)) ||
-        (rc = ensure_dev(h->hp.done, E))) return rc;
-    if (i8 && ((rc = ensure_dev(h->hp.obs8, E * row8 + 4)) || (rc = ensure_dev(h->hp.ts, E)))) return rc;
+    if ((rc = ensure_dev(h->hp.actions, E * A * 2)) || (rc = ensure_dev(h->hp.done, E))) return rc;
+    if (!direct8 && (rc = ensure_dev(h->hp.obs, E * row))) return rc;
+    if (i8 && ((rc = ensure_dev(h->hp.obs8, E * row8 + 16)) || (rc = ensure_dev(h->hp.ts, E)))) return rc;
     if (rew_f32 && (rc = ensure_dev(h->hp.rew32, E * A))) return rc;
     if (rew_f64 && (rc = ensure_dev(h->hp.rew64, E))) return rc;
     const bool want_term = term_obs != nullptr && (flags & OC_FLAG_AUTO_RESET);
-    if (want_term && !h->hp.term) {                    // rows of envs that never finished stay zero
-        if ((rc = ensure_dev(h->hp.term, E * row))) return rc;
-        CUDA_TRY(cudaMemsetAsync(h->hp.term, 0, E * row * sizeof(float), st));
+    // compact terminal rows into page-locked caller buffers: the kernel writes the few finished rows across PCIe itself
+    int8_t* term8_alias = (want_term && direct8 && h->zero_copy) ? device_alias((int8_t*)term_obs) : nullptr;
+    float* term_ts_alias = term8_alias ? device_alias(term_ts) : nullptr;
+    const bool term_direct = term8_alias != nullptr && (term_ts == nullptr || term_ts_alias != nullptr);
+    if (want_term && !term_direct) {                   // device-side terminal buffer; rows of envs that never finished stay zero
+        if (direct8) {
+            if (!h->hp.term8) {
+                if ((rc = ensure_dev(h->hp.term8, E * row8)) || (rc = ensure_dev(h->hp.term_ts, E))) return rc;
+                CUDA_TRY(cudaMemsetAsync(h->hp.term8, 0, E * row8, st));
+                CUDA_TRY(cudaMemsetAsync(h->hp.term_ts, 0, E * sizeof(float), st));
+            }
+        } else if (!h->hp.term) {
+            if ((rc = ensure_dev(h->hp.term, E * row))) return rc;
+            CUDA_TRY(cudaMemsetAsync(h->hp.term, 0, E * row * sizeof(float), st));
+        }
     }
     CUDA_TRY(cudaMemcpyAsync(h->hp.actions, actions, E * A * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    if ((rc = oc_step(h, h->hp.actions, h->hp.obs, rew_f32 ? h->hp.rew32 : nullptr, rew_f64 ? h->hp.rew64 : nullptr,
-                      h->hp.done, want_term ? h->hp.term : nullptr, flags, stream))) return rc;
+    if (direct8) {
+        StepIO io{h->hp.actions, h->hp.obs8, h->hp.ts, rew_f32 ? h->hp.rew32 : nullptr, rew_f64 ? h->hp.rew64 : nullptr,
+                  h->hp.done, nullptr, nullptr, flags, 0, p.E};
+        if (want_term) { io.term_obs = term_direct ? (void*)term8_alias : (void*)h->hp.term8; io.term_ts = term_direct ? term_ts_alias : h->hp.term_ts; }
+        if ((rc = launch_step(h, true, io, st))) return rc;
+    } else {
+        StepIO io{h->hp.actions, h->hp.obs, nullptr, rew_f32 ? h->hp.rew32 : nullptr, rew_f64 ? h->hp.rew64 : nullptr,
+                  h->hp.done, want_term ? h->hp.term : nullptr, nullptr, flags, 0, p.E};
+        if ((rc = launch_step(h, false, io, st))) return rc;
+    }
     CUDA_TRY(cudaMemcpyAsync(done, h->hp.done, E, cudaMemcpyDeviceToHost, st));
     if (rew_f32) CUDA_TRY(cudaMemcpyAsync(rew_f32, h->hp.rew32, E * A * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (rew_f64) CUDA_TRY(cudaMemcpyAsync(rew_f64, h->hp.rew64, E * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (i8) {
-        if ((rc = oc_pack_obs_i8(h, h->hp.obs, h->hp.obs8, h->hp.ts, stream))) return rc;
+        if (!direct8 && (rc = oc_pack_obs_i8(h, h->hp.obs, h->hp.obs8, h->hp.ts, stream))) return rc;
         CUDA_TRY(cudaMemcpyAsync(obs, h->hp.obs8, E * row8, cudaMemcpyDeviceToHost, st));
         if (ts) CUDA_TRY(cudaMemcpyAsync(ts, h->hp.ts, E * sizeof(float), cudaMemcpyDeviceToHost, st));
     } else {
         CUDA_TRY(cudaMemcpyAsync(obs, h->hp.obs, E * row * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     CUDA_TRY(cudaStreamSynchronize(st));
-    if (want_term) {                                   // only the rows of envs that just finished reach the caller's buffer
+    if (want_term && !term_direct) {                   // only the rows of envs that just finished reach the caller's buffer
         if ((rc = ensure_host(h->hp.h_idx, E))) return rc;
-        size_t nfin = 0, e = 0;
-        for (; e + 8 <= E; e += 8) {                   // finished envs are rare: skip eight clear flags at a time
-            uint64_t w8;
-            memcpy(&w8, done + e, 8);
-            if (w8 == 0) continue;
-            for (size_t k = e; k < e + 8; ++k)
-                if (done[k]) h->hp.h_idx[nfin++] = (int32_t)k;
-        }
-        for (; e < E; ++e)
-            if (done[e]) h->hp.h_idx[nfin++] = (int32_t)e;
+        const size_t nfin = scan_done(done, E, h->hp.h_idx);
         if (nfin == 0) return OC_OK;
         // gather them on the device into a dense [nfin, row] buffer (the compact format is packed on the way), one
         // copy to pinned host memory, then row-wise into the caller's (possibly pageable) buffer.  The staging
@@ -635,8 +946,12 @@ static int step_host_impl(oc_env* h, const int32_t* actions, void* obs, float* t
         const size_t rb = i8 ? row8 : row * sizeof(float);                // bytes of one env's rows
         CUDA_TRY(cudaMemcpyAsync(h->hp.idx, h->hp.h_idx, nfin * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         const int grid = (int)std::min<size_t>(nfin, 148 * 16);
-        oc_gather_term_kernel<<<grid, 128, 0, st>>>(p, h->hp.term, h->hp.idx, (int)nfin, i8 ? nullptr : h->hp.gather,
-                                                    i8 ? (int8_t*)h->hp.gather : nullptr, h->hp.gather_ts);
+        if (direct8)
+            oc_gather_term8_kernel<<<grid, 128, 0, st>>>(h->hp.term8, h->hp.term_ts, h->hp.idx, (int)nfin, (int)row8,
+                                                         (uint8_t*)h->hp.gather, h->hp.gather_ts);
+        else
+            oc_gather_term_kernel<<<grid, 128, 0, st>>>(p, h->hp.term, h->hp.idx, (int)nfin, i8 ? nullptr : h->hp.gather,
+                                                        i8 ? (int8_t*)h->hp.gather : nullptr, h->hp.gather_ts);
         CUDA_TRY(cudaGetLastError());
         h->launches += 1;
         CUDA_TRY(cudaMemcpyAsync(h->hp.h_gather, h->hp.gather, nfin * rb, cudaMemcpyDeviceToHost, st));
@@ -668,4 +983,63 @@ extern "C" int oc_step_host_i8(oc_env* h, const int32_t* actions, int8_t* obs_i8
                                double* rew_f64, uint8_t* done, int8_t* term_obs_i8, float* term_timestep,
                                uint32_t flags, void* stream) {
     return step_host_impl(h, actions, obs_i8, timestep, rew_f32, rew_f64, done, term_obs_i8, term_timestep, true, flags, stream);
+}
+
+// ---- one-block host path: a single page-locked block per step ------------------------------------------------
+static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+extern "C" int oc_host_block_layout(const oc_env* h, oc_host_block* out) {
+    if (!h || !out) return fail(OC_ERR_INVALID, "null argument");
+    const size_t E = (size_t)h->p.E, row8 = (size_t)h->p.A * (h->p.F - 1);
+    size_t off = 0;
+    out->obs_i8 = off;   off += align256(E * row8);
+    out->timestep = off; off += align256(E * 4);
+    out->reward = off;   off += align256(E * 4);
+    out->done = off;     off += align256(E);
+    out->total_bytes = off;
+    return OC_OK;
+}
+
+extern "C" int oc_reset_host_block(oc_env* h, const uint8_t* mask, const int32_t* placements, void* block, void* stream) {
+    if (!h || !block) return fail(OC_ERR_INVALID, "null argument");
+    oc_host_block L;
+    oc_host_block_layout(h, &L);
+    uint8_t* b = (uint8_t*)block;
+    return reset_host_impl(h, mask, placements, b + L.obs_i8, (float*)(b + L.timestep), true, stream);
+}
+
+extern "C" int oc_step_host_block(oc_env* h, const uint8_t* actions_u8, void* block, int8_t* term_obs_i8,
+                                  float* term_timestep, uint32_t flags, void* stream) {
+    if (!h || !actions_u8 || !block) return fail(OC_ERR_INVALID, "null argument");
+    if (!h->c.ok) return fail(OC_ERR_INVALID, "observation rows too wide for the compact format kernels; use oc_step_host_i8");
+    if (flags & ~(OC_FLAG_AUTO_RESET | OC_FLAG_NO_SYNC)) return fail(OC_ERR_INVALID, "oc_step_host_block takes OC_FLAG_AUTO_RESET | OC_FLAG_NO_SYNC");
+    if (int dc = check_device(h)) return dc;
+    const OcParams& p = h->p;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t E = (size_t)p.E, A = (size_t)p.A;
+    oc_host_block L;
+    oc_host_block_layout(h, &L);
+    int rc;
+    if ((rc = ensure_dev(h->hp.block, (size_t)L.total_bytes))) return rc;
+    const bool want_term = term_obs_i8 != nullptr && (flags & OC_FLAG_AUTO_RESET);
+    int8_t* term8_alias = want_term ? device_alias(term_obs_i8) : nullptr;
+    float* term_ts_alias = want_term ? device_alias(term_timestep) : nullptr;
+    if (want_term && (!term8_alias || (term_timestep && !term_ts_alias)))
+        return fail(OC_ERR_INVALID, "oc_step_host_block: terminal buffers must be page-locked (oc_host_alloc); pageable callers use oc_step_host_i8");
+    // actions: page-locked u8 pairs are read by the kernel across PCIe (0.26 MB at cfg2: no copy call, no dependent
+    // launch); pageable ones are staged with one copy
+    const uint8_t* act = h->zero_copy ? device_alias(actions_u8) : nullptr;
+    if (!act) {
+        if ((rc = ensure_dev(h->hp.actions8, E * A * 2))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h->hp.actions8, actions_u8, E * A * 2, cudaMemcpyHostToDevice, st));
+        act = h->hp.actions8;
+    }
+    uint8_t* d = h->hp.block;
+    StepIO io{act, d + L.obs_i8, (float*)(d + L.timestep), (float*)(d + L.reward), nullptr, d + L.done,
+              term8_alias, term_ts_alias,
+              (flags & OC_FLAG_AUTO_RESET) | OC_FLAG_ACTIONS_U8 | OC_FLAG_REWARD_PER_ENV, 0, p.E};
+    if ((rc = launch_step(h, true, io, st))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(block, d, (size_t)L.total_bytes, cudaMemcpyDeviceToHost, st));      // ONE copy for everything
+    if (!(flags & OC_FLAG_NO_SYNC)) CUDA_TRY(cudaStreamSynchronize(st));
+    return OC_OK;
 }

@@ -42,15 +42,19 @@ class OvercookedHostVecEnv:
     """E lock-step envs on one GPU, host (numpy) buffers.
 
     ``reset() -> obs [E, A, F] f32``;
-    ``step(actions int32 [E, A, 2]) -> (obs [E, A, F] f32, rewards [E, A] f32, dones [E] bool, infos)``
+    ``step(actions [E, A, 2]) -> (obs [E, A, F] f32, rewards [E, A] f32, dones [E] bool, infos)``
     with SB3's auto-reset contract: for an env that finished, ``obs`` is the first observation of its
     next episode and ``infos[e]["terminal_observation"]`` the last one of the finished episode (a view of
     ``env.terminal_obs[e]``; with very large batches read ``env.terminal_obs`` and ``done`` directly instead
     of walking the list).
-    ``obs_format="i8"`` switches the observation buffers to the compact integer format of
-    `oc_step_host_i8`: ``obs`` is int8 [E, A, F-1] (every key but the clock -- the reference builds these
-    keys as integer arrays, overcooked_env.py:145-157) and the clock is ``env.timestep`` f32 [E] (after a
-    finished episode: ``infos[e]["terminal_timestep"]``); 4x fewer bytes cross PCIe per step.
+    ``obs_format="i8"`` switches to the compact integer format and the ONE-BLOCK host path
+    (`oc_step_host_block`, include/overcooked_b200.h): ``obs`` is int8 [E, A, F-1] (every key but the clock --
+    the reference builds these keys as integer arrays, overcooked_env.py:145-157), the clock is
+    ``env.timestep`` f32 [E] (after a finished episode: ``infos[e]["terminal_timestep"]``), the reward is one
+    f32 per env (``rewards`` is its read-only [E, A] broadcast view; the reference hands both players the same
+    number, overcooked_env.py:282) and the actions cross PCIe as two bytes per agent.  Everything a step returns
+    sits in one page-locked block filled by one device->host copy; the step kernel writes the compact rows
+    itself (no float rows, no repack).
     ``obs_float()`` rebuilds the float rows, ``obs_dict()`` gives the reference's per-key view in both formats.
     The returned arrays (and the `infos` list) are the env's own pinned buffers, overwritten by the next
     call (copy them to keep them, as SB3's rollout buffer does) and invalid after `close()`.
@@ -62,8 +66,7 @@ class OvercookedHostVecEnv:
         self.arglist = normalize(arglist)
         a = self.arglist
         self.lib = lib if lib is not None else _cabi.default_library()
-        if self.lib.prefix != "oc_":
-            raise RuntimeError("OvercookedHostVecEnv needs liboc_b200.so (CUDA); there is no CPU backend")
+        self._require_backend()
         if obs_format not in ("f32", "i8"):
             raise ValueError("obs_format must be 'f32' or 'i8'")
         self.obs_format = obs_format
@@ -79,6 +82,7 @@ class OvercookedHostVecEnv:
         self._handle = C.c_void_p()
         self._pinned = []
         self._closed = False
+        self._pending = None
         self.lib.check(self.lib.set_device(self.device_index), "oc_set_device")
         self.lib.check(self.lib.create(C.byref(cfg), C.byref(self._handle)), "oc_create")
         self.obs_width = self.lib.obs_width(self._handle)
@@ -91,23 +95,60 @@ class OvercookedHostVecEnv:
         i8 = obs_format == "i8"
         if i8 and self.obs_layout["timestep"] != slice(F - 1, F):
             raise RuntimeError("the compact format expects `timestep` to be the last key of a row")
-        odt, Fo = (np.int8, F - 1) if i8 else (np.float32, F)
-        self.obs = self.pinned_array((E, A, Fo), odt)
-        self.timestep = self.pinned_array((E,), np.float32) if i8 else None
-        self.rewards = self.pinned_array((E, A), np.float32)
-        self._dones_padded = self.pinned_array(((E + 7) // 8 * 8,), np.uint8)     # scanned as uint64 words
+        self._block_mode = False
+        if i8:
+            # one page-locked block for everything a step returns, when the handle has the compact-row kernels and
+            # the messages fit a byte; otherwise the older entry points with separate buffers (same values)
+            lay = _cabi.OcHostBlock()
+            self.lib.check(self.lib.host_block_layout(self._handle, C.byref(lay)), "oc_host_block_layout")
+            self._block_mode = a.num_communication <= 256 and self.lib.compact_supported(self._handle) == 1
+        if self._block_mode:
+            self._block = self.pinned_array((int(lay.total_bytes),), np.uint8)
+            self.obs = self._block[lay.obs_i8:lay.obs_i8 + E * A * (F - 1)].view(np.int8).reshape(E, A, F - 1)
+            self.timestep = self._block[lay.timestep:lay.timestep + 4 * E].view(np.float32)
+            self.reward_per_env = self._block[lay.reward:lay.reward + 4 * E].view(np.float32)
+            self.rewards = np.broadcast_to(self.reward_per_env[:, None], (E, A))         # read-only view
+            self._dones_padded = self._block[lay.done:lay.done + (E + 7) // 8 * 8]         # sections are 256-byte padded
+            self.actions_u8 = self.pinned_array((E, A, 2), np.uint8)
+            self.actions = None
+        else:
+            odt, Fo = (np.int8, F - 1) if i8 else (np.float32, F)
+            self.obs = self.pinned_array((E, A, Fo), odt)
+            self.timestep = self.pinned_array((E,), np.float32) if i8 else None
+            self.rewards = self.pinned_array((E, A), np.float32)
+            self.reward_per_env = None
+            self._dones_padded = self.pinned_array(((E + 7) // 8 * 8,), np.uint8)     # scanned as uint64 words
+            self.actions = self.pinned_array((E, A, 2), np.int32)
+            self.actions_u8 = None
         self.dones = self._dones_padded[:E]
-        self.actions = self.pinned_array((E, A, 2), np.int32)
+        odt, Fo = (np.int8, F - 1) if i8 else (np.float32, F)
         self.terminal_obs = self.pinned_array((E, A, Fo), odt) if (terminal_observations and auto_reset) else None
         self.terminal_timestep = self.pinned_array((E,), np.float32) if (i8 and self.terminal_obs is not None) else None
         self._infos = [{} for _ in range(E)]
         self._term_rows = [None] * E
         self._touched = ()
+        # what crosses PCIe per step (bench.py's e2e keys)
+        obs_bytes = self.obs.nbytes + (self.timestep.nbytes if self.timestep is not None else 0)
+        if self._block_mode:
+            self.h2d_bytes_per_step = self.actions_u8.nbytes
+            self.d2h_bytes_per_step = int(lay.total_bytes)
+            self.kernel_launches_per_step = 1
+            self.transfer_desc = ("actions u8 [E,A,2] read by the step kernel from page-locked host memory; ONE device->host "
+                                  "copy of the block obs_i8 | timestep | reward f32 [E] | done; terminal rows written by the kernel")
+        else:
+            self.h2d_bytes_per_step = self.actions.nbytes
+            self.d2h_bytes_per_step = obs_bytes + self.rewards.nbytes + E
+            self.kernel_launches_per_step = 1 if (not i8 or self.lib.compact_supported(self._handle) == 1) else 2
+            self.transfer_desc = "actions int32 [E,A,2] host->device copy; separate device->host copies of obs, reward f32 [E,A], done"
 
     # ------------------------------------------------------------------ plumbing
+    def _require_backend(self):
+        if not isinstance(self.lib, _cabi.OcLibrary):
+            raise RuntimeError("OvercookedHostVecEnv needs liboc_b200.so (CUDA); there is no CPU backend")
+
     def pinned_array(self, shape, dtype) -> np.ndarray:
-        """numpy view of page-locked host memory from oc_host_alloc (freed in close()).  int32
-        [E, A, 2] arrays made here can be passed to `step` directly (no staging copy)."""
+        """numpy view of page-locked host memory from oc_host_alloc (freed in close()).  Arrays made here can be
+        passed to `step` directly (no staging copy)."""
         n = int(np.prod(shape)) * np.dtype(dtype).itemsize
         ptr = C.c_void_p()
         self.lib.check(self.lib.host_alloc(n, C.byref(ptr)), "oc_host_alloc")
@@ -132,7 +173,10 @@ class OvercookedHostVecEnv:
         if placements is not None:
             self._check(placements, (self.num_envs, self.level.num_random), np.int32, "placements")
         self.lib.check(self.lib.set_device(self.device_index), "oc_set_device")
-        if self.obs_format == "i8":
+        if self._block_mode:
+            self.lib.check(self.lib.reset_host_block(self._handle, self._p(mask), self._p(placements), self._p(self._block),
+                                                     None), "oc_reset_host_block")
+        elif self.obs_format == "i8":
             self.lib.check(self.lib.reset_host_i8(self._handle, self._p(mask), self._p(placements), self._p(self.obs),
                                                   self._p(self.timestep), None), "oc_reset_host_i8")
         else:
@@ -140,25 +184,50 @@ class OvercookedHostVecEnv:
                            "oc_reset_host")
         return self.obs
 
-    def step(self, actions: np.ndarray):
+    def _stage_actions(self, actions):
+        """-> the array handed to the C ABI: the caller's own buffer when it already has the wire format (uint8 pairs
+        for the one-block path, int32 pairs otherwise), else the env's pinned buffer after one conversion."""
+        want, buf = (np.uint8, self.actions_u8) if self._block_mode else (np.int32, self.actions)
         a = actions
-        if not (isinstance(a, np.ndarray) and a.dtype == np.int32 and a.flags.c_contiguous and a.shape == self.actions.shape):
-            a = np.asarray(actions)                  # any integer array-like: converted into the env's pinned buffer
-            if a.shape != self.actions.shape:
-                raise ValueError("actions must have shape %s (nav, comm per agent)" % (self.actions.shape,))
-            np.copyto(self.actions, a, casting="same_kind")
-            a = self.actions
+        if isinstance(a, np.ndarray) and a.dtype == want and a.flags.c_contiguous and a.shape == buf.shape:
+            return a
+        a = np.asarray(actions)                      # any integer array-like: converted into the env's pinned buffer
+        if a.shape != buf.shape:
+            raise ValueError("actions must have shape %s (nav, comm per agent)" % (buf.shape,))
+        np.copyto(buf, a, casting="unsafe" if self._block_mode else "same_kind")
+        return buf
+
+    def step_async(self, actions) -> None:
+        """Enqueue the step (upload, kernel, download) and return; `step_wait` waits and builds the results.  On the
+        one-block path the call does not block, so host work can overlap the GPU and the PCIe transfers."""
+        a = self._stage_actions(actions)
         flags = _cabi.OC_FLAG_AUTO_RESET if self.auto_reset else 0
         self.lib.check(self.lib.set_device(self.device_index), "oc_set_device")
-        if self.obs_format == "i8":
-            self.lib.check(self.lib.step_host_i8(self._handle, self._p(a), self._p(self.obs), self._p(self.timestep),
-                                                 self._p(self.rewards), None, self._p(self.dones),
-                                                 self._p(self.terminal_obs), self._p(self.terminal_timestep), flags, None),
-                           "oc_step_host_i8")
+        if self._block_mode:
+            self.lib.check(self.lib.step_host_block(self._handle, self._p(a), self._p(self._block), self._p(self.terminal_obs),
+                                                    self._p(self.terminal_timestep), flags | _cabi.OC_FLAG_NO_SYNC, None),
+                           "oc_step_host_block")
+            self._pending = "block"
         else:
-            self.lib.check(self.lib.step_host(self._handle, self._p(a), self._p(self.obs), self._p(self.rewards),
-                                              None, self._p(self.dones), self._p(self.terminal_obs), flags, None),
-                           "oc_step_host")
+            self._pending = (a, flags)
+
+    def step_wait(self):
+        if self._pending is None:
+            raise RuntimeError("step_wait without step_async")
+        if self._pending == "block":
+            self.lib.check(self.lib.sync(self._handle, None), "oc_sync")
+        else:
+            a, flags = self._pending
+            if self.obs_format == "i8":
+                self.lib.check(self.lib.step_host_i8(self._handle, self._p(a), self._p(self.obs), self._p(self.timestep),
+                                                     self._p(self.rewards), None, self._p(self.dones),
+                                                     self._p(self.terminal_obs), self._p(self.terminal_timestep), flags, None),
+                               "oc_step_host_i8")
+            else:
+                self.lib.check(self.lib.step_host(self._handle, self._p(a), self._p(self.obs), self._p(self.rewards),
+                                                  None, self._p(self.dones), self._p(self.terminal_obs), flags, None),
+                               "oc_step_host")
+        self._pending = None
         d = self.dones.view(np.bool_)
         # one dict per env; only the entries of envs that finished are touched
         infos = self._infos
@@ -184,13 +253,31 @@ class OvercookedHostVecEnv:
                 infos[e] = {"terminal_observation": r}
         return self.obs, self.rewards, d, self._infos
 
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    # packed state through host buffers (checkpointing; clock staggering for benchmarks)
+    def get_state(self) -> np.ndarray:
+        st = np.zeros((self.num_envs, _cabi.OC_STATE_WORDS), np.uint32)
+        self.lib.check(self.lib.set_device(self.device_index), "oc_set_device")
+        self.lib.check(self.lib.get_state_host(self._handle, self._p(st), None), "oc_get_state_host")
+        return st
+
+    def set_state(self, st: np.ndarray) -> None:
+        self._check(st, (self.num_envs, _cabi.OC_STATE_WORDS), np.uint32, "state")
+        self.lib.check(self.lib.set_device(self.device_index), "oc_set_device")
+        self.lib.check(self.lib.set_state_host(self._handle, self._p(st), None), "oc_set_state_host")
+
+    def stagger_clocks(self, period: Optional[int] = None) -> None:
+        """Env e's episode clock := e mod period (default: max_num_timesteps): the steady state of a long run, in
+        which about E / T envs finish in every step instead of all of them in the same one."""
+        T = int(period or self.arglist.max_num_timesteps)
+        st = self.get_state()
+        st[:, 0] = (st[:, 0] & np.uint32(0xFFFF0000)) | (np.arange(self.num_envs, dtype=np.uint32) % np.uint32(T))
+        self.set_state(st)
+
     # SB3 VecEnv duck type (the rest of the convention; every env shares one configuration)
-    def step_async(self, actions) -> None:
-        self._pending = actions
-
-    def step_wait(self):
-        return self.step(self._pending)
-
     def seed(self, seed=None):
         return [None] * self.num_envs          # placements are seeded at construction (oc_config.seed)
 
@@ -238,6 +325,7 @@ class OvercookedHostVecEnv:
             self._handle = C.c_void_p()
             self._pinned = []
             self.obs = self.rewards = self.dones = self._dones_padded = self.actions = self.terminal_obs = None
+            self.actions_u8 = self.reward_per_env = self._block = None
             self._term_rows = []
             self.timestep = self.terminal_timestep = None
 

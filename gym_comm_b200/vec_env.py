@@ -12,7 +12,6 @@ env logic on the host, and nothing falls back to a CPU implementation.
 from __future__ import annotations
 
 import ctypes as C
-import os
 from typing import Optional
 
 import numpy as np
@@ -41,14 +40,7 @@ class OvercookedVecEnv:
         a = self.arglist
         self.lib = lib if lib is not None else _cabi.default_library()
         self.device = torch.device(device)
-        if self.lib.prefix != "oc_" and os.environ.get("OC_TEST_EMULATION") != "1":
-            raise RuntimeError("only liboc_b200.so (CUDA) is a product backend; the host emulation of the device "
-                               "code is a test aid and needs OC_TEST_EMULATION=1 (set by tests/parity_util.py)")
-        if self.lib.prefix == "oc_":
-            if self.device.type != "cuda":
-                raise RuntimeError("OvercookedVecEnv runs on a CUDA device only (no CPU fallback)")
-            if not torch.cuda.is_available():
-                raise RuntimeError("no CUDA device available; the Overcooked kernels are sm_100a CUDA only")
+        self._require_backend()
         self.num_envs = int(num_envs)
         self.num_agents = int(a.num_agents)
         self.auto_reset = bool(auto_reset)
@@ -76,11 +68,20 @@ class OvercookedVecEnv:
         self._closed = False
 
     # ------------------------------------------------------------------ plumbing
+    def _require_backend(self):
+        """The only backend is the CUDA library on a CUDA device."""
+        if not isinstance(self.lib, _cabi.OcLibrary):
+            raise RuntimeError("lib must be a gym_comm_b200._cabi.OcLibrary (liboc_b200.so); there is no other backend")
+        if self.device.type != "cuda":
+            raise RuntimeError("OvercookedVecEnv runs on a CUDA device only (no CPU fallback)")
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device available; the Overcooked kernels are sm_100a CUDA only")
+
     def _device_guard(self):
-        return torch.cuda.device(self.device) if self.device.type == "cuda" else _NullCtx()
+        return torch.cuda.device(self.device)
 
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream) if self.device.type == "cuda" else None
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     @staticmethod
     def _ptr(t: Optional[torch.Tensor]):
@@ -128,6 +129,60 @@ class OvercookedVecEnv:
                                          self._ptr(self.rewards64) if want_f64 else None, self._ptr(done),
                                          self._ptr(term_obs_out), flags, self._stream()), "oc_step")
         return obs, rew, done
+
+    def compact_buffers(self):
+        """Output tensors of `step_i8` / `reset_i8`: (obs int8 [E, A, F-1], timestep f32 [E])."""
+        E, A, F = self.num_envs, self.num_agents, self.obs_width
+        return (torch.zeros((E, A, F - 1), dtype=torch.int8, device=self.device),
+                torch.zeros((E,), dtype=torch.float32, device=self.device))
+
+    def reset_i8(self, obs_out: torch.Tensor, timestep_out: torch.Tensor, mask=None, placements=None):
+        """`reset` with the observations in the compact integer format (`oc_reset_i8`): the reset kernel writes
+        int8 [E, A, F-1] rows and the f32 [E] clock itself."""
+        E, A, F = self.num_envs, self.num_agents, self.obs_width
+        self._check_tensor(obs_out, (E, A, F - 1), torch.int8, "obs_out")
+        self._check_tensor(timestep_out, (E,), torch.float32, "timestep_out")
+        if mask is not None:
+            self._check_tensor(mask, (E,), torch.uint8, "mask")
+        if placements is not None:
+            self._check_tensor(placements, (E, self.level.num_random), torch.int32, "placements")
+        with self._device_guard():
+            self.lib.check(self.lib.reset_i8(self._handle, self._ptr(mask), self._ptr(placements), self._ptr(obs_out),
+                                             self._ptr(timestep_out), self._stream()), "oc_reset_i8")
+        return obs_out, timestep_out
+
+    def step_i8(self, actions: torch.Tensor, obs_out: torch.Tensor, timestep_out: torch.Tensor, rew_out=None,
+                done_out=None, term_obs_out=None, term_timestep_out=None, want_f64: bool = False):
+        """`step` with the observations in the compact integer format (`oc_step_i8`): int8 [E, A, F-1] rows +
+        f32 [E] clock written by the step kernel itself (a quarter of the bytes of the float rows).
+        ``actions``: int32 [E, A, 2] or uint8 [E, A, 2]; ``rew_out``: f32 [E, A] (default) or f32 [E]."""
+        E, A, F = self.num_envs, self.num_agents, self.obs_width
+        rew = self.rewards if rew_out is None else rew_out
+        done = self.dones if done_out is None else done_out
+        flags = _cabi.OC_FLAG_AUTO_RESET if self.auto_reset else 0
+        if actions.dtype == torch.uint8:
+            self._check_tensor(actions, (E, A, 2), torch.uint8, "actions")
+            flags |= _cabi.OC_FLAG_ACTIONS_U8
+        else:
+            self._check_tensor(actions, (E, A, 2), torch.int32, "actions")
+        self._check_tensor(obs_out, (E, A, F - 1), torch.int8, "obs_out")
+        self._check_tensor(timestep_out, (E,), torch.float32, "timestep_out")
+        if rew.dim() == 1:
+            self._check_tensor(rew, (E,), torch.float32, "rew_out")
+            flags |= _cabi.OC_FLAG_REWARD_PER_ENV
+        else:
+            self._check_tensor(rew, (E, A), torch.float32, "rew_out")
+        self._check_tensor(done, (E,), torch.uint8, "done_out")
+        if term_obs_out is not None:
+            self._check_tensor(term_obs_out, (E, A, F - 1), torch.int8, "term_obs_out")
+        if term_timestep_out is not None:
+            self._check_tensor(term_timestep_out, (E,), torch.float32, "term_timestep_out")
+        with self._device_guard():
+            self.lib.check(self.lib.step_i8(self._handle, self._ptr(actions), self._ptr(obs_out), self._ptr(timestep_out),
+                                            self._ptr(rew), self._ptr(self.rewards64) if want_f64 else None,
+                                            self._ptr(done), self._ptr(term_obs_out), self._ptr(term_timestep_out),
+                                            flags, self._stream()), "oc_step_i8")
+        return obs_out, timestep_out, rew, done
 
     def rollout(self, n_steps: int, obs_out=None, rew_out=None, done_out=None, actions_out=None):
         """Fused synthetic rollout: ``n_steps`` steps in ONE launch, uniform random actions from
@@ -181,7 +236,7 @@ class OvercookedVecEnv:
         return {"episodes": ep, "num_completed_subtasks": lc}
 
     def launch_count(self) -> int:
-        return int(self.lib.launch_count(self._handle)) if self.lib.prefix == "oc_" else 0
+        return int(self.lib.launch_count(self._handle))
 
     def obs_dict(self, obs: Optional[torch.Tensor] = None) -> dict:
         """Zero-copy per-key views ``[..., size]`` of flat observation rows."""
@@ -260,14 +315,6 @@ class OvercookedVecEnv:
             pass
 
 
-class _NullCtx:
-    def __enter__(self):
-        return self
-
-    def __exit__(self, *a):
-        return False
-
-
 class OvercookedMultiEnv:
     """The reference's ``OvercookedMultiEnv`` surface (gym_comm/envs/overcooked_env.py:15-297).
 
@@ -279,6 +326,7 @@ class OvercookedMultiEnv:
     pantheonrl/common/multiagentenv.py:217-243)."""
 
     n_players = 2
+    _vec_cls = OvercookedVecEnv
 
     def __init__(self, arglist, ego_agent_idx: int = 0, device="cuda", seed: int = 0,
                  level_text: Optional[str] = None, subtasks=None, lib=None):
@@ -289,7 +337,7 @@ class OvercookedMultiEnv:
         if ego_agent_idx != 0:
             raise ValueError("only ego_agent_idx=0 is supported (the only value the reference's trainer uses)")
         self.ego_agent_idx = ego_agent_idx
-        self.vec = OvercookedVecEnv(self.arglist, num_envs=1, device=device, seed=seed, auto_reset=False,
+        self.vec = self._vec_cls(self.arglist, num_envs=1, device=device, seed=seed, auto_reset=False,
                                     level_text=level_text, subtasks=subtasks, lib=lib)
         self.observation_space = self.vec.observation_space
         self.action_space = self.vec.action_space

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define OC_ABI_VERSION 1
+#define OC_ABI_VERSION 2
 
 #define OC_MAX_AGENTS   4
 #define OC_MAX_OBJECTS  6
@@ -51,9 +51,12 @@ typedef enum oc_status {
     OC_ERR_ALLOC = -3
 } oc_status;
 
-/* oc_step / oc_rollout flags */
+/* step flags */
 #define OC_FLAG_AUTO_RESET 1u  /* on done: reset the env in place and return the first obs of the new
                                   episode (SB3 VecEnv contract; DummyVecEnv.step_wait)             */
+#define OC_FLAG_ACTIONS_U8 2u      /* oc_step_i8: actions are u8 [E, A, 2] (nav < 4, comm < C <= 256) instead of int32  */
+#define OC_FLAG_REWARD_PER_ENV 4u  /* oc_step_i8: rew_f32 is f32 [E] (one value per env) instead of f32 [E, A]           */
+#define OC_FLAG_NO_SYNC 8u         /* oc_step_host_block: return after enqueueing; oc_sync() before reading the block     */
 
 /* Order of the 11 observation keys inside one flat feature row = the key-sorted order a gym
  * spaces.Dict gives the dict built at gym_comm/envs/overcooked_env.py:66-78 (what
@@ -74,7 +77,8 @@ typedef struct oc_config {
     int32_t  num_envs;             /* E */
     int32_t  num_agents;           /* A, 2..4  (arglist.num_agents) */
     int32_t  width, height;        /* grid; width*height <= OC_MAX_CELLS */
-    int32_t  max_num_timesteps;    /* T (0 = no time limit)  overcooked_environment.py:245 */
+    int32_t  max_num_timesteps;    /* T, 1..65534 (0 is rejected: the timestep observation is t / T,
+                                      overcooked_env.py:146)  overcooked_environment.py:245 */
     int32_t  num_communication;    /* C  (arglist.num_communication) */
     int32_t  communication_on;     /* overcooked_env.py:229 */
     int32_t  ego_led;              /* overcooked_env.py:234 */
@@ -150,6 +154,18 @@ int oc_reset(oc_env* env, const uint8_t* mask, const int32_t* placements, float*
 int oc_step(oc_env* env, const int32_t* actions, float* obs, float* rew_f32, double* rew_f64,
             uint8_t* done, float* term_obs, uint32_t flags, void* stream);
 
+/* oc_step / oc_reset with the observations in the COMPACT INTEGER FORMAT (see oc_pack_obs_i8 below), produced by
+ * the step / reset kernel itself: obs_i8 int8 [E, A, F-1] (16-byte aligned) + timestep f32 [E] (may be NULL);
+ * term_obs_i8 / term_timestep likewise for envs that finished.  Every pointer may be device memory or
+ * page-locked host memory (cudaHostAlloc / oc_host_alloc: the kernel then reads / writes across PCIe).
+ * flags: OC_FLAG_AUTO_RESET | OC_FLAG_ACTIONS_U8 (actions u8 [E, A, 2]) | OC_FLAG_REWARD_PER_ENV (rew_f32 f32 [E]).
+ * Fails with OC_ERR_INVALID when 32 rows of A * (F-1) bytes exceed 64 KB (use oc_step + oc_pack_obs_i8 then). */
+int oc_compact_supported(const oc_env* env);   /* 1 when oc_reset_i8 / oc_step_i8 / oc_*_host_block can run on this handle */
+int oc_reset_i8(oc_env* env, const uint8_t* mask, const int32_t* placements, int8_t* obs_i8, float* timestep,
+                void* stream);
+int oc_step_i8(oc_env* env, const void* actions, int8_t* obs_i8, float* timestep, float* rew_f32, double* rew_f64,
+               uint8_t* done, int8_t* term_obs_i8, float* term_timestep, uint32_t flags, void* stream);
+
 /* Fused synthetic rollout (the throughput benchmark of SURVEY section 8d): n_steps env steps in
  * ONE launch with state kept on chip; actions nav~U{0..3}, comm~U{0..C-1} from Philox4x32-10
  * keyed by (seed; env index, global step); auto-reset always on.  Step s writes
@@ -170,6 +186,9 @@ int oc_replay(oc_env* env, int32_t n_steps, const int32_t* actions, float* obs, 
  * device, layout in DESIGN.md.  Replaces OvercookedEnvironment.__copy__/get_repr
  * (overcooked_environment.py:59-84). */
 int oc_get_state(oc_env* env, uint32_t* state, void* stream);
+/* Imported words are sanitised: agent cells and live object cells are clamped to the grid, holders to
+ * {0..A-1, none}, empty slots become the canonical dead word -- a state exported from another level cannot
+ * make the kernels index outside their tables. */
 int oc_set_state(oc_env* env, const uint32_t* state, void* stream);
 
 /* Per-env statistics kept on device: episodes finished, and completed-subtask count of the last
@@ -206,6 +225,29 @@ int oc_reset_host_i8(oc_env* env, const uint8_t* mask, const int32_t* placements
 int oc_step_host_i8(oc_env* env, const int32_t* actions, int8_t* obs_i8, float* timestep, float* rew_f32,
                     double* rew_f64, uint8_t* done, int8_t* term_obs_i8, float* term_timestep, uint32_t flags,
                     void* stream);
+/* ---- One-block host path: everything a step returns in ONE page-locked block, so that one device->host copy
+ * per step carries it (the host-side ceiling of this path is the PCIe link).  The block holds, at
+ * the 256-byte aligned offsets oc_host_block_layout reports,
+ *    obs_i8 int8 [E, A, F-1] | timestep f32 [E] | reward f32 [E] | done u8 [E]
+ * (reward: ONE value per env -- the reference hands the same reward to both players, overcooked_env.py:282).
+ * actions_u8: u8 [E, A, 2] host (nav, comm per agent; C <= 256).  When it is page-locked the kernel reads it
+ * across PCIe itself and the step is one launch + one copy.  term_obs_i8 / term_timestep (NULL or page-locked
+ * host, int8 [E, A, F-1] / f32 [E]): rows of envs that finished are written by the kernel directly.
+ * flags: OC_FLAG_AUTO_RESET | OC_FLAG_NO_SYNC (return after enqueueing; call oc_sync before reading). */
+typedef struct oc_host_block {
+    uint64_t obs_i8, timestep, reward, done;   /* byte offsets */
+    uint64_t total_bytes;
+} oc_host_block;
+int oc_host_block_layout(const oc_env* env, oc_host_block* out);
+int oc_reset_host_block(oc_env* env, const uint8_t* mask, const int32_t* placements, void* block, void* stream);
+int oc_step_host_block(oc_env* env, const uint8_t* actions_u8, void* block, int8_t* term_obs_i8,
+                       float* term_timestep, uint32_t flags, void* stream);
+/* cudaStreamSynchronize(stream) for callers that do not link the CUDA runtime. */
+int oc_sync(oc_env* env, void* stream);
+/* oc_get_state / oc_set_state with a HOST buffer u32 [E, OC_STATE_WORDS] (checkpointing from numpy); synchronous. */
+int oc_get_state_host(oc_env* env, uint32_t* state, void* stream);
+int oc_set_state_host(oc_env* env, const uint32_t* state, void* stream);
+
 /* Page-locked host memory for those buffers (cudaHostAlloc / cudaFreeHost without linking the CUDA runtime). */
 int oc_host_alloc(uint64_t bytes, void** out);
 int oc_host_free(void* ptr);

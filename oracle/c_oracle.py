@@ -34,6 +34,7 @@ def lib():
         l.oco_throughput.restype = C.c_longlong
         l.oco_throughput.argtypes = [C.c_void_p, C.c_double]
         l.oco_get_state.argtypes = [C.c_void_p, C.c_void_p]
+        l.oco_set_clocks.argtypes = [C.c_void_p, C.c_void_p]
         _lib = l
     return _lib
 
@@ -86,6 +87,11 @@ class COracle:
         acts = np.zeros((n_steps, self.N, self.A, 2), dtype=np.int32) if want_actions else None
         self.l.oco_rollout(self.h, n_steps, _p(obs), _p(rew), _p(done), _p(acts))
         return obs, rew, done, acts
+
+    def set_clocks(self, t):
+        """Episode clock of every env := t[e] (what `stagger_clocks` does to the device state)."""
+        t = np.ascontiguousarray(t, dtype=np.uint32).reshape(self.N)
+        self.l.oco_set_clocks(self.h, _p(t))
 
     def state(self):
         n = self.l.oco_state_ints(self.h)

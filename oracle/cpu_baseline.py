@@ -1,13 +1,16 @@
 """TEST / MEASUREMENT INFRASTRUCTURE ONLY -- the CPU arm timed beside the GPU numbers.
 
-The reference itself (pure Python, /root/reference) does not exist on the GPU box, so the CPU
-arm is the oracle PORT: ``kind="c"`` = oracle/oc_oracle.c, one env per thread-chunk over all host
-cores (the strongest CPU statement of the path we have); ``kind="py"`` = oracle/spec_model.py,
-one env per process -- structurally what the reference does (per-object Python loop), minus its
-template-object and networkx overheads.  BASELINE.md records the reference's own measured
-speed in the build container (1.2-1.7 k env-steps/s/core).
-Same action distribution as the GPU run: nav ~ U{0..3}, comm ~ U{0..C-1}, auto-reset, resets
-inside the clock.
+Three CPU statements of the path, all with the GPU run's action distribution (nav ~ U{0..3},
+comm ~ U{0..C-1}), auto-reset, resets inside the clock, one worker per host core:
+
+``reference``  the UNMODIFIED reference (`OvercookedMultiEnv.multi_step`, gym_comm/envs/overcooked_env.py:207-282),
+               one env per process, PYTHONHASHSEED=0, stdout discarded -- oracle/time_reference.py run as a
+               subprocess.  Found at /root/reference (build container) or in the git-ignored copy
+               oracle/stage_ref.py staged under oracle/_ref/ (GPU box).  This is the primary figure
+               (`kind: "reference"`) whenever it is available.
+``python_port``  oracle/spec_model.py, one env per process -- structurally the reference's per-object Python
+               loop minus its template-object and networkx overheads (`kind: "port"`).
+``c_port``     oracle/oc_oracle.c, one thread per core -- a far stronger CPU statement than the reference.
 """
 from __future__ import annotations
 
@@ -60,34 +63,69 @@ def _py_worker(args):
     return steps, time.perf_counter() - t0
 
 
-def run_all_cores(workload, ns, seconds, kind="py"):
-    """Primary figure: the Python port (structurally the reference: a per-object Python loop, one
-    env per process, all host cores).  The C port on all cores is reported next to it as
-    ``c_port`` -- a far stronger CPU statement of the path than the reference itself."""
+def run_reference(workload, seconds):
+    """The unmodified reference on all cores, or None when no reference tree is reachable."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = {k: v for k, v in workload.items() if k != "envs"}
+    env = dict(os.environ, PYTHONHASHSEED="0")
+    try:
+        out = subprocess.run([sys.executable, "-m", "oracle.time_reference", "--seconds", "%g" % seconds,
+                              "--workload", json.dumps(cfg)], cwd=root, env=env, stdout=subprocess.PIPE,
+                             stderr=subprocess.DEVNULL, timeout=seconds * 6 + 120, check=True).stdout.decode()
+        d = json.loads(out.strip().splitlines()[-1])
+    except Exception as ex:
+        return {"error": repr(ex)}
+    if not d.get("available"):
+        return None
+    n = int(workload.get("num_agents", 2))
+    return {"value": d["agent_steps_per_s"], "unit": "agent-steps/s", "cores": d["cores"], "kind": "reference",
+            "impl": "the unmodified reference (OvercookedMultiEnv.multi_step incl. observations), one env per process, "
+                    "PYTHONHASHSEED=0, from %s" % d["reference_root"],
+            "sample": "%.1f s per worker of random-action stepping incl. %d observations per step and %d resets" %
+                      (d["seconds"], n, d["resets"]),
+            "env_steps": d["env_steps"], "seconds": d["seconds"], "per_core": d["agent_steps_per_s_per_core"]}
+
+
+def run_python_port(ns, seconds):
     cores = os.cpu_count() or 1
     n = ns.num_agents
-    ns_dict = dict(vars(ns))
-    py_seconds = seconds * 0.75 if kind == "py" else seconds * 0.25
     with mp.get_context("fork").Pool(cores) as pool:
-        res = pool.map(_py_worker, [(ns_dict, py_seconds, 1000 + i) for i in range(cores)])
+        res = pool.map(_py_worker, [(dict(vars(ns)), seconds, 1000 + i) for i in range(cores)])
     steps = sum(r[0] for r in res)
     dt = max(r[1] for r in res)
-    py = {"value": steps * n / dt, "unit": "agent-steps/s", "cores": cores, "kind": "port",
-          "impl": "oracle/spec_model.py (Python restatement of the reference path, one env per process)",
-          "sample": "%.1f s per worker of random-action stepping incl. %d observations per step and resets" % (dt, n),
-          "env_steps": steps, "seconds": dt}
+    return {"value": steps * n / dt, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+            "impl": "oracle/spec_model.py (Python restatement of the reference path, one env per process)",
+            "sample": "%.1f s per worker of random-action stepping incl. %d observations per step and resets" % (dt, n),
+            "env_steps": steps, "seconds": dt}
+
+
+def run_c_port(ns, seconds):
     try:
         from oracle import c_oracle
-        csteps, cdt, threads = c_oracle.throughput(ns, max(1.0, seconds - py_seconds))
-        cport = {"value": csteps * n / cdt, "unit": "agent-steps/s", "cores": threads, "kind": "port",
-                 "impl": "oracle/oc_oracle.c (C restatement, one thread per host core, %d envs per thread)" % c_oracle.ENVS_PER_THREAD,
-                 "sample": "%.1f s of random-action stepping incl. obs featurisation and resets" % cdt,
-                 "env_steps": csteps, "seconds": cdt}
+        n = ns.num_agents
+        csteps, cdt, threads = c_oracle.throughput(ns, max(1.0, seconds))
+        return {"value": csteps * n / cdt, "unit": "agent-steps/s", "cores": threads, "kind": "port",
+                "impl": "oracle/oc_oracle.c (C restatement, one thread per host core, %d envs per thread)" % c_oracle.ENVS_PER_THREAD,
+                "sample": "%.1f s of random-action stepping incl. obs featurisation and resets" % cdt,
+                "env_steps": csteps, "seconds": cdt}
     except Exception as ex:
-        cport = {"error": repr(ex)}
-    out = dict(py if kind == "py" else cport)
-    out["c_port" if kind == "py" else "python_port"] = cport if kind == "py" else py
-    out["reference_measured_in_build_container"] = (
-        "the unmodified reference: 1.2-1.7 k env-steps/s per core (BASELINE.md section 2); it is pure Python and "
-        "cannot travel to the GPU box")
+        return {"error": repr(ex)}
+
+
+def run_all_cores(workload, ns, seconds):
+    """Primary figure: the unmodified reference when a reference tree is reachable (`kind: "reference"`),
+    else the Python port (`kind: "port"`); the other statements ride along under their own keys."""
+    ref = run_reference(workload, seconds * 0.6)
+    have_ref = isinstance(ref, dict) and "value" in ref
+    py = run_python_port(ns, seconds * (0.25 if have_ref else 0.75))
+    cport = run_c_port(ns, seconds * (0.15 if have_ref else 0.25))
+    out = dict(ref if have_ref else py)
+    if have_ref:
+        out["python_port"] = py
+    elif ref is not None:
+        out["reference_error"] = ref.get("error")
+    out["c_port"] = cport
     return out

@@ -664,6 +664,9 @@ long long oco_throughput(Batch* b, double seconds) {
  *   ints[0]=t, [1]=episodes, [2..2+A*2) agent xy, then completed bits, count bits (as ints S each),
  *   comm0, comm1, last_completed; objects in world iteration order: nobj rows of
  *   (contents, chopped, x, y, held) padded with -1. */
+/* episode clocks from outside (benchmarks stagger them so that a few envs finish in every step) */
+void oco_set_clocks(Batch* b, const uint32_t* t) { for (int i = 0; i < b->N; ++i) b->env[i].t = (int)t[i]; }
+
 int oco_state_ints(const Batch* b) { return 2 + 2 * b->A + 2 * b->S + 3 + 5 * b->nobj; }
 void oco_get_state(const Batch* b, int32_t* out) {
     const int n = oco_state_ints(b);

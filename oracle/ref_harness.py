@@ -6,11 +6,14 @@ container, where ``gym``, ``termcolor``, ``matplotlib`` and
 modules before the import (recipe: SURVEY.md section 8c).  It is used by
 
 * ``oracle/record_golden.py``  (generates ``tests/golden/*.npz``), and
-* ``tests/test_oracle_vs_reference.py`` (skipped when ``/root/reference`` is
-  absent, e.g. on the GPU box).
+* ``tests/test_oracle_vs_reference.py`` (skipped when no reference tree is
+  reachable), and
+* ``oracle/time_reference.py`` (the CPU arm of ``bench.py``).
 
-Nothing here is imported by the product package.  The reference tree is never
-copied; it is imported from where it lies (``/root/reference``).
+Nothing here is imported by the product package.  The reference is imported
+from where it lies (``/root/reference``); on the GPU box, where that path does
+not exist, from the unmodified copy ``oracle/stage_ref.py`` staged into the
+git-ignored ``oracle/_ref/``.
 
 Facts the harness depends on (reference file:line):
 * level path is cwd-relative      gym_cooking/envs/overcooked_environment.py:103
@@ -26,7 +29,18 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("OC_REFERENCE_ROOT", "/root/reference")
+def _find_reference_root() -> str:
+    """`/root/reference` in the build container; on the GPU box the byte-identical copy that
+    `oracle/stage_ref.py` left in the git-ignored `oracle/_ref/` (it travels with gpurun)."""
+    env = os.environ.get("OC_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/gym_cooking"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:

@@ -89,6 +89,54 @@ static void for_each_warp(emu_env* h, float* obs, float* term_obs, Body&& body) 
     }
 }
 
+// the same for the compact-row kernels (MODE 3): rows = int8 [A, F-1] per env, clock per env
+template <int A, int NOBJ, int NF, typename Body>
+static void for_each_warp_packed(emu_env* h, uint8_t* obs8, float* ts, uint8_t* term8, float* term_ts, Body&& body) {
+    OcParams p = h->p;
+    make_compact_params(p);
+    const Tables tb = make_tables(p, h->blob.data());
+    std::vector<uint8_t> rows((size_t)p.warp_row_bytes);
+    Env<A, NOBJ> we[32];
+    Info win[32];
+    for (int env0 = 0; env0 < p.E; env0 += 32) {
+        const int nvalid = std::min(32, p.E - env0);
+        for (int lane = 0; lane < 32; ++lane) warp_clear_rows<true>(rows.data(), p.warp_row_bytes, lane);
+        for (int lane = 0; lane < nvalid; ++lane) {
+            const int env = env0 + lane;
+            const bool fin = body(tb, env, we[lane], win[lane]);
+            if (fin) {
+                if (term8) {          // warp_terminal_obs_packed, one finished lane at a time (rows clear before and after)
+                    uint8_t* myrow = rows.data() + (size_t)lane * p.row_stride;
+                    build_rows_i8<A, NOBJ, NF>(we[lane], p, tb, win[lane], myrow);
+                    for (int j = 0; j < p.row_bytes; ++j) { term8[(size_t)env * p.row_bytes + j] = myrow[j]; myrow[j] = 0; }
+                    if (term_ts) term_ts[env] = timestep_of<A, NOBJ>(we[lane], p, tb);
+                }
+                finish_episode<A, NOBJ>(we[lane], p, tb, (uint32_t)env);
+                win[lane] = gather_info<A, NOBJ, NF>(we[lane], p, tb);
+            }
+            store_env<A, NOBJ>(we[lane], h->state.data(), p.E, env);
+        }
+        if (!obs8) continue;
+        // emit_obs_packed, lane by lane: fill, then the warp's copy, then the clocks
+        for (int lane = 0; lane < nvalid; ++lane)
+            build_rows_i8<A, NOBJ, NF>(we[lane], p, tb, win[lane], rows.data() + (size_t)lane * p.row_stride);
+        for (int lane = 0; lane < 32; ++lane)
+            warp_store_packed(p, rows.data(), obs8 + (size_t)env0 * p.row_bytes, nvalid, lane);
+        if (ts)
+            for (int lane = 0; lane < nvalid; ++lane) ts[env0 + lane] = timestep_of<A, NOBJ>(we[lane], p, tb);
+    }
+}
+
+template <typename F>
+static int dispatch_shape(int A, int NOBJ, F&& f) {
+#define OC_CASE(a, n, nfood)                                                                                       \
+    if (A == a && NOBJ == n) return f(std::integral_constant<int, a>(), std::integer_sequence<int, n, nfood>());
+    OC_CASE(2, 2, 1) OC_CASE(3, 2, 1) OC_CASE(4, 2, 1) OC_CASE(2, 4, 2) OC_CASE(3, 4, 2) OC_CASE(4, 4, 2)
+    OC_CASE(2, 6, 3) OC_CASE(3, 6, 3) OC_CASE(4, 6, 3)
+#undef OC_CASE
+    return OC_ERR_INVALID;
+}
+
 extern "C" {
 
 const char* emu_last_error(void) { return g_err.c_str(); }
@@ -152,6 +200,46 @@ int emu_step(emu_env* h, const int32_t* actions, float* obs, float* rew32, doubl
     });
 }
 
+// oc_reset_i8 / oc_step_i8: the compact-row kernels (MODE 3), incl. u8 actions and the per-env reward
+int emu_reset_i8(emu_env* h, const uint8_t* mask, const int32_t* placements, int8_t* obs8, float* ts, void*) {
+    return dispatch_shape(h->p.A, h->p.NOBJ, [&](auto a, auto n) -> int {
+        constexpr int AA = decltype(a)::value, NN = shape_nobj(n), FF = shape_nf(n);
+        for_each_warp_packed<AA, NN, FF>(h, (uint8_t*)obs8, ts, nullptr, nullptr, [&](const Tables& tb, int env, Env<AA, NN>& e, Info& in) {
+            load_env<AA, NN>(e, h->state.data(), h->p.E, env);
+            reset_logic<AA, NN>(e, h->p, tb, (uint32_t)env, false, mask, placements);
+            if (obs8) in = gather_info<AA, NN, FF>(e, h->p, tb);
+            return false;
+        });
+        return OC_OK;
+    });
+}
+
+int emu_step_i8(emu_env* h, const void* actions, int8_t* obs8, float* ts, float* rew32, double* rew64, uint8_t* done,
+                int8_t* term8, float* term_ts, uint32_t flags, void*) {
+    return dispatch_shape(h->p.A, h->p.NOBJ, [&](auto a, auto n) -> int {
+        constexpr int AA = decltype(a)::value, NN = shape_nobj(n), FF = shape_nf(n);
+        for_each_warp_packed<AA, NN, FF>(h, (uint8_t*)obs8, ts, (uint8_t*)term8, term_ts,
+                                         [&](const Tables& tb, int env, Env<AA, NN>& e, Info& in) {
+            load_env<AA, NN>(e, h->state.data(), h->p.E, env);
+            int nav[AA], comm[AA];
+            for (int k = 0; k < AA; ++k) {
+                if (flags & OC_FLAG_ACTIONS_U8) {
+                    const uint8_t* a8 = (const uint8_t*)actions + ((size_t)env * AA + k) * 2;
+                    nav[k] = a8[0] & 3; comm[k] = a8[1];
+                } else {
+                    const int32_t* a32 = (const int32_t*)actions + ((size_t)env * AA + k) * 2;
+                    nav[k] = a32[0] & 3; comm[k] = a32[1];
+                }
+            }
+            bool fin;
+            in = step_logic<AA, NN, FF>(e, h->p, tb, nav, comm[0], comm[1], (uint32_t)env, rew32, rew64, done, fin,
+                                        (flags & OC_FLAG_REWARD_PER_ENV) != 0);
+            return fin && (flags & OC_FLAG_AUTO_RESET);
+        });
+        return OC_OK;
+    });
+}
+
 int emu_rollout(emu_env* h, int32_t n_steps, float* obs, float* rew32, uint8_t* done, int32_t* actions_out, void*) {
     const size_t step_floats = (size_t)h->p.E * h->p.row_bytes;
     int rc = dispatch(h->p.A, h->p.NOBJ, h->p.rowf, [&](auto a, auto n, auto rf) -> int {
@@ -177,7 +265,8 @@ int emu_get_state(emu_env* h, uint32_t* state, void*) {
 }
 int emu_set_state(emu_env* h, const uint32_t* state, void*) {
     for (int env = 0; env < h->p.E; ++env)
-        for (int pl = 0; pl < 4; ++pl) h->state[(size_t)pl * h->p.E + env] = reinterpret_cast<const uint4*>(state)[(size_t)env * 4 + pl];
+        for (int pl = 0; pl < 4; ++pl)            // oc_state_import_kernel: sanitised on the way in
+            h->state[(size_t)pl * h->p.E + env] = sanitize_state_plane(h->p, pl, reinterpret_cast<const uint4*>(state)[(size_t)env * 4 + pl]);
     return OC_OK;
 }
 int emu_pack_obs_i8(emu_env* h, const float* obs, int8_t* obs_i8, float* timestep, void*) {   // oc_pack_i8_kernel, thread by thread

@@ -6,6 +6,11 @@ the device code (tests/test_multienv_api_cpu.py)."""
 import numpy as np
 
 from gym_comm_b200.vec_env import OvercookedMultiEnv
+
+
+def _make(ns, env_cls=None, **kw):
+    """`env_cls`: the CUDA-backed product class by default; the CPU suite passes tests.parity_util.EmuMultiEnv."""
+    return (env_cls or OvercookedMultiEnv)(ns, **kw)
 from tests.golden_util import load_golden
 from tests.parity_util import namespace_from_meta
 
@@ -28,7 +33,7 @@ TRACES = ["tomato_a9_script", "cramped_allergic", "open_tl"]
 
 def run_multi_step_matches_reference_trace(name, **envkw):
     meta, g = load_golden(name)
-    env = OvercookedMultiEnv(namespace_from_meta(meta), level_text=meta["level_text"], subtasks=meta["subtasks"], **envkw)
+    env = _make(namespace_from_meta(meta), level_text=meta["level_text"], subtasks=meta["subtasks"], **envkw)
     W = len(meta["level_text"].split("\n")[0])
 
     def placements(ep):
@@ -65,7 +70,7 @@ def run_known_answer_survey_a7(**envkw):
     d = dict(CAN_MOVE=True, ALLERGIC=False, BLIND=False)
     ns = argparse.Namespace(level="open-divider_tomato", num_agents=2, max_num_timesteps=500, communication_on=True,
                             num_communication=5, ego_led=False, fow_radius=2, ego_config=d, partner_config=d)
-    env = OvercookedMultiEnv(ns, **envkw)
+    env = _make(ns, **envkw)
     (o0, _), (r, _), done, _ = env.multi_step((3, 2), (0, 4))
     assert r == -8.206896551724139 and done is False
     assert o0["object_encodings_x"].tolist() == [2, 3, 0, 2] and o0["object_encodings_y"].tolist() == [-1, 0, 0, 5]
@@ -96,8 +101,8 @@ def run_multiagentenv_step_reset_with_partner(**envkw):
     d = dict(CAN_MOVE=True, ALLERGIC=False, BLIND=False)
     ns = argparse.Namespace(level="open-divider_tomato", num_agents=2, max_num_timesteps=5, communication_on=True,
                             num_communication=5, ego_led=False, fow_radius=2, ego_config=d, partner_config=d)
-    env = OvercookedMultiEnv(ns, **envkw)
-    twin = OvercookedMultiEnv(ns, **envkw)
+    env = _make(ns, **envkw)
+    twin = _make(ns, **envkw)
     p = Partner()
     env.add_partner_agent(p)
     ego_obs = env.reset()
@@ -139,7 +144,7 @@ def run_partner_selection_and_n_step(**envkw):
     d = dict(CAN_MOVE=True, ALLERGIC=False, BLIND=False)
     ns = argparse.Namespace(level="open-divider_tomato", num_agents=2, max_num_timesteps=3, communication_on=True,
                             num_communication=5, ego_led=False, fow_radius=2, ego_config=d, partner_config=d)
-    env = OvercookedMultiEnv(ns, **envkw)
+    env = _make(ns, **envkw)
     a, b, c = Const((0, 1)), Const((1, 2)), Const((2, 3))
     for p in (a, b, c):
         env.add_partner_agent(p)

@@ -12,14 +12,45 @@ import numpy as np
 import torch
 
 from gym_comm_b200 import _cabi
-from gym_comm_b200.vec_env import OvercookedVecEnv
+from gym_comm_b200.vec_env import OvercookedMultiEnv, OvercookedVecEnv
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU_DIR = os.path.join(ROOT, "tests", "emu")
 
 
+EMU_EXPORTS = ("oc_last_error", "oc_create", "oc_destroy", "oc_obs_width", "oc_obs_layout", "oc_reset", "oc_step",
+               "oc_reset_i8", "oc_step_i8", "oc_rollout", "oc_get_state", "oc_set_state", "oc_get_stats", "oc_pack_obs_i8")
+
+
+class EmuLibrary:
+    """TEST ONLY.  The CPU emulation of the device code (tests/emu/liboc_emu.so, symbols `emu_*`) behind the
+    attribute surface of `_cabi.OcLibrary`, so the host-side Python of the product can be exercised in the
+    GPU-less build container.  The product package knows nothing about it: `EmuVecEnv` below is the only way in."""
+
+    def __init__(self, path):
+        import ctypes as C
+        self.path = path
+        self.lib = C.CDLL(path)
+        for name in EMU_EXPORTS:
+            f = getattr(self.lib, "emu_" + name[3:])
+            f.restype, f.argtypes = _cabi.SIGNATURES[name]
+            setattr(self, name[3:], f)
+
+    def check(self, rc, what):
+        if rc != 0:
+            msg = self.last_error()
+            raise RuntimeError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else ""))
+
+    def launch_count(self, handle):
+        return 0
+
+
+_emu = None
+
+
 def emu_library():
     """Build (if stale) and load the CPU emulation of the device code.  TEST ONLY."""
+    global _emu
     so = os.path.join(EMU_DIR, "liboc_emu.so")
     srcs = [os.path.join(EMU_DIR, "oc_emu.cpp"), os.path.join(EMU_DIR, "oc_emu_shim.h")] + \
            [os.path.join(ROOT, "gym_comm_b200", "csrc", f) for f in ("oc_device.cuh", "oc_host.hpp", "oc_params.h")] + \
@@ -27,8 +58,33 @@ def emu_library():
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I" + EMU_DIR,
                                os.path.join(EMU_DIR, "oc_emu.cpp"), "-o", so])
-    os.environ["OC_TEST_EMULATION"] = "1"          # the product refuses non-CUDA backends without this
-    return _cabi.OcLibrary(so, prefix="emu_")
+        _emu = None
+    if _emu is None:
+        _emu = EmuLibrary(so)
+    return _emu
+
+
+class EmuVecEnv(OvercookedVecEnv):
+    """TEST ONLY: `OvercookedVecEnv` with its CUDA requirement lifted and the emulation library behind it
+    (CPU tensors, no stream).  Lives here, not in the product, so that the product has no CPU path."""
+
+    def __init__(self, arglist, num_envs=1, device="cpu", lib=None, **kw):
+        super().__init__(arglist, num_envs=num_envs, device="cpu", lib=lib if lib is not None else emu_library(), **kw)
+
+    def _require_backend(self):
+        assert isinstance(self.lib, EmuLibrary)
+
+    def _device_guard(self):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def _stream(self):
+        return None
+
+
+class EmuMultiEnv(OvercookedMultiEnv):
+    """TEST ONLY: the reference-shaped 2-player surface over `EmuVecEnv`."""
+    _vec_cls = EmuVecEnv
 
 
 def namespace_from_meta(meta):
@@ -58,8 +114,9 @@ def world_order_objects(dec, e, level):
 
 def replay_golden(meta, g, lib, device, num_envs=3):
     ns = namespace_from_meta(meta)
-    env = OvercookedVecEnv(ns, num_envs=num_envs, device=device, auto_reset=False, lib=lib,
-                           level_text=meta["level_text"], subtasks=meta["subtasks"])
+    cls = EmuVecEnv if isinstance(lib, EmuLibrary) else OvercookedVecEnv
+    env = cls(ns, num_envs=num_envs, device=device, auto_reset=False, lib=lib,
+              level_text=meta["level_text"], subtasks=meta["subtasks"])
     lv = env.level
     n, E = meta["num_agents"], num_envs
     S = len(meta["subtasks"])
@@ -106,29 +163,37 @@ def replay_golden(meta, g, lib, device, num_envs=3):
     env.close()
 
 
-class EmuHostLibrary:
+class EmuHostLibrary(_cabi.OcLibrary):
     """TEST ONLY.  Stands where `liboc_b200.so` stands for `OvercookedHostVecEnv`, so that the Python side of
-    the host-buffer path (buffers, formats, infos, terminal observations) can run in the GPU-less container:
-    the host-buffer entry points are re-expressed over the CPU emulation of the device functions
-    (emu_step, emu_pack_obs_i8, emu_gather_term -- the same sequence oc_step_host_i8 issues).  The real entry
-    points are covered on the GPU by tests/test_gpu_host_env.py and tests/cabi_smoke.c."""
-    prefix = "oc_"          # what OvercookedHostVecEnv checks for
+    the host-buffer path (buffers, formats, infos, terminal observations, the one-block layout) can run in the
+    GPU-less container: the host-buffer entry points are re-expressed over the CPU emulation of the device
+    functions (emu_step / emu_step_i8 / emu_reset_i8 -- the kernels the real entry points launch).  The real
+    entry points are covered on the GPU by tests/test_gpu_host_env.py and tests/cabi_smoke.c.
+    (Subclasses OcLibrary only to pass the product's isinstance check; nothing of the CUDA library is loaded.)"""
 
-    def __init__(self):
+    def __init__(self, compact=True):
         import ctypes as C
         self.C = C
         self.emu = emu_library()
-        self.create, self.destroy = self.emu.create, self.emu.destroy
+        self.destroy = self.emu.destroy
         self.obs_width, self.obs_layout = self.emu.obs_width, self.emu.obs_layout
+        self.last_error = self.emu.last_error
         self._gather = self.emu.lib.emu_gather_term
         self._gather.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3
         self._bufs, self._dims = {}, {}
+        self._compact = compact
 
     def check(self, rc, what):
         assert rc == 0, (what, rc)
 
     def set_device(self, index):
         return 0
+
+    def sync(self, h, stream):
+        return 0
+
+    def compact_supported(self, h):
+        return 1 if self._compact else 0
 
     def host_alloc(self, n, ref):
         buf = (self.C.c_uint8 * max(int(n), 1))()
@@ -141,18 +206,26 @@ class EmuHostLibrary:
         self._bufs.pop(ptr.value, None)
         return 0
 
-    def _shape(self, h, E_bytes_hint=None):
-        return self._dims[h.value]
+    def create(self, cfg, href):
+        rc = self.emu.create(cfg, href)
+        if rc == 0:                      # remember (E, A, F) of the handle (the C library knows them from oc_config)
+            self._dims[href._obj.value] = (cfg._obj.num_envs, cfg._obj.num_agents, self.emu.obs_width(href._obj))
+        return rc
 
     def bind(self, env):
-        """Remember (E, A, F) of a handle (the C library knows them from oc_config)."""
-        self._dims[env._handle.value] = (env.num_envs, env.num_agents, env.obs_width)
+        pass
 
     @staticmethod
     def _a(ptr, shape, dtype):
         import ctypes as C
         n = int(np.prod(shape)) * np.dtype(dtype).itemsize
         return np.frombuffer((C.c_uint8 * n).from_address(ptr.value), dtype=dtype).reshape(shape)
+
+    def get_state_host(self, h, st, stream):
+        return self.emu.get_state(h, st, None)
+
+    def set_state_host(self, h, st, stream):
+        return self.emu.set_state(h, st, None)
 
     def reset_host(self, h, mask, placements, obs, stream):
         return self.emu.reset(h, mask, placements, obs, None)
@@ -161,6 +234,8 @@ class EmuHostLibrary:
         return self.emu.step(h, actions, obs, rew, rew64, done, term, flags, None)
 
     def reset_host_i8(self, h, mask, placements, obs8, ts, stream):
+        if self._compact:
+            return self.emu.reset_i8(h, mask, placements, obs8, ts, None)
         E, A, F = self._dims[h.value]
         f = np.zeros((E, A, F), np.float32)
         rc = self.emu.reset(h, mask, placements, self.C.c_void_p(f.ctypes.data), None)
@@ -168,7 +243,9 @@ class EmuHostLibrary:
 
     def step_host_i8(self, h, actions, obs8, ts, rew, rew64, done, term8, term_ts, flags, stream):
         C = self.C
-        E, A, F = self._dims[h.value]
+        if self._compact:                 # the compact-row kernel writes everything itself, terminal rows included
+            return self.emu.step_i8(h, actions, obs8, ts, rew, rew64, done, term8, term_ts, flags, None)
+        E, A, F = self._dims[h.value]     # rows too wide for the compact kernels: float rows, repack, gather
         f = np.zeros((E, A, F), np.float32)
         t = np.zeros((E, A, F), np.float32)
         rc = self.emu.step(h, actions, C.c_void_p(f.ctypes.data), rew, rew64, done,
@@ -184,3 +261,31 @@ class EmuHostLibrary:
             if term_ts is not None:
                 self._a(term_ts, (E,), np.float32)[idx] = gts
         return 0
+
+    # the one-block path: same layout rule as oc_host_block_layout (sections padded to 256 bytes)
+    def host_block_layout(self, h, ref):
+        E, A, F = self._dims[h.value]
+        lay = ref._obj
+        off = 0
+        for name, n in (("obs_i8", E * A * (F - 1)), ("timestep", 4 * E), ("reward", 4 * E), ("done", E)):
+            setattr(lay, name, off)
+            off += (n + 255) // 256 * 256
+        lay.total_bytes = off
+        return 0
+
+    def _views(self, h, block):
+        E, A, F = self._dims[h.value]
+        lay = _cabi.OcHostBlock()
+        self.host_block_layout(h, self.C.byref(lay))
+        base = block.value
+        p = lambda off: self.C.c_void_p(base + off)
+        return p(lay.obs_i8), p(lay.timestep), p(lay.reward), p(lay.done)
+
+    def reset_host_block(self, h, mask, placements, block, stream):
+        obs8, ts, _, _ = self._views(h, block)
+        return self.emu.reset_i8(h, mask, placements, obs8, ts, None)
+
+    def step_host_block(self, h, actions_u8, block, term8, term_ts, flags, stream):
+        obs8, ts, rew, done = self._views(h, block)
+        fl = (flags & _cabi.OC_FLAG_AUTO_RESET) | _cabi.OC_FLAG_ACTIONS_U8 | _cabi.OC_FLAG_REWARD_PER_ENV
+        return self.emu.step_i8(h, actions_u8, obs8, ts, rew, None, done, term8, term_ts, fl, None)

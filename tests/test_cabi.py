@@ -54,29 +54,39 @@ def test_no_cpu_fallback(lib):
         OvercookedVecEnv(ns, num_envs=4, device="cpu")
 
 
-def test_host_env_has_no_cpu_fallback_either(lib):
-    """The numpy-only host path needs the CUDA library and a device; it refuses the test emulation."""
+def test_host_env_refuses_anything_but_the_cuda_library(lib):
+    """The numpy host path has no CPU fallback either: only an `OcLibrary` (liboc_b200.so) is accepted, and
+    without a device creation fails."""
     import torch
     import argparse
     from gym_comm_b200.host_env import OvercookedHostVecEnv
     from tests.parity_util import emu_library
     ns = argparse.Namespace(level="open-divider_tomato", num_agents=2, max_num_timesteps=100)
-    with pytest.raises(RuntimeError):
+    with pytest.raises(RuntimeError, match="no CPU backend"):
         OvercookedHostVecEnv(ns, num_envs=4, lib=emu_library())
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             OvercookedHostVecEnv(ns, num_envs=4)
 
 
-def test_emulation_backend_is_refused_outside_tests(monkeypatch):
+def test_product_env_refuses_the_emulation_and_cpu_devices():
+    """The CPU emulation of the device code is reachable only through the test-side subclass
+    (tests/parity_util.EmuVecEnv): the product class accepts nothing but the CUDA library on a CUDA device, and
+    the package itself holds no reference to the emulation."""
     import argparse
+    from gym_comm_b200 import _cabi
     from gym_comm_b200.vec_env import OvercookedVecEnv
     from tests.parity_util import emu_library
-    emu = emu_library()
-    monkeypatch.delenv("OC_TEST_EMULATION", raising=False)
     ns = argparse.Namespace(level="open-divider_tomato", num_agents=2, max_num_timesteps=100)
-    with pytest.raises(RuntimeError):
-        OvercookedVecEnv(ns, num_envs=4, device="cpu", lib=emu)
+    with pytest.raises(RuntimeError, match="no other backend"):
+        OvercookedVecEnv(ns, num_envs=4, device="cpu", lib=emu_library())
+    with pytest.raises(RuntimeError, match="CUDA device only"):
+        OvercookedVecEnv(ns, num_envs=4, device="cpu", lib=_cabi.default_library())
+    pkg = os.path.join(ROOT, "gym_comm_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            text = open(os.path.join(pkg, f)).read()
+            assert "emu_" not in text and "OC_TEST_EMULATION" not in text and "prefix" not in text, f
 
 
 def test_header_is_plain_c_and_cxx(tmp_path):

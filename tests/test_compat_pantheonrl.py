@@ -31,14 +31,14 @@ class ScriptedPartner:
 @pytest.mark.parametrize("level,T,C", [("open-divider_tomato", 9, 5), ("open-divider_salad", 14, 3)])
 def test_reference_multiagentenv_drives_the_drop_in(level, T, C):
     from gym_comm_b200 import compat
-    from tests.parity_util import emu_library
+    from tests.parity_util import EmuMultiEnv
     ns = ref_harness.make_namespace(level, max_num_timesteps=T, num_communication=C)
     live = ref_harness.LiveReference(ns, py_random_seed=3)            # installs the import stubs, builds the reference env
     ref_env = live.wrapper
-    Env = compat.gym_env_class()
+    Env = compat.gym_env_class(EmuMultiEnv)
     from pantheonrl.common.multiagentenv import SimultaneousEnv
     assert issubclass(Env, SimultaneousEnv)
-    ours = Env(ns, device="cpu", lib=emu_library(), level_text=live.level_text(), subtasks=live.subtask_strings())
+    ours = Env(ns, device="cpu", level_text=live.level_text(), subtasks=live.subtask_strings())
     p_ref, p_ours = ScriptedPartner(1, C), ScriptedPartner(1, C)
     ref_env.add_partner_agent(p_ref)
     ours.add_partner_agent(p_ours)

@@ -20,8 +20,8 @@ def _free_port():
 
 def _factory(ns, args):
     from gym_comm_b200.vec_env import OvercookedVecEnv
-    from tests.parity_util import emu_library
-    return OvercookedVecEnv(ns, num_envs=args.envs, device="cpu", seed=args.env_seed, auto_reset=True, lib=emu_library())
+    from tests.parity_util import EmuVecEnv, emu_library
+    return EmuVecEnv(ns, num_envs=args.envs, device="cpu", seed=args.env_seed, auto_reset=True, lib=emu_library())
 
 
 def _worker(rank, world, port, flags, out):

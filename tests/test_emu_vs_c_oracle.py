@@ -11,7 +11,7 @@ import torch
 from gym_comm_b200 import levels_data
 from gym_comm_b200.vec_env import OvercookedVecEnv
 from oracle.c_oracle import COracle
-from tests.parity_util import emu_library
+from tests.parity_util import EmuVecEnv, emu_library
 
 D = dict(CAN_MOVE=True, ALLERGIC=False, BLIND=False)
 CONFIGS = {
@@ -52,7 +52,7 @@ def test_step_autoreset_terminal_obs(name, fmt, monkeypatch):
     text = cfg.pop("level_text", None) or levels_data.LEVELS[cfg["level"]]
     subtasks = levels_data.SUBTASKS[tuple(text.split("\n\n")[1].split("\n"))]
     E, n, seed = 75, cfg["num_agents"], 99
-    env = OvercookedVecEnv(argparse.Namespace(**cfg), num_envs=E, device="cpu", lib=emu_library(), seed=seed,
+    env = EmuVecEnv(argparse.Namespace(**cfg), num_envs=E, device="cpu", lib=emu_library(), seed=seed,
                            auto_reset=True, level_text=text)
     ora = COracle(text, subtasks, E, seed=seed, **{k: v for k, v in cfg.items() if k != "level"})
     rng = np.random.default_rng(5)

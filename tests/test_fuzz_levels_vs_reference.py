@@ -13,7 +13,7 @@ from oracle.drivers import GoalChaser
 from oracle.level_fuzz import random_level
 from oracle.spec_model import BIT, SpecEnv
 from gym_comm_b200.vec_env import OvercookedVecEnv
-from tests.parity_util import emu_library
+from tests.parity_util import EmuVecEnv, emu_library
 
 pytestmark = pytest.mark.skipif(not ref_harness.reference_available(), reason="needs /root/reference")
 
@@ -47,7 +47,7 @@ def test_random_kitchen(seed):
     pl = placements()
     spec = SpecEnv(text, subtasks, placements=pl, **okw)
     cora = COracle(text, subtasks, 1, **okw)
-    env = OvercookedVecEnv(ns, num_envs=1, device="cpu", auto_reset=False, lib=emu_library(),
+    env = EmuVecEnv(ns, num_envs=1, device="cpu", auto_reset=False, lib=emu_library(),
                            level_text=text, subtasks=subtasks)
     W = probe.W
 

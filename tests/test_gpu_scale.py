@@ -141,6 +141,16 @@ def test_random_streams_autoreset_vs_c_oracle(name, E, T):
     term = torch.full((E, n, env.obs_width), -7.0, device=DEV)
     term_o = np.full((E, n, env.obs_width), -7.0)
     check_every = 1 if E <= 70000 else 3
+    staggered = T <= cfg["max_num_timesteps"]
+    if staggered:
+        # the full-size batches run fewer steps than one episode lasts: start env e at clock T_max - 1 - (e mod 50), on
+        # the device through oc_get_state / oc_set_state and in the oracle, so that EVERY env crosses an episode
+        # boundary (time limit, in-place reset, fresh random placements) within the first 50 steps
+        clocks = (cfg["max_num_timesteps"] - 1 - (np.arange(E) % 50)).astype(np.uint32)
+        st0 = env.get_state()
+        st0[:, 0] = (st0[:, 0] & ~0xFFFF) | torch.from_numpy(clocks.astype(np.int32)).to(DEV)
+        env.set_state(st0)
+        ora.set_clocks(clocks)
     for t in range(T):
         a = torch.stack([torch.randint(0, 4, (E, n), generator=gen, device=DEV, dtype=torch.int32),
                          torch.randint(0, cfg["num_communication"], (E, n), generator=gen, device=DEV, dtype=torch.int32)], -1).contiguous()
@@ -157,7 +167,7 @@ def test_random_streams_autoreset_vs_c_oracle(name, E, T):
     assert np.array_equal(st["t"], os_["t"])
     assert np.array_equal(st["episodes"], os_["episodes"])
     assert np.array_equal(st["last_completed"], os_["last_completed"])
-    if T > cfg["max_num_timesteps"]:
+    if T > cfg["max_num_timesteps"] or (staggered and T >= 51):
         assert st["episodes"].min() >= 1
     env.close()
     ora.close()

@@ -4,11 +4,11 @@ the SURVEY A.7 known answer, the MultiAgentEnv step / reset protocol with an emb
 import pytest
 
 from tests import multienv_cases as cases
-from tests.parity_util import emu_library
+from tests.parity_util import EmuMultiEnv
 
 
 def _kw():
-    return dict(device="cpu", lib=emu_library())
+    return dict(device="cpu", env_cls=EmuMultiEnv)
 
 
 @pytest.mark.parametrize("name", cases.TRACES)

@@ -32,11 +32,11 @@ def _reference_extractor():
 @pytest.mark.parametrize("level,C", [("open-divider_tomato", 10), ("random-salad-superwide", 100)])
 def test_flat_rows_are_the_reference_extractor_output(level, C):
     from gym_comm_b200.vec_env import OvercookedVecEnv
-    from tests.parity_util import emu_library
+    from tests.parity_util import EmuVecEnv, emu_library
     ns = argparse.Namespace(level=level, num_agents=2, max_num_timesteps=30, communication_on=True, num_communication=C,
                             ego_led=False, fow_radius=2, ego_config=D, partner_config=D)
     E = 19
-    env = OvercookedVecEnv(ns, num_envs=E, device="cpu", seed=2, auto_reset=True, lib=emu_library())
+    env = EmuVecEnv(ns, num_envs=E, device="cpu", seed=2, auto_reset=True, lib=emu_library())
     ext = _reference_extractor()(env.observation_space)
     assert ext._features_dim == env.obs_width
     gen = torch.Generator().manual_seed(0)

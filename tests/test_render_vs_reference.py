@@ -8,7 +8,7 @@ from oracle import ref_harness
 from oracle.drivers import GoalChaser
 from oracle.spec_model import SpecEnv
 from gym_comm_b200.vec_env import OvercookedVecEnv
-from tests.parity_util import emu_library
+from tests.parity_util import EmuVecEnv, emu_library
 
 pytestmark = pytest.mark.skipif(not ref_harness.reference_available(), reason="needs /root/reference")
 
@@ -17,7 +17,7 @@ def test_render_matches_reference_display():
     ns = ref_harness.make_namespace("partial-divider_salad", max_num_timesteps=400)
     ref = ref_harness.LiveReference(ns)
     spec = SpecEnv(ref.level_text(), ref.subtask_strings(), max_num_timesteps=400)
-    env = OvercookedVecEnv(ns, num_envs=1, device="cpu", auto_reset=False, lib=emu_library(),
+    env = EmuVecEnv(ns, num_envs=1, device="cpu", auto_reset=False, lib=emu_library(),
                            subtasks=ref.subtask_strings())
     chaser = GoalChaser(spec, seed=4, p_random=0.1)
     # (right after reset() the reference's display buffer is empty until the first step, :188)

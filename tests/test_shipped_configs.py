@@ -14,7 +14,7 @@ import torch
 from gym_comm_b200 import create_arglist, levels_data
 from gym_comm_b200.vec_env import OvercookedVecEnv
 from oracle.c_oracle import COracle
-from tests.parity_util import emu_library
+from tests.parity_util import EmuVecEnv, emu_library
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference"
@@ -34,7 +34,7 @@ def test_config_compiles_and_steps_like_the_oracle(path):
         want.update(raw.get(side, {}))
         assert getattr(ns, side) == want
     E = 37
-    env = OvercookedVecEnv(ns, num_envs=E, device="cpu", seed=11, auto_reset=True, lib=emu_library())
+    env = EmuVecEnv(ns, num_envs=E, device="cpu", seed=11, auto_reset=True, lib=emu_library())
     assert env.obs_width == 23 + len(env.level.subtasks) + 2 * ns.num_communication
     text = levels_data.LEVELS[ns.level]
     subtasks = levels_data.SUBTASKS[tuple(text.split("\n\n")[1].split("\n"))]

@@ -9,7 +9,7 @@ import torch
 
 from gym_comm_b200.pantheon import PantheonVecEnv, SB3VecEnvAdapter
 from gym_comm_b200.vec_env import OvercookedVecEnv
-from tests.parity_util import emu_library
+from tests.parity_util import EmuVecEnv, emu_library
 
 D = dict(CAN_MOVE=True, ALLERGIC=False, BLIND=False)
 
@@ -17,7 +17,7 @@ D = dict(CAN_MOVE=True, ALLERGIC=False, BLIND=False)
 def make(E=5, T=6, **kw):
     ns = argparse.Namespace(level="open-divider_tomato", num_agents=2, max_num_timesteps=T, communication_on=True,
                             num_communication=4, ego_led=False, fow_radius=2, ego_config=D, partner_config=D)
-    return OvercookedVecEnv(ns, num_envs=E, device="cpu", lib=emu_library(), **kw)
+    return EmuVecEnv(ns, num_envs=E, device="cpu", lib=emu_library(), **kw)
 
 
 def test_spaces_layout_and_views():
@@ -120,7 +120,7 @@ def test_train_ppo_main_loop_on_the_emulated_env(flags):
     import train_ppo
 
     def factory(ns, args):
-        return OvercookedVecEnv(ns, num_envs=args.envs, device="cpu", seed=args.seed, auto_reset=True, lib=emu_library())
+        return EmuVecEnv(ns, num_envs=args.envs, device="cpu", seed=args.seed, auto_reset=True, lib=emu_library())
     hist = train_ppo.main(["--envs", "8", "--n-steps", "5", "--total-timesteps", "81", "--log-every", "1", "--batch-size", "20",
                            "--max-num-timesteps", "4", "--epochs", "1", "--eval-steps", "9", "--device", "cpu"] + flags,
                           env_factory=factory)
@@ -135,7 +135,7 @@ def test_pack_obs_i8_is_the_float_row_without_the_clock(E, C):
     4-byte output word straddles rows (F-1 = 33, 39, 225) and a batch whose byte count is not a multiple of 4."""
     ns = argparse.Namespace(level="open-divider_tomato", num_agents=2, max_num_timesteps=9, communication_on=True,
                             num_communication=C, ego_led=False, fow_radius=2, ego_config=D, partner_config=D)
-    env = OvercookedVecEnv(ns, num_envs=E, device="cpu", lib=emu_library(), auto_reset=True)
+    env = EmuVecEnv(ns, num_envs=E, device="cpu", lib=emu_library(), auto_reset=True)
     gen = torch.Generator().manual_seed(E)
     env.reset()
     for t in range(14):
@@ -158,7 +158,7 @@ def test_terminal_row_gather_on_the_emulation():
     E, Cn = 37, 5
     ns = argparse.Namespace(level="open-divider_tomato", num_agents=2, max_num_timesteps=9, communication_on=True,
                             num_communication=Cn, ego_led=False, fow_radius=2, ego_config=D, partner_config=D)
-    env = OvercookedVecEnv(ns, num_envs=E, device="cpu", lib=emu_library(), auto_reset=True)
+    env = EmuVecEnv(ns, num_envs=E, device="cpu", lib=emu_library(), auto_reset=True)
     F = env.obs_width
     rng = np.random.default_rng(0)
     term = np.ascontiguousarray(rng.integers(-9, 10, (E, 2, F)).astype(np.float32))
@@ -186,7 +186,7 @@ def test_saved_policies_play_through_evaluate_policy(tmp_path, flags):
     from gym_comm_b200.ppo import load_learner
 
     def factory(ns, args):
-        return OvercookedVecEnv(ns, num_envs=args.envs, device="cpu", seed=args.seed, auto_reset=True, lib=emu_library())
+        return EmuVecEnv(ns, num_envs=args.envs, device="cpu", seed=args.seed, auto_reset=True, lib=emu_library())
     d = str(tmp_path / "model")
     train_ppo.main(["--envs", "8", "--n-steps", "5", "--iters", "2", "--log-every", "1", "--batch-size", "20",
                     "--max-num-timesteps", "6", "--epochs", "1", "--device", "cpu", "--save-dir", d] + flags, env_factory=factory)
@@ -240,7 +240,7 @@ def test_state_injection_continues_identically(level, A):
     E, C, T = 45, 4, 13
     ns = argparse.Namespace(level=level, num_agents=A, max_num_timesteps=T, communication_on=True, num_communication=C,
                             ego_led=False, fow_radius=2, ego_config=D, partner_config=D)
-    a_env = OvercookedVecEnv(ns, num_envs=E, device="cpu", seed=9, auto_reset=True, lib=emu_library())
+    a_env = EmuVecEnv(ns, num_envs=E, device="cpu", seed=9, auto_reset=True, lib=emu_library())
     gen = torch.Generator().manual_seed(2)
 
     def act():
@@ -249,7 +249,7 @@ def test_state_injection_continues_identically(level, A):
     for _ in range(T + 5):                                  # past the first auto-reset
         a_env.step(act())
     st = a_env.get_state()
-    b_env = OvercookedVecEnv(ns, num_envs=E, device="cpu", seed=9, auto_reset=True, lib=emu_library())
+    b_env = EmuVecEnv(ns, num_envs=E, device="cpu", seed=9, auto_reset=True, lib=emu_library())
     b_env.set_state(st)
     assert torch.equal(b_env.get_state(), st)
     for t in range(2 * T):

@@ -1,12 +1,9 @@
 import sys, argparse, os
-os.environ['OC_TEST_EMULATION'] = '1'
 sys.path.insert(0, '/root/repo')
 import numpy as np, torch
-from gym_comm_b200 import _cabi
-from gym_comm_b200.vec_env import OvercookedVecEnv
 from tests.golden_util import golden_names, load_golden
-from tests.parity_util import replay_golden
-lib = _cabi.OcLibrary(sys.argv[1], prefix='emu_')
+from tests.parity_util import EmuLibrary, EmuVecEnv, replay_golden
+lib = EmuLibrary(sys.argv[1])
 for name in golden_names():
     meta, g = load_golden(name)
     replay_golden(meta, g, lib, 'cpu', num_envs=33)
@@ -19,7 +16,7 @@ for c in [dict(level="random-open-divider_salad_small_cramped", num_agents=2, ma
           dict(level="open-divider_salad", num_agents=4, max_num_timesteps=10, num_communication=7, fow_radius=1)]:
     ns = argparse.Namespace(communication_on=True, ego_led=False, ego_config=d, partner_config=d, **c)
     for E in (1, 33, 70):
-        env = OvercookedVecEnv(ns, num_envs=E, device='cpu', seed=3, lib=lib)
+        env = EmuVecEnv(ns, num_envs=E, device='cpu', seed=3, lib=lib)
         A, F = env.num_agents, env.obs_width
         rng = np.random.default_rng(0)
         term = torch.zeros((E, A, F))
