@@ -460,9 +460,9 @@ def main():
         henv = OvercookedHostVecEnv(ns, num_envs=E, device_index=local_rank, seed=1234 + rank, auto_reset=True,
                                     terminal_observations=term, obs_format=fmt)
         try:
-            host_actions = []                              # the steps' inputs live in pinned host memory
-            for i in range(8):
-                pa = henv.pinned_array((E, A, 2), "int32")
+            host_actions = []                              # the steps' inputs live in pinned host memory, in the dtype
+            for i in range(8):                             # the entry point takes (u8 pairs on the one-block path)
+                pa = henv.pinned_array((E, A, 2), henv.action_dtype)
                 pa[...] = host_action_src[i]
                 host_actions.append(pa)
             henv.reset()

@@ -7,7 +7,10 @@ episode's total reward, then the average and the standard deviation).
     python evaluate_policy.py -j env_args.json --ego-load model/tomato/ppo_ego.pt --alt-load model/tomato/ppo_partner1.pt -t 10000
 
 The games run `--envs` at a time on the device (`OvercookedVecEnv` + `PantheonVecEnv` with a
-`BatchedStaticPolicyAgent` partner).  Like the reference's `StaticPolicyAgent` both agents sample from their
+`BatchedStaticPolicyAgent` partner).  Every env plays a fixed QUOTA of games (N // E, the first N % E envs one
+more) and only those count: auto-resetting envs that stopped at "the first N finished games" would over-count
+short (successful) episodes, whose envs replay while the long ones are still running -- the reference plays its N
+games one after the other and has no such bias.  Like the reference's `StaticPolicyAgent` both agents sample from their
 policies; `--deterministic` takes the argmax instead.  `--render` prints env 0's ASCII display every step
 (`env.render()`, tester.py:79-91).  The last line is one JSON object with the statistics.
 """
@@ -37,7 +40,7 @@ def main(argv=None, env_factory=None):
     ap.add_argument("--deterministic", action="store_true")
     ap.add_argument("--render", action="store_true", help="print env 0 as it is being run")
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--max-steps", type=int, default=0, help="safety stop (0 = none; needed when max_num_timesteps is 0)")
+    ap.add_argument("--max-steps", type=int, default=0, help="safety stop after this many env steps (0 = none)")
     args = ap.parse_args(argv)
 
     if args.json_path:
@@ -57,31 +60,43 @@ def main(argv=None, env_factory=None):
     penv = PantheonVecEnv(env, BatchedStaticPolicyAgent(alt, args.deterministic))
 
     obs = penv.reset()
-    starts = torch.ones(args.envs, device=env.device)
-    stats = dict(episodes=0.0, ret=0.0, ret_sq=0.0, length=0.0, delivered=0.0)
+    E, dev = args.envs, env.device
+    starts = torch.ones(E, device=dev)
+    # per-env quota of games: exactly --total-episodes in all
+    quota = torch.full((E,), args.total_episodes // E, device=dev, dtype=torch.int64)
+    quota[:args.total_episodes % E] += 1
+    played = torch.zeros(E, device=dev, dtype=torch.int64)
+    ret = torch.zeros(E, device=dev, dtype=torch.float64)
+    length = torch.zeros(E, device=dev, dtype=torch.float64)
+    acc = torch.zeros(5, device=dev, dtype=torch.float64)          # games, sum return, sum return^2, sum length, delivered
+    T = float(ns.max_num_timesteps)
     steps = 0
     if args.render:
         print(env.render(0))
-    while stats["episodes"] < args.total_episodes and not (args.max_steps and steps >= args.max_steps):
+    while not (args.max_steps and steps >= args.max_steps):
         act = ego.act(obs, starts, deterministic=args.deterministic)[0]
-        obs, _, done = penv.step(act.to(torch.int32))
+        obs, rew, done = penv.step(act.to(torch.int32))
         starts = done.to(torch.float32)
         steps += 1
+        ret += rew
+        length += 1
+        d = done.bool()
+        m = d & (played < quota)                                     # this game is one of the env's quota
+        acc += torch.stack([m.sum(), (ret * m).sum(), (ret * ret * m).sum(), (length * m).sum(),
+                            (m & (length < T)).sum()]).to(torch.float64)
+        played += m
+        ret.masked_fill_(d, 0.0)
+        length.masked_fill_(d, 0.0)
         if args.render:
             print(env.render(0))
-        if steps % 16 == 0 or args.render:                                  # one host sync every 16 steps
-            ev = penv.pop_episode_stats()
-            n = ev["episodes"]
-            stats["episodes"] += n
-            stats["ret"] += ev["ep_rew_mean"] * n
-            stats["ret_sq"] += (ev["ep_rew_std"] ** 2 + ev["ep_rew_mean"] ** 2) * n
-            stats["length"] += ev["ep_len_mean"] * n
-            stats["delivered"] += ev["delivered_frac"] * n
-    n = max(stats["episodes"], 1.0)
-    mean = stats["ret"] / n
-    out = dict(episodes=int(stats["episodes"]), env_steps=steps * args.envs, average_reward=mean,
-               standard_deviation=max(stats["ret_sq"] / n - mean * mean, 0.0) ** 0.5,
-               ep_len_mean=stats["length"] / n, delivered_frac=stats["delivered"] / n)
+        if (steps % 16 == 0 or args.render) and bool((played >= quota).all()):   # one host sync every 16 steps
+            break
+    games, rsum, rsq, lsum, deliv = acc.tolist()
+    n = max(games, 1.0)
+    mean = rsum / n
+    out = dict(episodes=int(games), env_steps=steps * args.envs, average_reward=mean,
+               standard_deviation=max(rsq / n - mean * mean, 0.0) ** 0.5,
+               ep_len_mean=lsum / n, delivered_frac=deliv / n)
     print("Average Reward: ", out["average_reward"])
     print("Standard Deviation: ", out["standard_deviation"])
     print(json.dumps(out), flush=True)

@@ -142,7 +142,8 @@ __device__ __noinline__ void draw_random_cells(const OcParams& p, const uint8_t*
                                                uint32_t env_id, uint32_t episode, uint32_t* cell) {
     uint32_t r[8];
     philox4x32_10(env_id, episode, 0x52455345u, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), r);
-    philox4x32_10(env_id, episode, 0x52455345u, 1u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), r + 4);
+    if (p.nrandom > 4)       // every shipped random level places 3 objects: one block of four words is enough
+        philox4x32_10(env_id, episode, 0x52455345u, 1u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), r + 4);
     uint32_t sorted[OCK_MAX_OBJECTS];
     int n = 0;
     for (int j = 0; j < p.nrandom; ++j) {

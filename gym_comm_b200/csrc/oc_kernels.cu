@@ -79,13 +79,12 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, co
 #endif
     OC_PROBE(0, 0u);
 
-    // Prologue.  (1) One thread hands the table blob to the copy engine (TMA bulk load, completion on an mbarrier): the
-    // tables are constant, so this does not wait for the previous grid, and nobody stalls on it until the dynamics
-    // need them.  (2) Programmatic dependent launch: the NEXT launch may start as soon as every CTA of this grid is
-    // running; everything below the wait may touch what the previous grid wrote (state, actions).  Both
-    // griddepcontrol instructions are no-ops when the launch carries no PDL attribute.  (3) Inside the loop, the
-    // first chunk issues its state / action loads BEFORE the rows are cleared, so the clear (82 KB of shared-memory
-    // stores per CTA at cfg2) runs under the latency of those loads instead of in front of them.
+    // Prologue, all of it in front of the dependency wait, where it is free: with programmatic dependent launch a CTA of
+    // this grid enters the moment a CTA of the previous grid leaves its slot, and then has nothing to do until that grid
+    // has completed (tools/probe_step.py: median 0.4-1.3 us).  (1) One thread hands the table blob to the copy engine
+    // (TMA bulk load, completion on an mbarrier): nobody stalls on it until the dynamics need the tables.  (2) The
+    // warps clear their rows.  (3) griddepcontrol.wait: everything below may touch what the previous grid wrote
+    // (state, actions).  Both griddepcontrol instructions are no-ops when the launch carries no PDL attribute.
     __shared__ __align__(8) uint64_t tbar;
     if (threadIdx.x == 0) {
         mbar_init(&tbar, 1);
@@ -93,6 +92,8 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, co
     }
     asm volatile("griddepcontrol.launch_dependents;");
     uint8_t* wrows = smem + p.blob_bytes + (size_t)warp * p.warp_row_bytes;
+    warp_clear_rows<MODE != 0>(wrows, p.warp_row_bytes, lane);
+    __syncthreads();                                // mbarrier initialised by thread 0 -> visible to everyone
     OC_PROBE(1, 0u);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     OC_PROBE(2, 0u);
@@ -123,10 +124,8 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, co
             }
         }
         if (first) {
-            warp_clear_rows<MODE != 0>(wrows, p.warp_row_bytes, lane);
-            __syncthreads();                            // mbarrier initialised by thread 0 -> visible to everyone
+            mbar_wait(&tbar, 0);                        // tables have landed (long ago, as a rule)
             OC_PROBE(3, 0u);
-            mbar_wait(&tbar, 0);                        // tables have landed
         }
         if (valid) {                                    // dynamics: no row access, may overlap the previous chunk's TMA read
             unpack_env<A, NOBJ>(e, s0, s1, s2, s3);
@@ -500,7 +499,12 @@ extern "C" int oc_create(const oc_config* c, oc_env** out) {
     h->threads = best_t;
     h->smem_bytes = smem_for(p, best_t);
     h->step_grid = (int)std::min<long long>(((long long)p.E + best_t - 1) / best_t, (long long)num_sm * best_cap);
-    if (want8 && pick_cta(p8, caps8, num_sm, 32.0, getenv("OC_BLOCK_THREADS_I8"), best_t, best_cap)) {
+    // compact rows: small CTAs when the batch is a fraction of a wave (<= 16 warps of work per SM) -- the launch is then
+    // bound by the slowest CTA, and two-warp CTAs hand their slots over soonest (cfg2: 6.1 us vs 8.3 us with 256 threads,
+    // tools/step_sweep.py); larger batches amortise the table copy over more warps
+    const char* tenv8 = getenv("OC_BLOCK_THREADS_I8");
+    if (!tenv8 && (long long)p.E <= (long long)num_sm * 16 * 32 && caps8[2] >= 1) tenv8 = "64";
+    if (want8 && pick_cta(p8, caps8, num_sm, 32.0, tenv8, best_t, best_cap)) {
         h->c.threads = best_t;
         h->c.smem_bytes = smem_for(p8, best_t);
         h->c.step_grid = (int)std::min<long long>(((long long)p.E + best_t - 1) / best_t, (long long)num_sm * best_cap);

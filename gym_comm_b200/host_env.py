@@ -121,6 +121,8 @@ class OvercookedHostVecEnv:
             self.actions = self.pinned_array((E, A, 2), np.int32)
             self.actions_u8 = None
         self.dones = self._dones_padded[:E]
+        # what `step` takes without a conversion: [E, A, 2] of this dtype, ideally in `pinned_array` memory
+        self.action_dtype = np.dtype(np.uint8 if self._block_mode else np.int32)
         odt, Fo = (np.int8, F - 1) if i8 else (np.float32, F)
         self.terminal_obs = self.pinned_array((E, A, Fo), odt) if (terminal_observations and auto_reset) else None
         self.terminal_timestep = self.pinned_array((E,), np.float32) if (i8 and self.terminal_obs is not None) else None

@@ -195,11 +195,15 @@ def compile_level(level: str, num_agents: int, level_text: Optional[str] = None,
     if subtasks is None:
         key = tuple(recipes)
         if key not in levels_data.SUBTASKS:
-            raise LevelError("no canonical subtask table for recipes %r; pass subtasks=" % (key,))
+            raise LevelError("no recorded subtask table for the recipe list %r: tools/gen_levels_data.py records the "
+                             "reference's tables (every ordered selection of its four recipes without repetition); "
+                             "for anything else pass subtasks= with the reference's own all_subtasks" % (key,))
         subtasks = levels_data.SUBTASKS[key]
     subtasks = list(subtasks)
     if not 1 <= len(subtasks) <= MAX_SUBTASKS:
-        raise LevelError("1..%d subtasks supported" % MAX_SUBTASKS)
+        raise LevelError("the recipe list %r has %d subtasks; the packed state holds one bit per subtask and supports "
+                         "1..%d subtasks (every shipped level has at most 9; lists that combine OnionSalad with another "
+                         "recipe have 32-44)" % (tuple(recipes), len(subtasks), MAX_SUBTASKS))
     parsed = [parse_subtask(s) for s in subtasks]
     if not any(k == SUBTASK_KIND["Deliver"] for k, _, _ in parsed):
         raise LevelError("no delivery subtask")    # the reference asserts (:251)

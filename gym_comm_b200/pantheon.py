@@ -25,7 +25,8 @@ from .vec_env import OvercookedVecEnv
 
 
 class BatchedOnPolicyAgent:
-    """`OnPolicyAgent` (pantheonrl/common/agents.py:84-213) over E envs at once."""
+    """`OnPolicyAgent` (pantheonrl/common/agents.py:84-213) over E envs at once.  Its per-env state lives in tensors
+    that keep their address (updated in place), so a whole rollout can be captured in a CUDA graph (`GraphedRollout`)."""
 
     def __init__(self, model: PPO, name: str = "partner"):
         self.model = model
@@ -36,22 +37,31 @@ class BatchedOnPolicyAgent:
         self.iteration = 0
         self.last_train_stats = None
 
+    def maybe_train(self) -> bool:
+        """Train the model if the buffer is full (agents.py:127-160) -- the reference does this at the top of
+        `get_action`, i.e. inside the env step that follows the one which filled the buffer."""
+        buf = self.model.buffer
+        if not buf.full:
+            return False
+        buf.compute_returns_and_advantage(self._values, self._last_episode_starts)
+        self.last_train_stats = self.model.train()
+        self.iteration += 1
+        buf.reset()
+        return True
+
     def get_action(self, obs: torch.Tensor, record: bool = True) -> torch.Tensor:
         buf = self.model.buffer
-        if record and buf.full:                         # train the model if the buffer is full (:127-160)
-            buf.compute_returns_and_advantage(self._values, self._last_episode_starts)
-            self.last_train_stats = self.model.train()
-            self.iteration += 1
-            buf.reset()
+        if record:
+            self.maybe_train()
         actions, values, log_probs = self.model.act(obs, self._last_episode_starts)
         if record:
             buf.add(obs, actions, self._last_episode_starts, values, log_probs)
         self.num_timesteps += obs.shape[0]
-        self._values = values
+        self._values.copy_(values)
         return actions
 
     def update(self, reward: torch.Tensor, done: torch.Tensor) -> None:
-        self._last_episode_starts = done.to(torch.float32)
+        self._last_episode_starts.copy_(done)
         self.model.buffer.add_reward(reward)
 
 
@@ -70,12 +80,16 @@ class BatchedStaticPolicyAgent:
         return self.model.act(obs, self._starts, deterministic=self.deterministic)[0]
 
     def update(self, reward: torch.Tensor, done: torch.Tensor) -> None:
-        self._starts = done.to(torch.float32)
+        self._starts.copy_(done)
 
 
 class PantheonVecEnv:
     """Ego-centric batched env: `reset() -> ego_obs [E, F]`, `step(ego_actions [E, 2]) ->
-    (ego_obs, reward [E], done [E] u8)`; the partner acts and learns inside `step`."""
+    (ego_obs, reward [E], done [E] u8)`; the partner acts and learns inside `step`.
+
+    Observations live in a ring of `[slots, E, A, F]` rows the step kernel writes straight into (`obs_out`): the row
+    of step t is never copied again -- the partner reads its half in place, and after `attach_rollout_storage` the
+    rollout buffers of the ego and the partner learner ARE views of that ring."""
 
     def __init__(self, env: OvercookedVecEnv, partner: Optional[BatchedOnPolicyAgent] = None, ego_ind: int = 0,
                  reward_scale: float = 1.0):
@@ -93,8 +107,10 @@ class PantheonVecEnv:
         self.device = env.device
         E, F = self.num_envs, self.obs_dim
         self._actions = torch.zeros((E, 2, 2), dtype=torch.int32, device=self.device)
-        self._obs = torch.zeros((E, 2, F), device=self.device)
-        self._old_ego_obs = torch.zeros((E, F), device=self.device)
+        self._ring = torch.zeros((2, E, 2, F), device=self.device)        # slot p: what the agents see before step p
+        self._slot = 0
+        self._rew = torch.zeros((E, 2), device=self.device)
+        self._done = torch.zeros((E,), dtype=torch.uint8, device=self.device)
         self.terminal_obs = torch.zeros((E, F), device=self.device)
         self.ep_return = torch.zeros(E, device=self.device)
         self.ep_length = torch.zeros(E, device=self.device)
@@ -105,28 +121,55 @@ class PantheonVecEnv:
         self.finished_success = torch.zeros((), device=self.device)
         self.finished_return_sq = torch.zeros((), device=self.device, dtype=torch.float64)
 
+    @property
+    def _obs(self) -> torch.Tensor:
+        """[E, 2, F]: the observations both agents currently see."""
+        return self._ring[self._slot]
+
     def add_partner_agent(self, agent: BatchedOnPolicyAgent):
         self.partner = agent
 
+    def attach_rollout_storage(self, n_steps: int, *learners) -> None:
+        """Make the observation ring `n_steps + 1` slots long and point the rollout buffers of `learners` (player 0,
+        player 1) at it: `buffer.obs[t]` is then the view `ring[t, :, player]` the env itself wrote, and
+        `RolloutBuffer.add` finds the observation already in place.  After `n_steps` steps call `rollover()`."""
+        E, F = self.num_envs, self.obs_dim
+        cur = self._ring[self._slot].clone()
+        self._ring = torch.zeros((n_steps + 1, E, 2, F), device=self.device)
+        self._ring[0].copy_(cur)
+        self._slot = 0
+        for player, lr in enumerate(learners):
+            if lr is not None:
+                assert lr.buffer.n_steps == n_steps and lr.buffer.num_envs == E
+                lr.buffer.obs = self._ring[:n_steps, :, player]
+
+    def rollover(self) -> None:
+        """The last slot becomes the first of the next rollout (one [E, 2, F] copy per rollout)."""
+        if self._slot != 0:
+            self._ring[0].copy_(self._ring[self._slot])
+            self._slot = 0
+
     def reset(self) -> torch.Tensor:
-        self._obs.copy_(self.env.reset())
-        self._old_ego_obs.copy_(self._obs[:, 0])
+        self._slot = 0
+        self.env.reset(obs_out=self._ring[0])
         self.ep_return.zero_()
         self.ep_length.zero_()
-        return self._obs[:, 0]
+        return self._ring[0][:, 0]
 
     def step(self, ego_actions: torch.Tensor):
         assert self.partner is not None, "add_partner_agent first (multiagentenv.py:92-101)"
-        partner_actions = self.partner.get_action(self._obs[:, 1])           # _get_actions (:149-161)
+        cur = self._ring[self._slot]
+        nxt_slot = (self._slot + 1) % self._ring.shape[0]
+        partner_actions = self.partner.get_action(cur[:, 1])                 # _get_actions (:149-161)
         self._actions[:, 0].copy_(ego_actions)
         self._actions[:, 1].copy_(partner_actions)
-        prev_ego = self._obs[:, 0].clone()
-        obs, rew, done = self.env.step(self._actions)                        # n_step -> multi_step
-        self._obs.copy_(obs)
+        # n_step -> multi_step: the kernel writes the next observations into the next ring slot
+        obs, rew, done = self.env.step(self._actions, obs_out=self._ring[nxt_slot], rew_out=self._rew, done_out=self._done)
         self.partner.update(rew[:, 1] * self.reward_scale, done)             # _update_players (:163-170)
         d = done.bool()
-        self.terminal_obs = torch.where(d[:, None], prev_ego, self.terminal_obs)   # "old ego obs" (:206-208)
-        # episode bookkeeping
+        torch.where(d[:, None], cur[:, 0], self.terminal_obs, out=self.terminal_obs)   # "old ego obs" (:206-208)
+        self._slot = nxt_slot
+        # episode bookkeeping (in place: the tensors keep their addresses)
         self.ep_return += rew[:, 0]
         self.ep_length += 1
         T = float(self.env.arglist.max_num_timesteps)
@@ -135,9 +178,9 @@ class PantheonVecEnv:
         self.finished_length_sum += (self.ep_length * d).sum()
         self.finished_return_sq += (self.ep_return.double() ** 2 * d).sum()
         self.finished_success += (d & (self.ep_length < T)).sum()             # ended by delivery, not by the clock
-        self.ep_return = torch.where(d, torch.zeros_like(self.ep_return), self.ep_return)
-        self.ep_length = torch.where(d, torch.zeros_like(self.ep_length), self.ep_length)
-        return self._obs[:, 0], rew[:, 0] * self.reward_scale, done
+        self.ep_return.masked_fill_(d, 0.0)
+        self.ep_length.masked_fill_(d, 0.0)
+        return obs[:, 0], rew[:, 0] * self.reward_scale, done
 
     def pop_episode_stats(self):
         """Host read (one sync) of the episode statistics accumulated since the last call; summed over the
@@ -164,11 +207,9 @@ class PantheonVecEnv:
         return out
 
 
-def collect_and_train(penv: PantheonVecEnv, ego: PPO, obs: torch.Tensor, episode_starts: torch.Tensor):
-    """One ego iteration: fill the ego buffer with n_steps of experience (the partner records and
-    trains on its own schedule inside penv.step), then one PPO update.  Mirrors
-    `collect_rollouts` + `train` of `OnPolicyAlgorithm.learn`
-    (sb3_contrib/ppo_recurrent/ppo_recurrent.py:195-312) without the per-step host syncs."""
+def collect_rollout(penv: PantheonVecEnv, ego: PPO, obs: torch.Tensor, episode_starts: torch.Tensor):
+    """`collect_rollouts` (sb3_contrib/ppo_recurrent/ppo_recurrent.py:195-310) over [E] tensors without its per-step
+    host synchronisations: n_steps x (ego acts and records, the partner acts / records / learns inside `penv.step`)."""
     buf = ego.buffer
     buf.reset()
     for _ in range(buf.n_steps):
@@ -177,10 +218,72 @@ def collect_and_train(penv: PantheonVecEnv, ego: PPO, obs: torch.Tensor, episode
         obs, rew, done = penv.step(actions.to(torch.int32))
         buf.add_reward(rew)
         episode_starts = done.to(torch.float32)
+    return obs, episode_starts
+
+
+def collect_and_train(penv: PantheonVecEnv, ego: PPO, obs: torch.Tensor, episode_starts: torch.Tensor):
+    """One ego iteration: fill the ego buffer with n_steps of experience (the partner records and
+    trains on its own schedule inside penv.step), then one PPO update.  Mirrors
+    `collect_rollouts` + `train` of `OnPolicyAlgorithm.learn`
+    (sb3_contrib/ppo_recurrent/ppo_recurrent.py:195-312) without the per-step host syncs."""
+    obs, episode_starts = collect_rollout(penv, ego, obs, episode_starts)
     last_values = ego.value(obs, episode_starts)
-    buf.compute_returns_and_advantage(last_values, episode_starts)
+    ego.buffer.compute_returns_and_advantage(last_values, episode_starts)
     stats = ego.train()
     return obs, episode_starts, stats
+
+
+class GraphedRollout:
+    """A whole rollout -- n_steps x [ego policy, partner policy, `oc_step`, rollout-buffer writes, episode
+    bookkeeping] -- captured ONCE in a CUDA graph and replayed per iteration: a rollout step is a few hundred tiny
+    launches, and replaying them costs the GPU time of the kernels instead of the host time of issuing them.
+
+    Needs feed-forward learners (their per-env state is the rollout buffer; the LSTM learner carries Python-side
+    state) and the ring storage of `PantheonVecEnv.attach_rollout_storage`, so that every tensor the graph touches
+    keeps its address.  The partner's own update ("train when the buffer is full", the first thing its next
+    `get_action` does in the reference) runs between replays, which is exactly where the reference runs it."""
+
+    def __init__(self, penv: PantheonVecEnv, ego: PPO):
+        if not isinstance(ego, PPO) or not isinstance(getattr(penv.partner, "model", None), PPO):
+            raise TypeError("GraphedRollout needs feed-forward PPO learners for ego and partner")
+        self.penv, self.ego = penv, ego
+        n = ego.buffer.n_steps
+        assert penv.partner.model.buffer.n_steps == n, "ego and partner must roll out the same number of steps"
+        penv.attach_rollout_storage(n, ego, penv.partner.model)
+        self.starts = torch.ones(penv.num_envs, device=penv.device)       # episode starts seen by the first step
+        self.graph = None
+        self.replays = 0
+
+    def _body(self):
+        penv, ego = self.penv, self.ego
+        obs = penv._ring[0][:, 0]
+        obs, starts = collect_rollout(penv, ego, obs, self.starts)
+        self.starts.copy_(starts)
+        penv.rollover()
+        return penv._ring[0][:, 0]
+
+    def run(self):
+        """One rollout.  -> (ego observation after it, episode starts), both tensors that keep their address."""
+        penv, ego, partner = self.penv, self.ego, self.penv.partner
+        partner.maybe_train()                         # the partner's buffer filled up during the previous rollout
+        n = ego.buffer.n_steps
+        if self.graph is None and self.replays >= 1:  # the first rollout ran eagerly (warm-up); capture the second
+            torch.cuda.synchronize(penv.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body()
+            self.graph = g
+            # capture records, it does not execute: rewind the Python-side counters the body advanced
+            partner.num_timesteps -= n * penv.num_envs
+        if self.graph is not None:
+            self.graph.replay()
+            ego.buffer.pos = n
+            partner.model.buffer.pos = n
+            partner.num_timesteps += n * penv.num_envs
+        else:
+            self._body()
+        self.replays += 1
+        return penv._ring[0][:, 0], self.starts
 
 
 class SB3VecEnvAdapter:

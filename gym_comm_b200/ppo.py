@@ -73,6 +73,29 @@ def average_gradients(module: nn.Module) -> None:
         o += p.numel()
 
 
+class Cat:
+    """Categorical over the last axis of `logits` with the four things PPO needs.  No argument validation and no host
+    synchronisation (torch.distributions checks its inputs with `.all()`), so it can sit inside a CUDA graph; sampling
+    is Gumbel-max over torch's own (graph-safe) Philox stream."""
+
+    def __init__(self, logits):
+        self.logp = torch.log_softmax(logits, -1)
+
+    @property
+    def probs(self):
+        return self.logp.exp()
+
+    def sample(self):
+        u = torch.rand_like(self.logp)
+        return (self.logp - torch.log(-torch.log(u))).argmax(-1)
+
+    def log_prob(self, a):
+        return self.logp.gather(-1, a.unsqueeze(-1)).squeeze(-1)
+
+    def entropy(self):
+        return -(self.logp.exp() * self.logp).sum(-1)
+
+
 class ActorCritic(nn.Module):
     """obs [.., F] -> logits over nav (4) and message (C), value."""
 
@@ -90,8 +113,7 @@ class ActorCritic(nn.Module):
 
     def _dists(self, obs):
         logits = self.action_head(self.pi(obs))
-        return (torch.distributions.Categorical(logits=logits[..., :self.num_nav]),
-                torch.distributions.Categorical(logits=logits[..., self.num_nav:]))
+        return Cat(logits[..., :self.num_nav]), Cat(logits[..., self.num_nav:])
 
     def value(self, obs):
         return self.value_head(self.vf(obs)).squeeze(-1)
@@ -117,6 +139,8 @@ class RolloutBuffer:
     def __init__(self, n_steps: int, num_envs: int, obs_dim: int, device, gamma=0.99, gae_lambda=0.95):
         self.n_steps, self.num_envs, self.gamma, self.gae_lambda = n_steps, num_envs, gamma, gae_lambda
         kw = dict(device=device)
+        # `obs` may be re-pointed at a view of storage the ENV writes (PantheonVecEnv.attach_rollout_storage): the step
+        # kernel then fills the rollout buffer itself and `add` has nothing to copy
         self.obs = torch.zeros((n_steps, num_envs, obs_dim), **kw)
         self.actions = torch.zeros((n_steps, num_envs, 2), dtype=torch.int64, **kw)
         self.rewards = torch.zeros((n_steps, num_envs), **kw)
@@ -137,7 +161,8 @@ class RolloutBuffer:
 
     def add(self, obs, actions, episode_starts, values, log_probs):
         p = self.pos
-        self.obs[p].copy_(obs)
+        if obs.data_ptr() != self.obs[p].data_ptr():       # already in place when the env wrote this slot itself
+            self.obs[p].copy_(obs)
         self.actions[p].copy_(actions)
         self.episode_starts[p].copy_(episode_starts)
         self.values[p].copy_(values)
@@ -158,7 +183,7 @@ class RolloutBuffer:
             delta = self.rewards[step] + self.gamma * next_values * next_non_terminal - self.values[step]
             last_gae = delta + self.gamma * self.gae_lambda * next_non_terminal * last_gae
             self.advantages[step] = last_gae
-        self.returns = self.advantages + self.values
+        torch.add(self.advantages, self.values, out=self.returns)
 
 
 @dataclass
@@ -175,6 +200,8 @@ class PPOConfig:
     ent_coef: float = 0.01
     vf_coef: float = 0.5
     max_grad_norm: float = 0.5
+    cuda_graph: bool = True      # capture the minibatch update (gather, forward, backward, clip, Adam) in a CUDA graph when
+                                 # the learner sits on a GPU and trains alone (one process); eager otherwise
 
     @staticmethod
     def from_hyperparams(h: dict, **over):
@@ -199,9 +226,12 @@ class PPO:
             torch.manual_seed(int(torch.randint(0, 2 ** 31 - 1, (1,), generator=gen)))
             self.policy = ActorCritic(obs_dim, num_nav, num_comm).to(self.device)
         broadcast_parameters(self.policy)
-        self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.learning_rate, eps=1e-5)
+        on_gpu = self.device.type == "cuda"
+        self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.learning_rate, eps=1e-5,
+                                          **(dict(fused=True, capturable=True) if on_gpu else {}))
         self.buffer = RolloutBuffer(self.cfg.n_steps, num_envs, obs_dim, self.device, self.cfg.gamma, self.cfg.gae_lambda)
         self.n_updates = 0
+        self._graph = None           # (CUDAGraph, static index buffer, static stats) of the captured minibatch update
 
     # uniform entry points of the rollout code (the recurrent learner keeps LSTM state behind them)
     def act(self, obs, episode_starts=None, deterministic: bool = False):
@@ -211,40 +241,73 @@ class PPO:
         with torch.no_grad():
             return self.policy.value(obs)
 
+    def _minibatch(self, obs, actions, old_logp, adv_all, ret, idx, acc):
+        """One clipped-surrogate update on the samples `idx`; the five statistics are ADDED to `acc` on the device (no
+        host synchronisation, so the call can be captured in a CUDA graph)."""
+        c = self.cfg
+        values, logp, ent = self.policy.evaluate(obs[idx], actions[idx])
+        adv = adv_all[idx]
+        adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+        olp = old_logp[idx]
+        ratio = torch.exp(logp - olp)
+        pg = -torch.min(adv * ratio, adv * torch.clamp(ratio, 1 - c.clip_range, 1 + c.clip_range)).mean()
+        vf = torch.nn.functional.mse_loss(values, ret[idx])
+        entm = ent.mean()
+        loss = pg + c.vf_coef * vf - c.ent_coef * entm
+        self.optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        average_gradients(self.policy)
+        nn.utils.clip_grad_norm_(self.policy.parameters(), c.max_grad_norm)
+        self.optimizer.step()
+        with torch.no_grad():
+            acc += torch.stack([pg.detach(), vf.detach(), entm.detach(),
+                                ((ratio - 1).abs() > c.clip_range).float().mean(), (olp - logp).mean().detach()])
+
     def train(self):
-        """One PPO update over the (full) rollout buffer.  Returns a dict of float stats."""
+        """One PPO update over the (full) rollout buffer.  Returns a dict of float stats (ONE host read at the end)."""
         c, b = self.cfg, self.buffer
         n = b.n_steps * b.num_envs
-        obs = b.obs.reshape(n, -1)
+        if b.obs.is_contiguous():
+            obs = b.obs.view(n, -1)
+        else:                                       # a strided view of the env's own storage: one gather per update, into a
+            if getattr(self, "_obs_flat", None) is None or self._obs_flat.shape[0] != n:    # buffer that keeps its address
+                self._obs_flat = torch.empty((n, b.obs.shape[-1]), device=self.device)
+            self._obs_flat.view(b.obs.shape).copy_(b.obs)
+            obs = self._obs_flat
         actions = b.actions.reshape(n, 2)
         old_logp, adv_all, ret = b.log_probs.reshape(n), b.advantages.reshape(n), b.returns.reshape(n)
         bs = min(c.batch_size, n)
-        stats = dict(pg=0.0, vf=0.0, ent=0.0, clipfrac=0.0, kl=0.0, n=0)
+        acc = torch.zeros(5, device=self.device)
+        nmb = 0
+        # The first update runs eagerly (it is also the warm-up every capture needs); from the second one on, the whole
+        # minibatch update -- gather, forward, backward, gradient clipping, the (capturable, fused) Adam step -- is ONE
+        # CUDA graph over static tensors, replayed per minibatch with a fresh index vector.
+        graphed = c.cuda_graph and self.device.type == "cuda" and _world() == 1 and self.n_updates > 0
+        if graphed:
+            g = self._graph
+            key = (n, bs, obs.data_ptr(), actions.data_ptr(), old_logp.data_ptr(), adv_all.data_ptr(), ret.data_ptr())
+            if g is None or g["key"] != key:
+                idx_buf = torch.zeros(bs, dtype=torch.int64, device=self.device)
+                acc_buf = torch.zeros(5, device=self.device)
+                graph = torch.cuda.CUDAGraph()
+                self.optimizer.zero_grad(set_to_none=True)
+                torch.cuda.synchronize(self.device)
+                with torch.cuda.graph(graph):
+                    self._minibatch(obs, actions, old_logp, adv_all, ret, idx_buf, acc_buf)
+                g = self._graph = dict(key=key, graph=graph, idx=idx_buf, acc=acc_buf)
+            g["acc"].zero_()
         for _ in range(c.n_epochs):
             perm = torch.randperm(n, device=self.device)
             for i in range(0, n - bs + 1, bs):
-                idx = perm[i:i + bs]
-                values, logp, ent = self.policy.evaluate(obs[idx], actions[idx])
-                adv = adv_all[idx]
-                adv = (adv - adv.mean()) / (adv.std() + 1e-8)
-                ratio = torch.exp(logp - old_logp[idx])
-                pg = -torch.min(adv * ratio, adv * torch.clamp(ratio, 1 - c.clip_range, 1 + c.clip_range)).mean()
-                vf = torch.nn.functional.mse_loss(values, ret[idx])
-                loss = pg + c.vf_coef * vf - c.ent_coef * ent.mean()
-                self.optimizer.zero_grad(set_to_none=True)
-                loss.backward()
-                average_gradients(self.policy)
-                nn.utils.clip_grad_norm_(self.policy.parameters(), c.max_grad_norm)
-                self.optimizer.step()
-                with torch.no_grad():
-                    stats["pg"] += float(pg); stats["vf"] += float(vf); stats["ent"] += float(ent.mean())
-                    stats["clipfrac"] += float(((ratio - 1).abs() > c.clip_range).float().mean())
-                    stats["kl"] += float((old_logp[idx] - logp).mean())
-                    stats["n"] += 1
+                if graphed:
+                    g["idx"].copy_(perm[i:i + bs])
+                    g["graph"].replay()
+                else:
+                    self._minibatch(obs, actions, old_logp, adv_all, ret, perm[i:i + bs], acc)
+                nmb += 1
         self.n_updates += 1
-        k = max(stats.pop("n"), 1)
-        return {a: v / k for a, v in stats.items()}
-
+        vals = ((g["acc"] if graphed else acc) / max(nmb, 1)).tolist()
+        return dict(zip(("pg", "vf", "ent", "clipfrac", "kl"), vals))
 
 # ------------------------------------------------------------------------------------------------
 # Recurrent learner: what the reference actually trains (`RecurrentPPO("MultiInputPolicy", ...)`,
@@ -281,8 +344,7 @@ class RecurrentActorCritic(nn.Module):
         hv, cv = self.lstm_vf(obs, (state[2] * keep, state[3] * keep))
         logits = self.action_head(self.pi(hp))
         value = self.value_head(self.vf(hv)).squeeze(-1)
-        return (torch.distributions.Categorical(logits=logits[..., :self.num_nav]),
-                torch.distributions.Categorical(logits=logits[..., self.num_nav:]), value, (hp, cp, hv, cv))
+        return Cat(logits[..., :self.num_nav]), Cat(logits[..., self.num_nav:]), value, (hp, cp, hv, cv)
 
 
 class RecurrentPPO:
@@ -338,7 +400,8 @@ class RecurrentPPO:
         c, b = self.cfg, self.buffer
         E, T = b.num_envs, b.n_steps
         envs_per_batch = max(1, min(E, c.batch_size // T))
-        stats = dict(pg=0.0, vf=0.0, ent=0.0, clipfrac=0.0, kl=0.0, n=0)
+        acc = torch.zeros(5, device=self.device)             # statistics stay on the device until the update is over
+        nmb = 0
         for _ in range(c.n_epochs):
             perm = torch.randperm(E, device=self.device)
             for i in range(0, E - envs_per_batch + 1, envs_per_batch):
@@ -350,20 +413,19 @@ class RecurrentPPO:
                 ratio = torch.exp(logp - old_logp)
                 pg = -torch.min(adv * ratio, adv * torch.clamp(ratio, 1 - c.clip_range, 1 + c.clip_range)).mean()
                 vf = torch.nn.functional.mse_loss(values, b.returns[:, idx])
-                loss = pg + c.vf_coef * vf - c.ent_coef * ent.mean()
+                entm = ent.mean()
+                loss = pg + c.vf_coef * vf - c.ent_coef * entm
                 self.optimizer.zero_grad(set_to_none=True)
                 loss.backward()
                 average_gradients(self.policy)
                 nn.utils.clip_grad_norm_(self.policy.parameters(), c.max_grad_norm)
                 self.optimizer.step()
                 with torch.no_grad():
-                    stats["pg"] += float(pg); stats["vf"] += float(vf); stats["ent"] += float(ent.mean())
-                    stats["clipfrac"] += float(((ratio - 1).abs() > c.clip_range).float().mean())
-                    stats["kl"] += float((old_logp - logp).mean())
-                    stats["n"] += 1
+                    acc += torch.stack([pg.detach(), vf.detach(), entm.detach(),
+                                        ((ratio - 1).abs() > c.clip_range).float().mean(), (old_logp - logp).mean().detach()])
+                nmb += 1
         self.n_updates += 1
-        k = max(stats.pop("n"), 1)
-        return {a: v / k for a, v in stats.items()}
+        return dict(zip(("pg", "vf", "ent", "clipfrac", "kl"), (acc / max(nmb, 1)).tolist()))
 
 
 # ------------------------------------------------------------------------------------------------

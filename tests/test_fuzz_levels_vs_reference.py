@@ -27,7 +27,52 @@ def test_random_kitchen(seed):
               ego_config=dict(BLIND=(seed % 6 == 5)), partner_config=dict(ALLERGIC=(seed % 9 == 4)))
     ns = ref_harness.make_namespace("fuzz-%d" % seed, **kw)
     ref = ref_harness.LiveReference(ns, py_random_seed=seed, level_text=text)
-    subtasks = ref.subtask_strings()
+    lockstep(ref, ns, text, ref.subtask_strings(), n, seed, 160)
+
+
+# every recipe list the reference's four recipes allow has a recorded subtask table (tools/gen_levels_data.py); a
+# sample of them -- every single recipe, pairs in both orders, a triple, the largest list that fits 32 subtasks --
+# is re-derived from the live reference here and driven in lock-step on a kitchen that holds all foods
+SYNTH = "--/--*-\nt     l\n-     o\n-     p\n---p---\n\n%s\n\n1 1\n5 1\n"
+RECIPE_LISTS = [("SimpleTomato",), ("SimpleLettuce",), ("Salad",), ("OnionSalad",), ("SimpleLettuce", "SimpleTomato"),
+                ("SimpleTomato", "SimpleLettuce"), ("Salad", "SimpleLettuce"), ("SimpleTomato", "Salad"),
+                ("OnionSalad", "SimpleTomato"), ("Salad", "SimpleTomato", "SimpleLettuce")]
+
+
+@pytest.mark.parametrize("recipes", RECIPE_LISTS, ids=lambda r: "+".join(r))
+def test_recorded_subtask_tables_drive_every_recipe_list(recipes):
+    from gym_comm_b200 import levels_data
+    text = SYNTH % "\n".join(recipes)
+    ns = ref_harness.make_namespace("synthetic", max_num_timesteps=70, num_communication=4)
+    ref = ref_harness.LiveReference(ns, py_random_seed=1, level_text=text)
+    table = levels_data.SUBTASKS[tuple(recipes)]
+    if ref_harness.hashseed_is_canonical():          # the ORDER is the reference's at PYTHONHASHSEED=0
+        assert ref.subtask_strings() == table
+    else:
+        assert sorted(ref.subtask_strings()) == sorted(table)
+    assert len(table) <= 32
+    lockstep(ref, ns, text, ref.subtask_strings(), 2, 3, 120)
+
+
+def test_every_recipe_list_has_a_table_and_wide_ones_fail_by_name():
+    import itertools
+    from gym_comm_b200 import levels_data
+    from gym_comm_b200.level_compiler import LevelError, compile_level
+    names = ("SimpleTomato", "SimpleLettuce", "Salad", "OnionSalad")
+    for k in range(1, 5):
+        for recipes in itertools.permutations(names, k):
+            table = levels_data.SUBTASKS[recipes]
+            if len(table) <= 32:
+                lv = compile_level("synthetic", 2, level_text=SYNTH % "\n".join(recipes))
+                assert lv.subtasks == table
+            else:
+                with pytest.raises(LevelError, match="32 subtasks"):
+                    compile_level("synthetic", 2, level_text=SYNTH % "\n".join(recipes))
+    with pytest.raises(LevelError, match="gen_levels_data"):
+        compile_level("synthetic", 2, level_text=SYNTH % "Salad\nSalad")
+
+
+def lockstep(ref, ns, text, subtasks, n, seed, steps):
     probe = SpecEnv.__new__(SpecEnv)
     probe.n = n
     probe._parse_level(text)
@@ -71,7 +116,7 @@ def test_random_kitchen(seed):
             assert np.array_equal(o_e[0, k].numpy(), want.astype(np.float32)), (tag, k, "device code")
 
     check_obs(o_c, o_e, "reset")
-    for i in range(160):
+    for i in range(steps):
         navs, comms = chaser.act()
         try:
             r, d = ref.step(navs, comms)

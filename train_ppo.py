@@ -19,7 +19,7 @@ import torch
 import torch.distributed as dist
 
 from gym_comm_b200 import OvercookedVecEnv, create_arglist, namespace_from_dict
-from gym_comm_b200.pantheon import BatchedOnPolicyAgent, PantheonVecEnv, collect_and_train
+from gym_comm_b200.pantheon import BatchedOnPolicyAgent, GraphedRollout, PantheonVecEnv, collect_and_train
 from gym_comm_b200.ppo import PPO, PPOConfig, RecurrentPPO, save_learner
 from gym_comm_b200.sharding import rank_world, shard_seed
 
@@ -47,6 +47,8 @@ def main(argv=None, env_factory=None, learners_out=None):
     ap.add_argument("--recurrent", action="store_true",
                     help="LSTM actor-critic for both learners (the reference's RecurrentPPO, trainer.py:92-121)")
     ap.add_argument("--lstm-hidden", type=int, default=256)
+    ap.add_argument("--no-graph", action="store_true",
+                    help="issue every rollout step and every minibatch update from Python instead of replaying CUDA graphs")
     ap.add_argument("--log-every", type=int, default=10)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--device", default="cuda:0")
@@ -99,17 +101,30 @@ def main(argv=None, env_factory=None, learners_out=None):
         args.iters = max(1, -(-args.total_timesteps // per_iter))
     obs = penv.reset()
     starts = torch.ones(args.envs, device=env.device)
+    # On a GPU with feed-forward learners the rollout is ONE CUDA graph (n_steps x [ego policy, partner policy, oc_step,
+    # buffer writes]; the step kernel writes the observations straight into the rollout buffers' storage) and so is each
+    # learner's minibatch update (ppo.PPO.train); `--no-graph` keeps the eager loop, which is also what the LSTM learner
+    # and the CPU tests use.  The rollout has no collective in it, so it is graphed under torchrun too.
+    cfg.cuda_graph = not args.no_graph
+    graphed = (not args.no_graph) and (not args.recurrent) and env.device.type == "cuda"
+    roll = GraphedRollout(penv, ego) if graphed else None
     t0 = time.time()
     steps = 0
     history = []
     for it in range(1, args.iters + 1):
-        obs, starts, stats = collect_and_train(penv, ego, obs, starts)
+        if roll is not None:
+            obs, starts = roll.run()
+            last_values = ego.value(obs, starts)
+            ego.buffer.compute_returns_and_advantage(last_values, starts)
+            stats = ego.train()
+        else:
+            obs, starts, stats = collect_and_train(penv, ego, obs, starts)
         steps += args.n_steps * args.envs * world
         if it % args.log_every == 0 or it == args.iters:
             ep = penv.pop_episode_stats()
             dt = time.time() - t0
-            line = dict(iter=it, env_steps=steps, agent_steps_per_s=2 * steps / dt, wall_s=dt, world=world, **ep,
-                        ego_loss=stats, partner_updates=partner.iteration)
+            line = dict(iter=it, env_steps=steps, agent_steps_per_s=2 * steps / dt, wall_s=dt, world=world,
+                        cuda_graphs=bool(graphed), **ep, ego_loss=stats, partner_updates=partner.iteration)
             history.append(line)
             if rank == 0:
                 print(json.dumps(line), flush=True)
@@ -125,7 +140,7 @@ def main(argv=None, env_factory=None, learners_out=None):
                 return partner.model.act(o, self.starts, deterministic=True)[0]
 
             def update(self, r, d):
-                self.starts = d.to(torch.float32)
+                self.starts.copy_(d)
         penv.add_partner_agent(_Frozen())
         ego_starts = torch.ones(args.envs, device=env.device)
         for _ in range(args.eval_steps):
