@@ -173,6 +173,7 @@ class Bench:
         self.torch, self.wname, self.w = torch, wname, WORKLOADS[wname]
         self.rank, self.world, self.dev = rank, world, dev
         self.peak, self.peak_src, self.no_graph = peak, peak_src, no_graph
+        self.chain = None            # True: the step API's K steps form one chain (head + chained launches) per graph
         self.ns = workload_namespace(self.w)
         self.E, self.A = E, self.ns.num_agents
         self.env = OvercookedVecEnv(self.ns, num_envs=E, device=dev, seed=1234 + rank, auto_reset=True)
@@ -226,10 +227,10 @@ class Bench:
             torch.distributed.barrier()
         torch.cuda.synchronize(self.dev)
 
-    def do_step(self, i):
+    def do_step(self, i, chain=None):
         R, P = self.R, self.P
         self.env.step(self.actions[i % P], obs_out=self.obs_ring[i % R], rew_out=self.rew_ring[i % R],
-                      done_out=self.done_ring[i % R])
+                      done_out=self.done_ring[i % R], chain=chain)
 
     def do_rollout(self, n):
         self.env.rollout(n, obs_out=self.obs_ring[:n], rew_out=self.rew_ring[:n], done_out=self.done_ring[:n])
@@ -256,13 +257,13 @@ class Bench:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     for j in range(G):
-                        self.do_step(g0 + j)
+                        self.do_step(g0 + j, (("head" if j == 0 else "next") if self.chain else None))
                 graphs.append(g)
             if K % G:
                 tail_graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(tail_graph):
                     for j in range(K % G):
-                        self.do_step(j)
+                        self.do_step(j, (("head" if j == 0 else "next") if self.chain else None))
             self.barrier()
         capture_launches = env.launch_count() - launches0
 
@@ -276,7 +277,7 @@ class Bench:
                 return K
             if mode == "step":
                 for i in range(K):
-                    self.do_step(rep * K + i)
+                    self.do_step(rep * K + i, (("head" if i == 0 else "next") if self.chain else None))
                 return K
             i, n_l = 0, 0
             while i < K:
@@ -374,11 +375,14 @@ class Bench:
                             "p10_ms": ms_max[len(ms_max) // 10], "p90_ms": ms_max[(len(ms_max) * 9) // 10]},
                 "gpu_launches": int(nlaunch), "captured_launches": int(capture_launches),
                 "clocks": sampler.summary() if sampler is not None else None,
-                "cuda_graphs": bool(graphs), "resets_per_step": self.resets_per_step}
+                "cuda_graphs": bool(graphs), "resets_per_step": self.resets_per_step,
+                "chained": bool(self.chain) if mode == "step" else None}
 
 
 DESC = {"rollout": "fused oc_rollout (up to R steps per launch, Philox actions drawn on the device, state on chip)",
-        "step": "C-ABI oc_step, one launch per step, actions read from an HBM pool, CUDA graphs of min(K, R) launches"}
+        "step": "C-ABI oc_step, one launch per step, actions read from an HBM pool, CUDA graphs of min(K, R) launches; the "
+                "steps of a graph form a chain (OC_FLAG_CHAIN_HEAD + OC_FLAG_CHAINED: a launch starts when the previous one "
+                "has stored its states) unless --no-chain"}
 
 
 # ------------------------------------------------------------------------------- main
@@ -401,6 +405,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-workloads", action="store_true", help="skip the other BASELINE configs (cfg3, cfg4, cfg5)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of CUDA graphs")
+    ap.add_argument("--no-chain", action="store_true",
+                    help="step API: plain launches (each waits for the previous grid to retire) instead of chained ones")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -443,6 +449,7 @@ def main():
 
     E = args.envs or w["envs"]
     b = Bench(args.workload, E, rank, world, dev, max(2, args.ring), peak, peak_src, args.no_graph)
+    b.chain = not args.no_chain
     A, F, R, P = b.A, b.F, b.R, b.P
     ns = b.ns
     primary = b.measure(args.mode, K, W_, seconds=args.seconds)
@@ -526,6 +533,7 @@ def main():
                 continue
             try:
                 ob = Bench(name, WORKLOADS[name]["envs"], rank, world, dev, max(2, args.ring), peak, peak_src, args.no_graph)
+                ob.chain = not args.no_chain
                 r1 = ob.measure("rollout", K, W_, seconds=0.3, min_reps=10, diagnostics=False, clocks=False)
                 r2 = ob.measure("step", K, W_, seconds=0.3, min_reps=10, diagnostics=False, clocks=False)
                 others[name] = {"config": workload_config(name, ob.E, "rollout")[0], "value": r1["value"],

@@ -17,6 +17,8 @@ OC_FLAG_AUTO_RESET = 1
 OC_FLAG_ACTIONS_U8 = 2
 OC_FLAG_REWARD_PER_ENV = 4
 OC_FLAG_NO_SYNC = 8
+OC_FLAG_CHAIN_HEAD = 16
+OC_FLAG_CHAINED = 32
 OBS_KEYS = ("agent1_comm", "agent1_location", "agent2_comm", "agent2_location", "agent_is_holding",
             "completed_subtasks", "is_hidden", "object_encodings_x", "object_encodings_y",
             "state_encodings", "timestep")

@@ -707,6 +707,16 @@ __device__ __forceinline__ void store_timesteps(const OcParams& p, float* __rest
     for (int k = 0; k < A; ++k) env_row[k * p.F + p.off_ts] = ts;
 }
 
+// Chained steps (oc_kernels.cu): tell the successor of this warp-chunk that its new state is in memory.  Called after
+// the rows were filled and BEFORE they are handed to the copy engine: the release waits for the warp's earlier stores
+// (state, reward, done -- acknowledged long ago at this point) but not for a bulk copy of its own.
+__device__ __forceinline__ void chain_release(uint32_t* flag, uint32_t val, int lane) {
+#ifndef OCK_HOST_EMU
+    if (flag != nullptr && lane == 0)
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(flag), "r"(val) : "memory");
+#endif
+}
+
 // ---- observation emission of one warp's 32 envs.  The warp owns nbuf buffers of p.nb env rows
 // (1 x 32, or 2 x 16 / 1 x 16 / 2 x 8 ... for float rows); the envs go out in 32 / nb passes, lanes
 // [pass * nb, pass * nb + nb) filling buffer (pass mod nbuf) in their pass, one bulk copy per pass.
@@ -718,7 +728,8 @@ template <int A, int NOBJ, int NF, int MODE /* 0 byte rows, 1 float rows, 2 floa
 __device__ __forceinline__ void emit_obs(const Env<A, NOBJ>& e, const Info& in, bool valid, const OcParams& p,
                                          const Tables& tb, uint8_t* wrows, int lane,
                                          float* __restrict__ out_env0 /* warp's first env row */, int nvalid,
-                                         bool clean_on_entry = false /* rows already clear and not in flight */) {
+                                         bool clean_on_entry = false /* rows already clear and not in flight */,
+                                         uint32_t* chain_flag = nullptr, uint32_t chain_val = 0 /* see chain_release */) {
     constexpr bool ROWF = MODE != 0;
     constexpr bool MULTI = MODE == 2;               // compile-time: e / in stay live across passes only here
     const float ts = valid ? timestep_of<A, NOBJ>(e, p, tb) : 0.0f;
@@ -734,6 +745,7 @@ __device__ __forceinline__ void emit_obs(const Env<A, NOBJ>& e, const Info& in, 
         uint8_t* myrow = buf + (MULTI ? (lane & (p.nb - 1)) : lane) * p.row_stride;
         if (valid && (!MULTI || (lane >> p.nb_shift) == pass)) fill_rows<A, NOBJ, NF, ROWF>(e, p, tb, in, ts, myrow);
         __syncwarp();
+        if (pass == 0) chain_release(chain_flag, chain_val, lane);
         const int first = MULTI ? (pass << p.nb_shift) : 0;
         const int nv = min(MULTI ? p.nb : 32, nvalid - first);
         if (nv > 0) warp_expand_rows<ROWF>(p, buf, out_env0 + (size_t)first * p.row_bytes, nv, lane);
@@ -814,7 +826,7 @@ template <int A, int NOBJ, int NF>
 __device__ __forceinline__ void emit_obs_packed(const Env<A, NOBJ>& e, const Info& in, bool valid, const OcParams& p,
                                                 const Tables& tb, uint8_t* wrows, int lane,
                                                 uint8_t* __restrict__ out_env0, float* __restrict__ ts_env0, int nvalid,
-                                                bool clean_on_entry = false) {
+                                                bool clean_on_entry = false, uint32_t* chain_flag = nullptr, uint32_t chain_val = 0) {
     const float ts = valid ? timestep_of<A, NOBJ>(e, p, tb) : 0.0f;
     if (!clean_on_entry) {
         rows_wait_read(p);
@@ -823,6 +835,7 @@ __device__ __forceinline__ void emit_obs_packed(const Env<A, NOBJ>& e, const Inf
     }
     if (valid) build_rows_i8<A, NOBJ, NF>(e, p, tb, in, wrows + (size_t)lane * p.row_stride);
     __syncwarp();
+    chain_release(chain_flag, chain_val, lane);
     if (nvalid > 0) warp_store_packed(p, wrows, out_env0, nvalid, lane);
     if (valid && ts_env0 != nullptr) ts_env0[lane] = ts;         // 128 contiguous bytes per warp
 }

@@ -65,7 +65,23 @@ struct StepIO {
     float* term_ts;           // MODE 3 only
     uint32_t flags;
     int32_t env_lo, env_hi;   // this launch steps envs [env_lo, env_hi); env_lo is a multiple of 32
+    // chained steps (OC_FLAG_CHAIN_HEAD / OC_FLAG_CHAINED): one flag per warp-chunk of 32 envs; the launch at chain
+    // position k (head = 0) sets flag[c] = k + 1 once chunk c's NEW state is in memory, and a chained launch lets chunk c
+    // start as soon as flag[c] == k -- chunk by chunk, instead of waiting for the previous grid to drain and retire
+    uint32_t* chain_flags;    // nullptr: this launch is not part of a chain
+    uint32_t chain_pos;       // 0: depend on the previous grid as a whole (griddepcontrol.wait)
 };
+
+// bounded spin on a device counter (a chain that was put together wrongly must fail loudly, not hang the GPU)
+__device__ __forceinline__ void chain_wait_for(const uint32_t* cnt, uint32_t target) {
+    for (uint32_t spins = 0;; ++spins) {
+        uint32_t v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+        if (v == target) return;
+        if (spins > (1u << 22)) __trap();       // ~ a second: the predecessor never stored its state
+        __nanosleep(64);
+    }
+}
 
 // dynamic shared memory: [table blob][per warp: nb env rows (float / biased-byte / compact int8 format)]
 template <int A, int NOBJ, int NF, int MODE>
@@ -95,7 +111,7 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, co
     warp_clear_rows<MODE != 0>(wrows, p.warp_row_bytes, lane);
     __syncthreads();                                // mbarrier initialised by thread 0 -> visible to everyone
     OC_PROBE(1, 0u);
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (io.chain_pos == 0) asm volatile("griddepcontrol.wait;" ::: "memory");     // chained launches wait per chunk, below
     OC_PROBE(2, 0u);
     const Tables tb = make_tables(p, smem);
     const uint32_t flags = io.flags;
@@ -111,8 +127,15 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, co
         bool done = false;
         uint4 s0, s1, s2, s3;
         int nav[A], comm[A];
+        const int wchunk = (base >> 5) + warp;          // this warp's chunk of 32 envs
+        if (io.chain_pos != 0 && base + warp * 32 < io.env_hi) {        // chained: our chunk's state from the previous step
+            if (lane == 0) chain_wait_for(io.chain_flags + wchunk, io.chain_pos);
+            __syncwarp();
+        }
         if (valid) {                                    // raw loads: state planes + this env's actions
-            s0 = state[env]; s1 = state[p.E + env]; s2 = state[2 * p.E + env]; s3 = state[3 * p.E + env];
+            // L2 loads (ld.global.cg): in a chain the previous writer of these lines may be a grid that is still running
+            s0 = __ldcg(state + env); s1 = __ldcg(state + p.E + env);
+            s2 = __ldcg(state + 2 * p.E + env); s3 = __ldcg(state + 3 * p.E + env);
             if (flags & OC_FLAG_ACTIONS_U8) {
                 const uchar2* a2 = reinterpret_cast<const uchar2*>(io.actions) + (size_t)env * A;
 #pragma unroll
@@ -149,16 +172,20 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, co
             in = gather_info<A, NOBJ, NF>(e, p, tb);
         }
         if (valid) store_env<A, NOBJ>(e, state, p.E, env);
-        OC_PROBE(6, 0u);
         const int env0 = base + warp * 32;
         const int nvalid = max(0, min(32, io.env_hi - env0));
+        OC_PROBE(6, 0u);
+        // chained steps: the successor of this chunk (the same chunk of the next launch) may start once the new state is
+        // in memory; the flag is released inside emit_obs, between filling the rows and handing them to the copy engine
+        uint32_t* cflag = (io.chain_flags != nullptr && nvalid > 0) ? io.chain_flags + wchunk : nullptr;
         if (MODE == 3)
             emit_obs_packed<A, NOBJ, NF>(e, in, valid, p, tb, wrows, lane,
                                          reinterpret_cast<uint8_t*>(io.obs) + (size_t)env0 * p.row_bytes,
-                                         io.ts ? io.ts + env0 : nullptr, nvalid, first);
+                                         io.ts ? io.ts + env0 : nullptr, nvalid, first, cflag, io.chain_pos + 1u);
         else
             emit_obs<A, NOBJ, NF, (MODE == 3 ? 0 : MODE)>(e, in, valid, p, tb, wrows, lane,
-                                         reinterpret_cast<float*>(io.obs) + (size_t)env0 * p.row_bytes, nvalid, first);
+                                         reinterpret_cast<float*>(io.obs) + (size_t)env0 * p.row_bytes, nvalid, first,
+                                         cflag, io.chain_pos + 1u);
         OC_PROBE(7, 0u);
         first = false;
     }
@@ -334,7 +361,18 @@ struct oc_env {
     int pdl = 1;
     int tma_rows_in_step = 1;
     int step_grid = 1;
+    int chain_threads = 0, chain_grid = 0;   // CTA shape of chained float-row launches (0: same as plain launches)
+    size_t chain_smem = 0;
     int zero_copy = 1;        // OC_HOST_ZEROCOPY: page-locked caller buffers are read / written by the kernels directly where that pays
+    // chained steps: one flag per warp-chunk of 32 envs + what the next OC_FLAG_CHAINED call must match
+    uint32_t* chain_cnt = nullptr;
+    struct Chain {
+        bool active = false, compact = false;
+        uint32_t pos = 0;                     // launches of the chain so far
+        cudaStream_t stream = nullptr;
+        int lo = 0, hi = 0;
+        const void *obs = nullptr, *rew32 = nullptr, *rew64 = nullptr, *done = nullptr, *term = nullptr;
+    } chain;
     int obs_off[OC_NUM_OBS_KEYS], obs_size[OC_NUM_OBS_KEYS];
     // device-side staging of the host-buffer entry points (oc_step_host* / oc_reset_host*), allocated on first use
     struct HostPath {
@@ -499,6 +537,19 @@ extern "C" int oc_create(const oc_config* c, oc_env** out) {
     h->threads = best_t;
     h->smem_bytes = smem_for(p, best_t);
     h->step_grid = (int)std::min<long long>(((long long)p.E + best_t - 1) / best_t, (long long)num_sm * best_cap);
+    // Chained launches overlap with their predecessor CTA by CTA: when the batch is a single wave of contiguous
+    // single-pass float rows, four-warp CTAs (four or more resident per SM) hand their slots over in finer steps than
+    // the seven-warp CTAs plain launches like best (cfg2: 6.7 us vs 7.6 us per chained step; tools/r2_chain_sweep.sh).
+    {
+        const char* ce = getenv("OC_BLOCK_THREADS_CHAIN");
+        const int ct = ce ? atoi(ce) : 128;
+        if (ct >= 32 && ct <= 256 && ct % 32 == 0 && caps[ct / 32] >= 1 && (ce || (p.use_tma == 1 && p.obs_passes == 1 && !tenv &&
+            caps[ct / 32] >= 3 && ((long long)p.E + ct - 1) / ct <= (long long)num_sm * caps[ct / 32]))) {
+            h->chain_threads = ct;
+            h->chain_smem = smem_for(p, ct);
+            h->chain_grid = (int)std::min<long long>(((long long)p.E + ct - 1) / ct, (long long)num_sm * caps[ct / 32]);
+        }
+    }
     // compact rows: small CTAs when the batch is a fraction of a wave (<= 16 warps of work per SM) -- the launch is then
     // bound by the slowest CTA, and two-warp CTAs hand their slots over soonest (cfg2: 6.1 us vs 8.3 us with 256 threads,
     // tools/step_sweep.py); larger batches amortise the table copy over more warps
@@ -513,6 +564,8 @@ extern "C" int oc_create(const oc_config* c, oc_env** out) {
 
     cudaError_t ce;
     if ((ce = cudaMalloc(&h->state, (size_t)p.E * 64)) != cudaSuccess ||
+        (ce = cudaMalloc(&h->chain_cnt, (size_t)((p.E + 31) / 32) * sizeof(uint32_t))) != cudaSuccess ||   // here, not on first use:
+        (ce = cudaMemset(h->chain_cnt, 0, (size_t)((p.E + 31) / 32) * sizeof(uint32_t))) != cudaSuccess ||  // that may be inside a capture
         (ce = cudaMalloc(&h->blob, blob.size())) != cudaSuccess ||
         (ce = cudaMalloc(&h->ts, ts.size() * 4)) != cudaSuccess ||
         (ce = cudaMemcpy(h->blob, blob.data(), blob.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
@@ -542,6 +595,7 @@ extern "C" int oc_create(const oc_config* c, oc_env** out) {
 extern "C" int oc_destroy(oc_env* h) {
     if (!h) return OC_OK;
     if (h->state) cudaFree(h->state);
+    if (h->chain_cnt) cudaFree(h->chain_cnt);
     if (h->blob) cudaFree(h->blob);
     if (h->ts) cudaFree(h->ts);
     for (void* q : {(void*)h->hp.actions, (void*)h->hp.obs, (void*)h->hp.rew32, (void*)h->hp.rew64, (void*)h->hp.done,
@@ -580,6 +634,7 @@ static int check_device(const oc_env* h) {
 // compact = kernel MODE 3 (obs int8 [E, A, F-1] + ts f32 [E]); otherwise float rows
 static int launch_reset(oc_env* h, bool compact, const uint8_t* mask, const int32_t* placements, void* obs, float* ts,
                         cudaStream_t st) {
+    h->chain.active = false;                          // anything but a step ends a chain of steps
     const OcParams& p = compact ? h->c.p : h->p;
     const int threads = compact ? h->c.threads : h->threads;
     const size_t smem = compact ? h->c.smem_bytes : h->smem_bytes;
@@ -605,11 +660,42 @@ static int launch_reset(oc_env* h, bool compact, const uint8_t* mask, const int3
 static int launch_step(oc_env* h, bool compact, StepIO io, cudaStream_t st) {
     const OcParams& p = compact ? h->c.p : h->p;
     if (io.env_hi <= 0) { io.env_lo = 0; io.env_hi = p.E; }
+    // ---- chained steps.  HEAD: zero the chain counter (stream-ordered, before the kernel), run with the ordinary
+    // grid-wide dependency, count this launch's state chunks.  CHAINED: must directly follow a HEAD / CHAINED step of
+    // the same kind on the same stream with DIFFERENT output buffers (the two grids overlap: nothing orders their
+    // observation / reward / done stores); it starts as soon as every state chunk of the chain so far is in memory.
+    const uint32_t chain_flags = io.flags & (OC_FLAG_CHAIN_HEAD | OC_FLAG_CHAINED);
+    io.chain_flags = nullptr; io.chain_pos = 0;
+    if (chain_flags) {
+        if (chain_flags == (OC_FLAG_CHAIN_HEAD | OC_FLAG_CHAINED)) return fail(OC_ERR_INVALID, "OC_FLAG_CHAIN_HEAD and OC_FLAG_CHAINED exclude each other");
+        oc_env::Chain& c = h->chain;
+        if (chain_flags & OC_FLAG_CHAIN_HEAD) {
+            // stale flags of an earlier chain (or an earlier replay of this graph) must not look like this chain's
+            CUDA_TRY(cudaMemsetAsync(h->chain_cnt, 0, (size_t)((p.E + 31) / 32) * sizeof(uint32_t), st));
+            c.active = true; c.compact = compact; c.pos = 0; c.stream = st; c.lo = io.env_lo; c.hi = io.env_hi;
+        } else {
+            if (!c.active || c.compact != compact || c.stream != st || c.lo != io.env_lo || c.hi != io.env_hi)
+                return fail(OC_ERR_INVALID, "OC_FLAG_CHAINED: the previous launch of this handle must be a chain head or a chained "
+                                            "step of the same kind (float / compact rows), on the same stream, over the same envs");
+            if (io.obs == c.obs || (io.rew32 && io.rew32 == c.rew32) || (io.rew64 && io.rew64 == c.rew64) || io.done == c.done ||
+                (io.term_obs && io.term_obs == c.term))
+                return fail(OC_ERR_INVALID, "OC_FLAG_CHAINED: consecutive steps of a chain overlap in time and must write different "
+                                            "obs / reward / done / terminal buffers (e.g. consecutive rollout-buffer slots)");
+            if (c.pos >= (1u << 30)) return fail(OC_ERR_INVALID, "chain too long: start a new one with OC_FLAG_CHAIN_HEAD");
+            io.chain_pos = c.pos;
+        }
+        io.chain_flags = h->chain_cnt;
+        c.pos += 1;
+        c.obs = io.obs; c.rew32 = io.rew32; c.rew64 = io.rew64; c.done = io.done; c.term = io.term_obs;
+    } else {
+        h->chain.active = false;                      // a plain step ends the chain
+    }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(compact ? h->c.step_grid : h->step_grid);
-    cfg.blockDim = dim3(compact ? h->c.threads : h->threads);
-    cfg.dynamicSmemBytes = compact ? h->c.smem_bytes : h->smem_bytes;
+    const bool chain_shape = !compact && io.chain_flags != nullptr && h->chain_threads != 0;
+    cfg.gridDim = dim3(compact ? h->c.step_grid : (chain_shape ? h->chain_grid : h->step_grid));
+    cfg.blockDim = dim3(compact ? h->c.threads : (chain_shape ? h->chain_threads : h->threads));
+    cfg.dynamicSmemBytes = compact ? h->c.smem_bytes : (chain_shape ? h->chain_smem : h->smem_bytes);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -653,7 +739,8 @@ extern "C" int oc_step(oc_env* h, const int32_t* actions, float* obs, float* rew
                        uint8_t* done, float* term_obs, uint32_t flags, void* stream) {
     if (!h || !actions || !obs || !done) return fail(OC_ERR_INVALID, "null argument");
     if (misaligned16(obs) || (reinterpret_cast<uintptr_t>(actions) & 7)) return fail(OC_ERR_INVALID, "obs must be 16-byte and actions 8-byte aligned");
-    if (flags & ~OC_FLAG_AUTO_RESET) return fail(OC_ERR_INVALID, "oc_step takes OC_FLAG_AUTO_RESET only");
+    if (flags & ~(OC_FLAG_AUTO_RESET | OC_FLAG_CHAIN_HEAD | OC_FLAG_CHAINED))
+        return fail(OC_ERR_INVALID, "oc_step takes OC_FLAG_AUTO_RESET | OC_FLAG_CHAIN_HEAD | OC_FLAG_CHAINED");
     if (int dc = check_device(h)) return dc;
     StepIO io{actions, obs, nullptr, rew_f32, rew_f64, done, term_obs, nullptr, flags, 0, h->p.E};
     return launch_step(h, false, io, (cudaStream_t)stream);
@@ -666,7 +753,8 @@ extern "C" int oc_step_i8(oc_env* h, const void* actions, int8_t* obs_i8, float*
     if (misaligned16(obs_i8)) return fail(OC_ERR_INVALID, "obs_i8 must be 16-byte aligned");
     if (!(flags & OC_FLAG_ACTIONS_U8) && (reinterpret_cast<uintptr_t>(actions) & 7)) return fail(OC_ERR_INVALID, "int32 actions must be 8-byte aligned");
     if ((flags & OC_FLAG_ACTIONS_U8) && (reinterpret_cast<uintptr_t>(actions) & 1)) return fail(OC_ERR_INVALID, "u8 actions must be 2-byte aligned");
-    if (flags & ~(OC_FLAG_AUTO_RESET | OC_FLAG_ACTIONS_U8 | OC_FLAG_REWARD_PER_ENV)) return fail(OC_ERR_INVALID, "unknown flag");
+    if (flags & ~(OC_FLAG_AUTO_RESET | OC_FLAG_ACTIONS_U8 | OC_FLAG_REWARD_PER_ENV | OC_FLAG_CHAIN_HEAD | OC_FLAG_CHAINED))
+        return fail(OC_ERR_INVALID, "unknown flag");
     if (int dc = check_device(h)) return dc;
     StepIO io{actions, obs_i8, timestep, rew_f32, rew_f64, done, term_obs_i8, term_timestep, flags, 0, h->p.E};
     return launch_step(h, true, io, (cudaStream_t)stream);
@@ -692,6 +780,7 @@ static int launch_rollout(oc_env* h, int32_t n_steps, float* obs, float* rew_f32
     if (!h || n_steps <= 0) return fail(OC_ERR_INVALID, "bad argument");
     if (obs && misaligned16(obs)) return fail(OC_ERR_INVALID, "obs must be 16-byte aligned");
     if (int dc = check_device(h)) return dc;
+    h->chain.active = false;
     const OcParams& p = h->p;
     int rc = dispatch(p.A, p.NOBJ, row_mode(p), [&](auto a, auto nobj, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = shape_nobj(nobj), FF = shape_nf(nobj);
@@ -710,6 +799,7 @@ extern "C" int oc_get_state(oc_env* h, uint32_t* state, void* stream) {
     if (!h || !state) return fail(OC_ERR_INVALID, "null argument");
     if (misaligned16(state)) return fail(OC_ERR_INVALID, "state must be 16-byte aligned");
     if (int dc = check_device(h)) return dc;
+    h->chain.active = false;
     const int n = h->p.E * 4;
     oc_state_export_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->state, state, h->p.E);
     CUDA_TRY(cudaGetLastError());
@@ -721,6 +811,7 @@ extern "C" int oc_set_state(oc_env* h, const uint32_t* state, void* stream) {
     if (!h || !state) return fail(OC_ERR_INVALID, "null argument");
     if (misaligned16(state)) return fail(OC_ERR_INVALID, "state must be 16-byte aligned");
     if (int dc = check_device(h)) return dc;
+    h->chain.active = false;
     const int n = h->p.E * 4;
     oc_state_import_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->p, h->state, state, h->p.E);
     CUDA_TRY(cudaGetLastError());
@@ -731,6 +822,7 @@ extern "C" int oc_set_state(oc_env* h, const uint32_t* state, void* stream) {
 extern "C" int oc_get_stats(oc_env* h, uint32_t* episodes, uint32_t* last_completed, void* stream) {
     if (!h) return fail(OC_ERR_INVALID, "null handle");
     if (int dc = check_device(h)) return dc;
+    h->chain.active = false;
     oc_stats_kernel<<<(h->p.E + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->state, episodes, last_completed, h->p.E);
     CUDA_TRY(cudaGetLastError());
     h->launches += 1;

@@ -13,6 +13,7 @@ env's device; nothing syncs to the host inside a rollout.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Tuple
 
@@ -200,8 +201,8 @@ class PPOConfig:
     ent_coef: float = 0.01
     vf_coef: float = 0.5
     max_grad_norm: float = 0.5
-    cuda_graph: bool = True      # capture the minibatch update (gather, forward, backward, clip, Adam) in a CUDA graph when
-                                 # the learner sits on a GPU and trains alone (one process); eager otherwise
+    cuda_graph: bool = True      # capture the minibatch update (gather, forward, backward, [all-reduce,] clip, Adam) in a
+                                 # CUDA graph when the learner sits on a GPU; eager otherwise
 
     @staticmethod
     def from_hyperparams(h: dict, **over):
@@ -282,7 +283,10 @@ class PPO:
         # The first update runs eagerly (it is also the warm-up every capture needs); from the second one on, the whole
         # minibatch update -- gather, forward, backward, gradient clipping, the (capturable, fused) Adam step -- is ONE
         # CUDA graph over static tensors, replayed per minibatch with a fresh index vector.
-        graphed = c.cuda_graph and self.device.type == "cuda" and _world() == 1 and self.n_updates > 0
+        # (Data parallel: the gradient all-reduce is part of the captured update -- NCCL collectives can be captured;
+        # `OC_PPO_GRAPH_DP=0` keeps the multi-rank update eager.)
+        graphed = (c.cuda_graph and self.device.type == "cuda" and self.n_updates > 0 and
+                   (_world() == 1 or os.environ.get("OC_PPO_GRAPH_DP", "1") != "0"))
         if graphed:
             g = self._graph
             key = (n, bs, obs.data_ptr(), actions.data_ptr(), old_logp.data_ptr(), adv_all.data_ptr(), ret.data_ptr())

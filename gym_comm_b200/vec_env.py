@@ -108,12 +108,18 @@ class OvercookedVecEnv:
                                           self._stream()), "oc_reset")
         return obs
 
+    _CHAIN = {None: 0, "head": _cabi.OC_FLAG_CHAIN_HEAD, "next": _cabi.OC_FLAG_CHAINED}
+
     def step(self, actions: torch.Tensor, obs_out=None, rew_out=None, done_out=None, term_obs_out=None,
-             want_f64: bool = False):
+             want_f64: bool = False, chain=None):
         """``actions`` int32 [E, A, 2] = (nav in [0,4), comm in [0,C)) per agent.  Returns
         (obs [E,A,F] f32, rewards [E,A] f32, dones [E] u8); with ``want_f64`` the reward in the
         reference's own f64 is also left in ``self.rewards64``.  Asynchronous on the current
-        stream; outputs may be caller-provided rollout-buffer slots."""
+        stream; outputs may be caller-provided rollout-buffer slots.
+        ``chain``: ``"head"`` / ``"next"`` for a run of steps whose actions are all in memory beforehand
+        (OC_FLAG_CHAIN_HEAD / OC_FLAG_CHAINED, include/overcooked_b200.h): the steps then overlap, each
+        starting as soon as the previous one has stored its states; consecutive steps must write
+        different output tensors."""
         obs = self.obs if obs_out is None else obs_out
         rew = self.rewards if rew_out is None else rew_out
         done = self.dones if done_out is None else done_out
@@ -123,7 +129,7 @@ class OvercookedVecEnv:
         self._check_tensor(done, self.dones.shape, torch.uint8, "done_out")
         if term_obs_out is not None:
             self._check_tensor(term_obs_out, self.obs.shape, torch.float32, "term_obs_out")
-        flags = _cabi.OC_FLAG_AUTO_RESET if self.auto_reset else 0
+        flags = (_cabi.OC_FLAG_AUTO_RESET if self.auto_reset else 0) | self._CHAIN[chain]
         with self._device_guard():
             self.lib.check(self.lib.step(self._handle, self._ptr(actions), self._ptr(obs), self._ptr(rew),
                                          self._ptr(self.rewards64) if want_f64 else None, self._ptr(done),
@@ -152,14 +158,14 @@ class OvercookedVecEnv:
         return obs_out, timestep_out
 
     def step_i8(self, actions: torch.Tensor, obs_out: torch.Tensor, timestep_out: torch.Tensor, rew_out=None,
-                done_out=None, term_obs_out=None, term_timestep_out=None, want_f64: bool = False):
+                done_out=None, term_obs_out=None, term_timestep_out=None, want_f64: bool = False, chain=None):
         """`step` with the observations in the compact integer format (`oc_step_i8`): int8 [E, A, F-1] rows +
         f32 [E] clock written by the step kernel itself (a quarter of the bytes of the float rows).
         ``actions``: int32 [E, A, 2] or uint8 [E, A, 2]; ``rew_out``: f32 [E, A] (default) or f32 [E]."""
         E, A, F = self.num_envs, self.num_agents, self.obs_width
         rew = self.rewards if rew_out is None else rew_out
         done = self.dones if done_out is None else done_out
-        flags = _cabi.OC_FLAG_AUTO_RESET if self.auto_reset else 0
+        flags = (_cabi.OC_FLAG_AUTO_RESET if self.auto_reset else 0) | self._CHAIN[chain]
         if actions.dtype == torch.uint8:
             self._check_tensor(actions, (E, A, 2), torch.uint8, "actions")
             flags |= _cabi.OC_FLAG_ACTIONS_U8

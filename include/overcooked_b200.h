@@ -57,6 +57,17 @@ typedef enum oc_status {
 #define OC_FLAG_ACTIONS_U8 2u      /* oc_step_i8: actions are u8 [E, A, 2] (nav < 4, comm < C <= 256) instead of int32  */
 #define OC_FLAG_REWARD_PER_ENV 4u  /* oc_step_i8: rew_f32 is f32 [E] (one value per env) instead of f32 [E, A]           */
 #define OC_FLAG_NO_SYNC 8u         /* oc_step_host_block: return after enqueueing; oc_sync() before reading the block     */
+/* Chained steps (oc_step / oc_step_i8) -- for runs of steps whose actions are ALL in memory before the first of them is
+ * enqueued (recorded, scripted or pre-drawn action sequences; oc_replay is the same thing in one launch when the
+ * outputs form one contiguous block).  The first step of the run carries OC_FLAG_CHAIN_HEAD, the following ones
+ * OC_FLAG_CHAINED: a chained launch does not wait for the previous grid to drain and retire; each warp of it starts as
+ * soon as the states of ITS 32 envs from the previous step are in memory, so the observation stores of step N overlap
+ * the dynamics of step N+1.  Rules (violations fail with OC_ERR_INVALID, never silently): a chained step directly follows a
+ * head / chained step of the same entry point on the same handle and stream, with nothing else enqueued on that stream
+ * in between; consecutive steps write DIFFERENT obs / reward / done / terminal buffers (rollout-buffer slots); the
+ * first step of a captured CUDA graph is a head.  A step with neither flag, and any other call, ends the chain. */
+#define OC_FLAG_CHAIN_HEAD 16u
+#define OC_FLAG_CHAINED 32u
 
 /* Order of the 11 observation keys inside one flat feature row = the key-sorted order a gym
  * spaces.Dict gives the dict built at gym_comm/envs/overcooked_env.py:66-78 (what

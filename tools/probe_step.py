@@ -19,13 +19,15 @@ from bench import WORKLOADS, workload_namespace  # noqa: E402
 from gym_comm_b200 import _cabi  # noqa: E402
 from gym_comm_b200.vec_env import OvercookedVecEnv  # noqa: E402
 
-PHASES = ["entry->tables+clear issued", "griddepcontrol.wait", "__syncthreads", "state+actions arrive",
+PHASES = ["entry->tables+clear issued", "griddepcontrol.wait (plain launches)", "tables landed (mbarrier)", "chain flag + state+actions arrive",
           "dynamics + reward/done", "finish/reset + state store", "obs clear/fill + bulk store issue",
           "wait for the copy engine to read the rows"]
 
 
 def main():
-    name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    chained = "--chain" in sys.argv
+    name = args[0] if args else "cfg2"
     w = WORKLOADS[name]
     E, R = w["envs"], 16
     dev = torch.device("cuda", 0)
@@ -47,7 +49,8 @@ def main():
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         for i in range(R):
-            env.step(acts[i], obs_out=obs[i], rew_out=rew[i], done_out=done[i])
+            env.step(acts[i], obs_out=obs[i], rew_out=rew[i], done_out=done[i],
+                     chain=(("head" if i == 0 else "next") if chained else None))
     for _ in range(5):
         g.replay()
     torch.cuda.synchronize()
@@ -58,7 +61,8 @@ def main():
         g.replay()
     b.record()
     torch.cuda.synchronize()
-    print("%s: %.2f us per step over 20 graph replays of %d steps (probe build)" % (name, a.elapsed_time(b) * 1e3 / (20 * R), R))
+    print("%s%s: %.2f us per step over 20 graph replays of %d steps (probe build)" %
+          (name, " CHAINED" if chained else "", a.elapsed_time(b) * 1e3 / (20 * R), R))
     p = probe.cpu().numpy().reshape(-1, 16).astype(np.int64)
     p = p[p[:, 9] != 0]                        # warps that ran (every launch overwrites its own slots: last launch wins)
     print("warps recorded: %d on %d SMs" % (len(p), len(set(p[:, 11].tolist()))))

@@ -2,7 +2,7 @@
 """End-to-end PantheonRL-style PPO training off the GPU env.
 
     python train_ppo.py --json-path cfg.json            # same JSON schema as the reference trainer
-    python train_ppo.py                                 # open-divider_tomato, 65 536 envs: delivers 100 % after ~45 s
+    python train_ppo.py                                 # open-divider_tomato, 65 536 envs: delivers 100 % after ~13 s
     torchrun --nproc-per-node 8 train_ppo.py            # data parallel: --envs per GPU, gradients all-reduced (NCCL)
 
 Ego PPO + partner PPO (the partner records and trains inside `env.step`, like PantheonRL's
@@ -38,8 +38,12 @@ def main(argv=None, env_factory=None, learners_out=None):
     ap.add_argument("--total-timesteps", type=int, default=0,
                     help="train for this many ego env-steps summed over all envs (SB3's `learn(total_timesteps)`, "
                          "trainer.py:121) instead of --iters; the JSON's own total_timesteps is not applied automatically")
-    ap.add_argument("--batch-size", type=int, default=65536)
-    ap.add_argument("--epochs", type=int, default=4)
+    ap.add_argument("--batch-size", type=int, default=262144,
+                    help="minibatch of the PPO update; with 65,536 envs x 32 steps a rollout holds 2 M samples, and large "
+                         "minibatches keep the (memory-bound) update kernels busy: 262,144 x 2 epochs trains at 30 M "
+                         "agent-steps/s and solves open-divider_tomato in 13 s, 65,536 x 4 epochs at 10 M / 21 s "
+                         "(profiles/r2_train_n1.jsonl)")
+    ap.add_argument("--epochs", type=int, default=2)
     ap.add_argument("--clip-range", type=float, default=0.2)
     ap.add_argument("--ent-coef", type=float, default=0.01)
     ap.add_argument("--lr", type=float, default=1e-3)
