@@ -194,7 +194,9 @@ class Bench:
         self.rew_ring = torch.empty((R, E, A), dtype=torch.float32, device=dev)
         self.done_ring = torch.empty((R, E), dtype=torch.uint8, device=dev)
         self.env.reset()
-        self.stagger_clocks()
+        self.resets_per_step = 0.0
+        if os.environ.get("OC_BENCH_NO_STAGGER") != "1":      # diagnostic: lock-step clocks, no env finishes inside the region
+            self.stagger_clocks()
         self.traffic = load_json("profiles", "traffic.json")
 
     def close(self):

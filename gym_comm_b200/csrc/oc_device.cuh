@@ -135,26 +135,38 @@ __device__ __forceinline__ uint32_t obj_set_cell(uint32_t o, uint32_t c) { retur
 // ---------------------------------------------------------------------------------------------
 // load_level phase 4 (overcooked_environment.py:157-173): each random object goes to a Counter
 // drawn uniformly from ALL Counter tiles, rejecting tiles already taken by an earlier phase-4
-// object == sequential sampling without replacement.  Rare path (once per episode), kept out of
-// line so its index arithmetic does not cost registers in the step loop.  Same algorithm in
-// oracle/oc_oracle.c: draw j uses Philox word j of counter (env, episode, 'RESE', j / 4).
-__device__ __noinline__ void draw_random_cells(const OcParams& p, const uint8_t* __restrict__ counters,
-                                               uint32_t env_id, uint32_t episode, uint32_t* cell) {
+// object == sequential sampling without replacement: draw j picks the k-th still-free counter,
+// k = mulhi(Philox word j of counter (env, episode, 'RESE', j / 4), ncounters - j) -- the same
+// algorithm as oracle/oc_oracle.c.  Registers only (a 128-bit "taken" mask, no local arrays, no
+// call): a finishing env holds up its whole warp, and in a launch of a few steps the slowest warp
+// IS the launch (a stack-based version cost cfg4 1.3 us per step of a 20-step rollout).
+__device__ __forceinline__ uint32_t kth_free_counter(uint64_t taken_lo, uint64_t taken_hi, uint32_t k) {
+    uint64_t z = ~taken_lo;
+    uint32_t base = 0;
+    const uint32_t c = (uint32_t)__popcll(z);
+    if (k >= c) { k -= c; z = ~taken_hi; base = 64; }
+    for (; k != 0; --k) z &= z - 1;                      // drop the k lowest free bits
+    return base + (uint32_t)__ffsll((long long)z) - 1u;
+}
+
+__device__ __forceinline__ void draw_random_cells(const OcParams& p, const uint8_t* __restrict__ counters,
+                                                  uint32_t env_id, uint32_t episode, uint32_t (&cell)[OCK_MAX_OBJECTS]) {
     uint32_t r[8];
     philox4x32_10(env_id, episode, 0x52455345u, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), r);
     if (p.nrandom > 4)       // every shipped random level places 3 objects: one block of four words is enough
         philox4x32_10(env_id, episode, 0x52455345u, 1u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), r + 4);
-    uint32_t sorted[OCK_MAX_OBJECTS];
-    int n = 0;
-    for (int j = 0; j < p.nrandom; ++j) {
-        uint32_t idx = __umulhi(r[j], (uint32_t)(p.ncounters - j));      // uniform in [0, n - j)
-        for (int a = 0; a < n; ++a)
-            if (sorted[a] <= idx) ++idx;                                   // skip counters already taken
-        int pos = n;
-        while (pos > 0 && sorted[pos - 1] > idx) { sorted[pos] = sorted[pos - 1]; --pos; }
-        sorted[pos] = idx;
-        ++n;
-        cell[j] = counters[idx];
+    else
+        r[4] = r[5] = r[6] = r[7] = 0u;
+    // counters beyond ncounters count as taken, so that "the k-th free bit" only ever lands on a real counter
+    uint64_t lo = p.ncounters >= 64 ? 0ull : ~0ull << p.ncounters;
+    uint64_t hi = p.ncounters >= 128 ? 0ull : (p.ncounters <= 64 ? ~0ull : ~0ull << (p.ncounters - 64));
+#pragma unroll
+    for (int j = 0; j < OCK_MAX_OBJECTS; ++j) {
+        if (j < p.nrandom) {
+            const uint32_t idx = kth_free_counter(lo, hi, __umulhi(r[j], (uint32_t)(p.ncounters - j)));
+            if (idx < 64) lo |= 1ull << idx; else hi |= 1ull << (idx - 64);
+            cell[j] = counters[idx];
+        }
     }
 }
 

@@ -155,7 +155,14 @@ def compile_level(level: str, num_agents: int, level_text: Optional[str] = None,
                 a, b = line.split(" ")
                 starts_xy.append((int(a), int(b)))
         elif phase == 4:
-            random_reps += [ch for ch in line if ch in "tlop"]
+            reps = [ch for ch in line if ch in "tlop"]
+            if reps and random_reps:
+                # the reference starts a fresh `occupied` set per phase-4 LINE (:157-166), so objects of different lines
+                # may share a counter; the device draws all random objects without replacement.  No shipped level has
+                # a second line -- refuse instead of silently diverging.
+                raise LevelError("more than one line of random (phase-4) objects is not supported: the reference places "
+                                 "each line independently, so their objects may collide on one counter")
+            random_reps += reps
     if not rows:
         raise LevelError("empty level map")
     height = len(rows)

@@ -24,6 +24,8 @@ static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
+static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t s) {
     const uint64_t v = ((uint64_t)b << 32) | a;
     uint32_t r = 0;

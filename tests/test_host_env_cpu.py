@@ -26,15 +26,22 @@ def test_finished_indices_equals_flatnonzero(E):
         assert got == np.flatnonzero(buf[:E]).tolist() and all(type(e) is int for e in got)
 
 
-@pytest.mark.parametrize("fmt", ["f32", "i8"])
+@pytest.mark.parametrize("fmt", ["f32", "i8", "i8-separate-buffers"])
 @pytest.mark.parametrize("level,A,T,C,E", [("open-divider_tomato", 2, 11, 5, 75), ("partial-divider_salad", 3, 9, 4, 41)])
 def test_host_env_on_the_emulation_vs_c_oracle(fmt, level, A, T, C, E):
+    """"i8" runs the one-block path (`oc_step_host_block`: u8 actions, per-env reward, compact rows from the step
+    kernel); "i8-separate-buffers" the older `oc_step_host_i8` entry points a handle falls back to when its rows are
+    too wide for the compact kernels (float rows + repack + gather)."""
+    compact = fmt != "i8-separate-buffers"
+    fmt = "i8" if fmt.startswith("i8") else fmt
     cfg = dict(level=level, num_agents=A, max_num_timesteps=T, communication_on=True, num_communication=C,
                ego_led=False, fow_radius=2, ego_config=D, partner_config=D)
     text = levels_data.LEVELS[level]
     subtasks = levels_data.SUBTASKS[tuple(text.split("\n\n")[1].split("\n"))]
-    lib = EmuHostLibrary()
+    lib = EmuHostLibrary(compact=compact)
     env = OvercookedHostVecEnv(argparse.Namespace(**cfg), num_envs=E, seed=31, obs_format=fmt, lib=lib)
+    assert env._block_mode == (fmt == "i8" and compact)
+    assert env.action_dtype == (np.uint8 if env._block_mode else np.int32)
     lib.bind(env)
     ora = COracle(text, subtasks, E, seed=31, **{k: v for k, v in cfg.items() if k != "level"})
     F = env.obs_width

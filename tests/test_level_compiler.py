@@ -65,3 +65,15 @@ def test_level_errors():
         compile_level("x", 2, level_text=two_tomatoes)
     with pytest.raises(LevelError):
         compile_level("x", 2, level_text="-t-\n- -\n-*-\n\nNoSuchRecipe\n\n1 1\n1 1\n")
+
+
+def test_second_line_of_random_objects_is_refused():
+    """The reference draws every phase-4 line with its own `occupied` set (overcooked_environment.py:157-166); the
+    device draws all random objects without replacement, so a second line would diverge -- refused by name."""
+    import pytest
+    from gym_comm_b200.level_compiler import LevelError, compile_level
+    text = " --- \n-   -\n-   *\n -/- \n\nSimpleTomato\n\n1 1\n2 1\n\npt\np\n"
+    with pytest.raises(LevelError, match="phase-4"):
+        compile_level("custom", 2, level_text=text)
+    ok = compile_level("custom", 2, level_text=text.replace("\np\n", "\n"))
+    assert ok.num_random == 2
