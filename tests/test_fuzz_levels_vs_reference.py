@@ -48,8 +48,12 @@ def test_recorded_subtask_tables_drive_every_recipe_list(recipes):
     table = levels_data.SUBTASKS[tuple(recipes)]
     if ref_harness.hashseed_is_canonical():          # the ORDER is the reference's at PYTHONHASHSEED=0
         assert ref.subtask_strings() == table
-    else:
-        assert sorted(ref.subtask_strings()) == sorted(table)
+    else:                                            # another hash seed: the same subtasks in another order, and the
+        def canon(st):                               # two operands of a Merge in either order
+            if st.startswith("Merge("):
+                return "Merge(%s)" % ", ".join(sorted(st[6:-1].split(", ")))
+            return st
+        assert sorted(map(canon, ref.subtask_strings())) == sorted(map(canon, table))
     assert len(table) <= 32
     lockstep(ref, ns, text, ref.subtask_strings(), 2, 3, 120)
 
