@@ -456,6 +456,13 @@ def main():
     ns = b.ns
     primary = b.measure(args.mode, K, W_, seconds=args.seconds)
     secondary = None if args.single_mode else b.measure(other_mode, K, W_, seconds=args.seconds)
+    # the same per-step launches WITHOUT chaining: what a closed loop gets (a policy that needs step N's observations
+    # before it can produce step N+1's actions -- train_ppo.py's graphed rollout): each launch waits for the previous grid
+    plain = None
+    if not args.single_mode and not args.no_chain:
+        b.chain = False
+        plain = b.measure("step", K, W_, seconds=0.3, min_reps=10, diagnostics=False, clocks=False)
+        b.chain = True
 
     # ---- e2e: the reference-facing call with HOST buffers: OvercookedHostVecEnv.step = C ABI oc_step_host*
     # (pinned numpy buffers; every step copies the actions host->device, runs the step kernel, copies
@@ -482,12 +489,13 @@ def main():
             for i in range(5):
                 henv.step(host_actions[i % 8])
             b.barrier()
-            nfin, n = 0, 0
+            nfin, nsampled, n = 0, 0, 0
             t0 = time.perf_counter()
             while True:
                 for i in range(25):
                     d_ = henv.step(host_actions[(n + i) % 8])[2]   # returns with obs / reward / done valid on the host
-                    nfin += int(np.count_nonzero(d_))
+                nfin += int(np.count_nonzero(d_))                  # bookkeeping of the bench itself: sampled, one step in 25
+                nsampled += 1
                 n += 25
                 if time.perf_counter() - t0 >= window:
                     break
@@ -511,7 +519,7 @@ def main():
                                         # (tests/test_gpu_host_env.py, tests/cabi_smoke.c); nothing is quantised
                 "api": "OvercookedHostVecEnv(obs_format=%r).step = C ABI %s, pinned numpy buffers, results valid on return" % (fmt, entry),
                 "transfers": desc, "gpu_launches_per_step": launches,
-                "terminal_observations": bool(term), "finished_envs_per_step": nfin / n,
+                "terminal_observations": bool(term), "finished_envs_per_step": nfin / nsampled,
                 "cpu_affinity": "nvml (GPU-local cores)" if affinity else "none"}
 
     e2e = e2e_f32 = e2e_term = None
@@ -576,6 +584,12 @@ def main():
                                          "ms_per_step": secondary["ms_per_step"], "roofline": secondary["roofline"],
                                          "repeats": secondary["repeats"],
                                          "gpu_launches": secondary["gpu_launches"], "clocks": secondary["clocks"]}
+        if plain is not None:
+            line["step_api_unchained"] = {
+                "desc": "C-ABI oc_step, one launch per step, plain launches with programmatic dependent launch (each grid "
+                        "waits for the previous one): the closed-loop case, where step N+1's actions depend on step N's output",
+                "value": plain["value"], "unit": "agent-steps/s", "ms_per_step": plain["ms_per_step"],
+                "roofline": plain["roofline"], "repeats": plain["repeats"], "gpu_launches": plain["gpu_launches"]}
         if others:
             line["workloads"] = others
         print(json.dumps(line))

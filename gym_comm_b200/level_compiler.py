@@ -5,8 +5,9 @@ once per configuration:
 
 * ``OvercookedEnvironment.load_level``      gym_cooking/envs/overcooked_environment.py:100-178
 * ``run_recipes`` / ``STRIPSWorld.get_subtasks``  :452-459, recipe_planner/stripsworld.py:61-79
-  (table looked up from ``levels_data.SUBTASKS`` -- the order is PYTHONHASHSEED-dependent in the
-  reference, canonical seed 0; pass ``subtasks=`` to override)
+  (derived by ``recipe_planner.derive_recipe_subtasks`` from the recipe list and the objects of the level; the ORDER
+  is PYTHONHASHSEED-dependent in the reference and is taken from ``levels_data.SUBTASKS``, recorded at the canonical
+  seed 0, which the derivation must reproduce as a set; pass ``subtasks=`` to override)
 * ``get_subtask_obj`` goal templates        gym_cooking/navigation_planner/utils.py:161-209
 * ``World.make_reachability_graph`` + ``get_path_distance_between``  gym_cooking/utils/world.py:61-131
 """
@@ -18,7 +19,9 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from . import levels_data
+from functools import lru_cache
+
+from . import levels_data, recipe_planner
 
 # encodings shared with include/overcooked_b200.h
 TILE_FLOOR, TILE_COUNTER, TILE_CUTBOARD, TILE_DELIVERY = 0, 1, 2, 3
@@ -129,8 +132,41 @@ def path_distance_table(tiles: np.ndarray, width: int, height: int) -> np.ndarra
     return pd.astype(np.uint8).reshape(-1)
 
 
+@lru_cache(maxsize=256)
+def _recipe_subtasks(recipe: str, world: Tuple[Tuple[str, ...], ...], max_num_subtasks: int) -> Tuple[str, ...]:
+    """One recipe's subtasks: the set from the planner, in the reference's PYTHONHASHSEED=0 order."""
+    try:
+        d = recipe_planner.derive_recipe_subtasks(recipe, world, max_num_subtasks)
+    except ValueError as ex:
+        raise LevelError(str(ex))
+    gets = [s for s in d.subtasks if s.startswith("Get(")]
+    if gets:      # the plan has to fetch an ingredient the level does not hold; the reference has no goal objects for Get
+        raise LevelError("recipe %s needs %s but the level holds no such object" % (recipe, ", ".join(g[4:-1] for g in gets)))
+    recorded = levels_data.SUBTASKS.get((recipe,))
+    if recorded is None:
+        return tuple(d.subtasks)
+    try:
+        return tuple(recipe_planner.order_like(d.subtasks, recorded))
+    except ValueError as ex:
+        raise LevelError("recipe %s: %s (regenerate levels_data.py with tools/gen_levels_data.py)" % (recipe, ex))
+
+
+def derive_level_subtasks(recipes: Sequence[str], obj_contents: Sequence[int], max_num_subtasks: int = 14) -> List[str]:
+    """``all_subtasks`` of a level (overcooked_environment.py:452-459): per recipe, the union of the actions on all
+    shortest STRIPS plans from the level's objects to the delivered dish, concatenated over the recipe list."""
+    world = tuple(tuple(n for n in _NAME_ORDER if CONTENT_BIT[n] & bits) for bits in obj_contents)
+    out: List[str] = []
+    for r in recipes:
+        out += _recipe_subtasks(r, world, max_num_subtasks)
+    recorded = levels_data.SUBTASKS.get(tuple(recipes))
+    if recorded is not None and list(recorded) != out:
+        raise LevelError("derived subtasks of %r differ from the recorded table (regenerate levels_data.py with "
+                         "tools/gen_levels_data.py): %r vs %r" % (tuple(recipes), out, list(recorded)))
+    return out
+
+
 def compile_level(level: str, num_agents: int, level_text: Optional[str] = None,
-                  subtasks: Optional[Sequence[str]] = None) -> CompiledLevel:
+                  subtasks: Optional[Sequence[str]] = None, max_num_subtasks: int = 14) -> CompiledLevel:
     if level_text is None:
         if level not in levels_data.LEVELS:
             raise LevelError("unknown level %r (known: %s)" % (level, ", ".join(sorted(levels_data.LEVELS))))
@@ -200,12 +236,7 @@ def compile_level(level: str, num_agents: int, level_text: Optional[str] = None,
         if r not in RECIPE_FOODS:
             raise LevelError("unknown recipe %r" % r)
     if subtasks is None:
-        key = tuple(recipes)
-        if key not in levels_data.SUBTASKS:
-            raise LevelError("no recorded subtask table for the recipe list %r: tools/gen_levels_data.py records the "
-                             "reference's tables (every ordered selection of its four recipes without repetition); "
-                             "for anything else pass subtasks= with the reference's own all_subtasks" % (key,))
-        subtasks = levels_data.SUBTASKS[key]
+        subtasks = derive_level_subtasks(recipes, obj_contents, max_num_subtasks)
     subtasks = list(subtasks)
     if not 1 <= len(subtasks) <= MAX_SUBTASKS:
         raise LevelError("the recipe list %r has %d subtasks; the packed state holds one bit per subtask and supports "

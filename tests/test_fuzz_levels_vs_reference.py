@@ -72,8 +72,26 @@ def test_every_recipe_list_has_a_table_and_wide_ones_fail_by_name():
             else:
                 with pytest.raises(LevelError, match="32 subtasks"):
                     compile_level("synthetic", 2, level_text=SYNTH % "\n".join(recipes))
-    with pytest.raises(LevelError, match="gen_levels_data"):
-        compile_level("synthetic", 2, level_text=SYNTH % "Salad\nSalad")
+    # a repeated recipe is no table entry: its subtasks are derived (gym_comm_b200/recipe_planner.py) per recipe
+    lv = compile_level("synthetic", 2, level_text=SYNTH % "Salad\nSalad")
+    assert lv.subtasks == levels_data.SUBTASKS[("Salad",)] * 2
+
+
+@pytest.mark.parametrize("recipes", [("Salad", "Salad"), ("SimpleTomato", "Salad", "SimpleTomato")], ids=lambda r: "+".join(r))
+def test_repeated_recipes_are_derived_and_match_the_reference(recipes):
+    """Recipe lists outside the recorded tables: the planner's subtasks equal the live reference's all_subtasks (order
+    included at the canonical hash seed) and drive the env in lock-step."""
+    from gym_comm_b200.level_compiler import compile_level
+    from gym_comm_b200.recipe_planner import canonical_label
+    text = SYNTH % "\n".join(recipes)
+    ns = ref_harness.make_namespace("synthetic", max_num_timesteps=70, num_communication=4)
+    ref = ref_harness.LiveReference(ns, py_random_seed=1, level_text=text)
+    lv = compile_level("synthetic", 2, level_text=text)
+    if ref_harness.hashseed_is_canonical():
+        assert ref.subtask_strings() == lv.subtasks
+    else:
+        assert sorted(map(canonical_label, ref.subtask_strings())) == sorted(map(canonical_label, lv.subtasks))
+    lockstep(ref, ns, text, ref.subtask_strings(), 2, 3, 120)
 
 
 def lockstep(ref, ns, text, subtasks, n, seed, steps):
