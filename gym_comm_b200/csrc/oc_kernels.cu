@@ -70,10 +70,6 @@ struct StepIO {
     // start as soon as flag[c] == k -- chunk by chunk, instead of waiting for the previous grid to drain and retire
     uint32_t* chain_flags;    // nullptr: this launch is not part of a chain
     uint32_t chain_pos;       // 0: depend on the previous grid as a whole (griddepcontrol.wait)
-    // MODE 3, host-block path: the rows of envs [0, direct_hi) go to `obs_direct` (the caller's page-locked block, written
-    // across PCIe while the kernel is still running) instead of `obs`
-    void* obs_direct;
-    int32_t direct_hi;
 };
 
 // bounded spin on a device counter (a chain that was put together wrongly must fail loudly, not hang the GPU)
@@ -184,7 +180,7 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, co
         uint32_t* cflag = (io.chain_flags != nullptr && nvalid > 0) ? io.chain_flags + wchunk : nullptr;
         if (MODE == 3)
             emit_obs_packed<A, NOBJ, NF>(e, in, valid, p, tb, wrows, lane,
-                                         reinterpret_cast<uint8_t*>(env0 < io.direct_hi ? io.obs_direct : io.obs) + (size_t)env0 * p.row_bytes,
+                                         reinterpret_cast<uint8_t*>(io.obs) + (size_t)env0 * p.row_bytes,
                                          io.ts ? io.ts + env0 : nullptr, nvalid, first, cflag, io.chain_pos + 1u);
         else
             emit_obs<A, NOBJ, NF, (MODE == 3 ? 0 : MODE)>(e, in, valid, p, tb, wrows, lane,
@@ -368,16 +364,6 @@ struct oc_env {
     int chain_threads = 0, chain_grid = 0;   // CTA shape of chained float-row launches (0: same as plain launches)
     size_t chain_smem = 0;
     int zero_copy = 1;        // OC_HOST_ZEROCOPY: page-locked caller buffers are read / written by the kernels directly where that pays
-    // oc_step_host_block steps the batch in `host_pieces` env ranges (OC_HOST_PIECES, 1..8): the download of one piece's
-    // rows (on copy_stream) overlaps the kernel of the next, so that only the first piece's kernel sits in front of PCIe
-    int host_pieces = 1;      // measured on a B200 (profiles/r2_e2e_host_path_ab.txt): every extra launch / event / copy call costs more host time than the overlap returns
-    // oc_step_host_block, page-locked block: the kernel stores the rows of the first `host_direct_pct` % of the envs
-    // straight into the caller's block (posted PCIe writes while the rest of the grid is still computing), so the link is
-    // already busy during the kernel; the copy that follows moves the other rows (OC_HOST_DIRECT_PCT, 0 = off)
-    int host_direct_pct = 0;
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t piece_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t copy_done_ev = nullptr;
     // chained steps: one flag per warp-chunk of 32 envs + what the next OC_FLAG_CHAINED call must match
     uint32_t* chain_cnt = nullptr;
     struct Chain {
@@ -491,8 +477,6 @@ extern "C" int oc_create(const oc_config* c, oc_env** out) {
     if (const char* pe = getenv("OC_PDL")) h->pdl = atoi(pe) != 0;
     if (const char* te = getenv("OC_TMA")) h->tma_rows_in_step = atoi(te) != 0;
     if (const char* ze = getenv("OC_HOST_ZEROCOPY")) h->zero_copy = atoi(ze) != 0;
-    if (const char* pe = getenv("OC_HOST_PIECES")) h->host_pieces = std::min(8, std::max(1, atoi(pe)));
-    if (const char* de = getenv("OC_HOST_DIRECT_PCT")) h->host_direct_pct = std::min(100, std::max(0, atoi(de)));
     cudaDeviceProp prop;
     {
         cudaError_t cep = cudaGetDeviceProperties(&prop, dev);
@@ -621,9 +605,6 @@ extern "C" int oc_destroy(oc_env* h) {
         if (q) cudaFree(q);
     for (void* q : {(void*)h->hp.h_idx, (void*)h->hp.h_gather, (void*)h->hp.h_gather_ts})
         if (q) cudaFreeHost(q);
-    for (cudaEvent_t ev : h->piece_ev) if (ev) cudaEventDestroy(ev);
-    if (h->copy_done_ev) cudaEventDestroy(h->copy_done_ev);
-    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     delete h;
     return OC_OK;
 }
@@ -685,7 +666,6 @@ static int launch_step(oc_env* h, bool compact, StepIO io, cudaStream_t st) {
     // observation / reward / done stores); it starts as soon as every state chunk of the chain so far is in memory.
     const uint32_t chain_flags = io.flags & (OC_FLAG_CHAIN_HEAD | OC_FLAG_CHAINED);
     io.chain_flags = nullptr; io.chain_pos = 0;
-    if (io.obs_direct == nullptr) io.direct_hi = 0;
     if (chain_flags) {
         if (chain_flags == (OC_FLAG_CHAIN_HEAD | OC_FLAG_CHAINED)) return fail(OC_ERR_INVALID, "OC_FLAG_CHAIN_HEAD and OC_FLAG_CHAINED exclude each other");
         oc_env::Chain& c = h->chain;
@@ -715,8 +695,6 @@ static int launch_step(oc_env* h, bool compact, StepIO io, cudaStream_t st) {
     const bool chain_shape = !compact && io.chain_flags != nullptr && h->chain_threads != 0;
     cfg.gridDim = dim3(compact ? h->c.step_grid : (chain_shape ? h->chain_grid : h->step_grid));
     cfg.blockDim = dim3(compact ? h->c.threads : (chain_shape ? h->chain_threads : h->threads));
-    // a launch over part of the batch (oc_step_host_block's pieces) needs no more CTAs than its env range has chunks
-    cfg.gridDim.x = std::min<unsigned>(cfg.gridDim.x, (unsigned)((io.env_hi - io.env_lo + (int)cfg.blockDim.x - 1) / (int)cfg.blockDim.x));
     cfg.dynamicSmemBytes = compact ? h->c.smem_bytes : (chain_shape ? h->chain_smem : h->smem_bytes);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -1156,49 +1134,8 @@ extern "C" int oc_step_host_block(oc_env* h, const uint8_t* actions_u8, void* bl
     StepIO io{act, d + L.obs_i8, (float*)(d + L.timestep), (float*)(d + L.reward), nullptr, d + L.done,
               term8_alias, term_ts_alias,
               (flags & OC_FLAG_AUTO_RESET) | OC_FLAG_ACTIONS_U8 | OC_FLAG_REWARD_PER_ENV, 0, p.E};
-    // The batch is stepped in `pieces` env ranges.  Pieces 0 .. n-2: kernel on `st`, event, their obs rows go down on
-    // copy_stream while the next piece's kernel runs.  The last piece's rows and the small arrays behind them (timestep |
-    // reward | done: contiguous in the block) go down in one copy on `st`, which finally waits for copy_stream -- so
-    // everything is ordered on the caller's stream as before, and only the FIRST piece's kernel is exposed in front of PCIe.
-    const size_t row8 = A * (size_t)(p.F - 1);
-    const int quantum = 1024;                                   // piece boundaries: whole CTAs of every shape, 256-byte aligned rows
-    int pieces = h->host_pieces;
-    while (pieces > 1 && p.E / pieces < 8 * quantum) --pieces;  // small batches: the launches would cost more than they hide
-    if (pieces > 1 && !h->copy_stream) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-        for (cudaEvent_t& ev : h->piece_ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&h->copy_done_ev, cudaEventDisableTiming));
-    }
-    // rows the kernel writes across PCIe itself (single-piece launches with a page-locked block only)
-    size_t direct_bytes = 0;
-    if (pieces == 1 && h->zero_copy && h->host_direct_pct > 0 && p.E >= 8 * quantum) {
-        if (uint8_t* balias = device_alias((uint8_t*)block)) {
-            const int dhi = std::min(p.E, (int)((long long)p.E * h->host_direct_pct / 100 + quantum - 1) / quantum * quantum);
-            io.obs_direct = balias + L.obs_i8;
-            io.direct_hi = dhi;
-            direct_bytes = (size_t)dhi * row8;
-        }
-    }
-    const int per = pieces > 1 ? (p.E / pieces + quantum - 1) / quantum * quantum : p.E;
-    for (int k = 0, lo = 0; lo < p.E; ++k, lo += per) {
-        const int hi = (k == pieces - 1) ? p.E : std::min(p.E, lo + per);
-        io.env_lo = lo; io.env_hi = hi;
-        if ((rc = launch_step(h, true, io, st))) return rc;
-        if (hi < p.E) {
-            CUDA_TRY(cudaEventRecord(h->piece_ev[k], st));
-            CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->piece_ev[k], 0));
-            CUDA_TRY(cudaMemcpyAsync((uint8_t*)block + L.obs_i8 + (size_t)lo * row8, d + L.obs_i8 + (size_t)lo * row8,
-                                     (size_t)(hi - lo) * row8, cudaMemcpyDeviceToHost, h->copy_stream));
-        } else {
-            const size_t off = L.obs_i8 + std::max((size_t)lo * row8, direct_bytes);
-            CUDA_TRY(cudaMemcpyAsync((uint8_t*)block + off, d + off, (size_t)L.total_bytes - off, cudaMemcpyDeviceToHost, st));
-            if (lo > 0) {
-                CUDA_TRY(cudaEventRecord(h->copy_done_ev, h->copy_stream));
-                CUDA_TRY(cudaStreamWaitEvent(st, h->copy_done_ev, 0));
-            }
-            break;
-        }
-    }
+    if ((rc = launch_step(h, true, io, st))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(block, d, (size_t)L.total_bytes, cudaMemcpyDeviceToHost, st));      // ONE copy for everything
     if (!(flags & OC_FLAG_NO_SYNC)) CUDA_TRY(cudaStreamSynchronize(st));
     return OC_OK;
 }
