@@ -7,7 +7,7 @@
 A "step" is one pass of the hot path over one batch: every env of the workload advances one
 timestep and every agent's observation is featurised.  Headline workload (BASELINE.json configs[1]):
 open-divider_tomato, 2 agents, comm on (C=10), T=500, 65,536 lock-step envs per GPU, uniform random
-actions, auto-reset, episode clocks staggered so that about E/T envs finish in EVERY step.  N GPUs =
+actions, auto-reset, episode clocks staggered ((e * M) mod T) so that about E/T envs finish in EVERY step.  N GPUs =
 N independent shards (weak scaling, no collective on the step path; torch.distributed only for the
 barrier and the max-over-ranks of the device time).
 
@@ -163,11 +163,20 @@ def load_json(*path):
         return {}
 
 
+def spread_multiplier(T: int) -> int:
+    """Smallest M >= 0.618 T that is coprime to T: e -> (e * M) mod T is a bijection on every block of T envs."""
+    M = max(1, int(round(0.618 * T)))
+    while math.gcd(M, T) != 1:
+        M += 1
+    return M
+
+
 # ------------------------------------------------------------------------------- one workload on this rank's GPU
 class Bench:
     """One workload on this rank's GPU: env handle, rollout-buffer ring, action pool, the timing protocol."""
 
-    def __init__(self, wname, E, rank, world, dev, ring_slots, peak, peak_src, no_graph=False):
+    def __init__(self, wname, E, rank, world, dev, ring_slots, peak, peak_src, no_graph=False, stagger="spread"):
+        self.stagger = stagger
         import torch
         from gym_comm_b200.vec_env import OvercookedVecEnv
         self.torch, self.wname, self.w = torch, wname, WORKLOADS[wname]
@@ -205,13 +214,18 @@ class Bench:
         self.torch.cuda.empty_cache()
 
     def stagger_clocks(self):
-        """Steady state of a long run: env e's episode clock starts at e mod T (through the C ABI's state
+        """Steady state of a long run: env e's episode clock starts at (e * M) mod T (through the C ABI's state
         export / import), then one full episode length of fused rollout, so every env has crossed a reset
-        and about E/T envs finish -- reset in place, random placements redrawn -- in every later step."""
+        and about E/T envs finish -- reset in place, random placements redrawn -- in every later step.
+        M (coprime to T, near 0.618 T) permutes the clocks inside every block of T consecutive envs: the E/T
+        resets of a step are spread over the batch, as the asynchronous episode ends of a real run are.  With
+        M = 1 (`--stagger consecutive`) the same number of resets falls on CONSECUTIVE envs, i.e. a few warps pay
+        for all resets of a whole launch and the one-wave kernels wait for them (random levels: +25 %)."""
         torch, env = self.torch, self.env
         T = int(self.w["max_num_timesteps"])
         st = env.get_state()
-        t = (torch.arange(self.E, device=self.dev, dtype=torch.int64) % T).to(torch.int32)
+        M = spread_multiplier(T) if self.stagger == "spread" else 1
+        t = ((torch.arange(self.E, device=self.dev, dtype=torch.int64) * M) % T).to(torch.int32)
         st[:, 0] = (st[:, 0] & ~0xFFFF) | t
         env.set_state(st)
         left = T
@@ -407,6 +421,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-workloads", action="store_true", help="skip the other BASELINE configs (cfg3, cfg4, cfg5)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of CUDA graphs")
+    ap.add_argument("--stagger", default="spread", choices=["spread", "consecutive"],
+                    help="episode-clock pattern of the steady state: (e * M) mod T with M coprime to T (the resets of a "
+                         "step are spread over the batch) or e mod T (they fall on consecutive envs)")
     ap.add_argument("--no-chain", action="store_true",
                     help="step API: plain launches (each waits for the previous grid to retire) instead of chained ones")
     args = ap.parse_args()
@@ -450,7 +467,7 @@ def main():
     other_mode = "step" if args.mode == "rollout" else "rollout"
 
     E = args.envs or w["envs"]
-    b = Bench(args.workload, E, rank, world, dev, max(2, args.ring), peak, peak_src, args.no_graph)
+    b = Bench(args.workload, E, rank, world, dev, max(2, args.ring), peak, peak_src, args.no_graph, args.stagger)
     b.chain = not args.no_chain
     A, F, R, P = b.A, b.F, b.R, b.P
     ns = b.ns
@@ -485,7 +502,7 @@ def main():
             # steady state of a long run: env e starts e mod T steps into its episode, so that about E / T envs
             # finish in every step (and, with `term`, their terminal rows are delivered)
             T = int(w["max_num_timesteps"])
-            henv.stagger_clocks(T)
+            henv.stagger_clocks(T, spread_multiplier(T) if args.stagger == "spread" else 1)
             for i in range(5):
                 henv.step(host_actions[i % 8])
             b.barrier()
@@ -542,7 +559,8 @@ def main():
             if name == args.workload:
                 continue
             try:
-                ob = Bench(name, WORKLOADS[name]["envs"], rank, world, dev, max(2, args.ring), peak, peak_src, args.no_graph)
+                ob = Bench(name, WORKLOADS[name]["envs"], rank, world, dev, max(2, args.ring), peak, peak_src, args.no_graph,
+                           args.stagger)
                 ob.chain = not args.no_chain
                 r1 = ob.measure("rollout", K, W_, seconds=0.3, min_reps=10, diagnostics=False, clocks=False)
                 r2 = ob.measure("step", K, W_, seconds=0.3, min_reps=10, diagnostics=False, clocks=False)
@@ -573,6 +591,9 @@ def main():
             "config": dict(workload_config(args.workload, E, args.mode)[0],
                            mode_desc=DESC[args.mode], cuda_graphs=primary["cuda_graphs"], rollout_ring_slots=R,
                            resets_per_step=primary["resets_per_step"],
+                           episode_clocks=("env e starts at (e * %d) mod T: about E/T envs finish in every step, spread over the batch"
+                                           % spread_multiplier(int(w["max_num_timesteps"]))) if args.stagger == "spread"
+                                          else "env e starts at e mod T: about E/T CONSECUTIVE envs finish in every step",
                            l2="inputs/outputs larger than L2: the obs ring (%d x %.1f MB) is rewritten round-robin and the action pool is %.2f GB; only the %.1f MB packed state stays L2-resident (by design)"
                               % (R, E * A * F * 4 / 1e6, P * E * A * 8 / 1e9, E * 64 / 1e6)),
             "repeats": primary["repeats"],

@@ -271,12 +271,14 @@ class OvercookedHostVecEnv:
         self.lib.check(self.lib.set_device(self.device_index), "oc_set_device")
         self.lib.check(self.lib.set_state_host(self._handle, self._p(st), None), "oc_set_state_host")
 
-    def stagger_clocks(self, period: Optional[int] = None) -> None:
-        """Env e's episode clock := e mod period (default: max_num_timesteps): the steady state of a long run, in
-        which about E / T envs finish in every step instead of all of them in the same one."""
+    def stagger_clocks(self, period: Optional[int] = None, multiplier: int = 1) -> None:
+        """Env e's episode clock := (e * multiplier) mod period (default: max_num_timesteps, 1): the steady state of a
+        long run, in which about E / T envs finish in every step instead of all of them in the same one; a multiplier
+        coprime to the period spreads the envs that finish in one step over the batch."""
         T = int(period or self.arglist.max_num_timesteps)
         st = self.get_state()
-        st[:, 0] = (st[:, 0] & np.uint32(0xFFFF0000)) | (np.arange(self.num_envs, dtype=np.uint32) % np.uint32(T))
+        clocks = (np.arange(self.num_envs, dtype=np.uint64) * np.uint64(multiplier)) % np.uint64(T)
+        st[:, 0] = (st[:, 0] & np.uint32(0xFFFF0000)) | clocks.astype(np.uint32)
         self.set_state(st)
 
     # SB3 VecEnv duck type (the rest of the convention; every env shares one configuration)
