@@ -83,6 +83,31 @@ def workload_config(wname, E, mode):
             "fow_radius": w["fow_radius"]}, A, F
 
 
+def ring_and_pool(E, A, F, ring_slots):
+    """(R, P): slots of the observation ring (at least 4x L2, at most ~2 GB) and batches of the action pool (> L2)."""
+    slot = E * A * F * 4
+    R = max(4, min(ring_slots, int(2.0e9 // slot)))
+    P = max(R, min(1024, int(math.ceil(256e6 / (E * A * 8)))))
+    return R, P
+
+
+def headline_config(wname, E, mode, ring_slots, stagger):
+    """The complete `config` object of the JSON line -- static, so that `--impl reference` prints the SAME object
+    (the reference arm runs on this arm's config)."""
+    cfg, A, F = workload_config(wname, E, mode)
+    R, P = ring_and_pool(E, A, F, ring_slots)
+    T = int(WORKLOADS[wname]["max_num_timesteps"])
+    cfg.update(
+        mode_desc=DESC[mode], rollout_ring_slots=R,
+        episode_clocks=("env e starts at (e * %d) mod T: about E/T envs finish in every step, spread over the batch"
+                        % spread_multiplier(T)) if stagger == "spread"
+        else "env e starts at e mod T: about E/T CONSECUTIVE envs finish in every step",
+        l2="inputs/outputs larger than L2: the obs ring (%d x %.1f MB) is rewritten round-robin and the action pool is "
+           "%.2f GB; only the %.1f MB packed state stays L2-resident (by design)"
+           % (R, E * A * F * 4 / 1e6, P * E * A * 8 / 1e9, E * 64 / 1e6))
+    return cfg
+
+
 def bytes_per_env_step(A, F):
     """obs out A*4*F + actions in A*2*4 + reward out A*4 + done 4 (u8 padded) +
     packed state read+write 2*64."""
@@ -189,11 +214,9 @@ class Bench:
         self.F = F = self.env.obs_width
         A = self.A
         self.bpes = bytes_per_env_step(A, F)
-        slot = E * A * F * 4
-        # ring of rollout-buffer slots the observations go to, round-robin: at least 4x L2 (126 MB), at most ~2 GB
-        self.R = R = max(4, min(ring_slots, int(2.0e9 // slot)))
-        # pool of pre-drawn action batches resident in HBM, cycled through by the step API: larger than L2
-        self.P = P = max(R, min(1024, int(math.ceil(256e6 / (E * A * 8)))))
+        # ring of rollout-buffer slots the observations go to, round-robin; pool of pre-drawn action batches resident
+        # in HBM, cycled through by the step API: both larger than L2
+        self.R, self.P = R, P = ring_and_pool(E, A, F, ring_slots)
         gen = torch.Generator(device=dev)
         gen.manual_seed(99 + rank)
         self.actions = torch.stack([torch.randint(0, 4, (P, E, A), generator=gen, device=dev, dtype=torch.int32),
@@ -442,7 +465,7 @@ def main():
                 "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32+f64", "data": "synthetic",
-                "config": workload_config(args.workload, args.envs or w["envs"], args.mode)[0],
+                "config": headline_config(args.workload, args.envs or w["envs"], args.mode, max(2, args.ring), args.stagger),
                 "cpu_baseline": res,
                 "e2e": {"value": res["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "wall_s": time.time() - t0}
@@ -588,14 +611,9 @@ def main():
             "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": primary["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32+f64", "data": "synthetic",
-            "config": dict(workload_config(args.workload, E, args.mode)[0],
-                           mode_desc=DESC[args.mode], cuda_graphs=primary["cuda_graphs"], rollout_ring_slots=R,
-                           resets_per_step=primary["resets_per_step"],
-                           episode_clocks=("env e starts at (e * %d) mod T: about E/T envs finish in every step, spread over the batch"
-                                           % spread_multiplier(int(w["max_num_timesteps"]))) if args.stagger == "spread"
-                                          else "env e starts at e mod T: about E/T CONSECUTIVE envs finish in every step",
-                           l2="inputs/outputs larger than L2: the obs ring (%d x %.1f MB) is rewritten round-robin and the action pool is %.2f GB; only the %.1f MB packed state stays L2-resident (by design)"
-                              % (R, E * A * F * 4 / 1e6, P * E * A * 8 / 1e9, E * 64 / 1e6)),
+            "config": headline_config(args.workload, E, args.mode, max(2, args.ring), args.stagger),
+            "protocol": {"cuda_graphs": primary["cuda_graphs"], "resets_per_step": primary["resets_per_step"],
+                         "repeats": primary["repeats"]["n"], "statistic": "median repeat, max over ranks per repeat"},
             "repeats": primary["repeats"],
             "roofline": primary["roofline"], "cpu_baseline": cpu, "e2e": e2e, "e2e_f32": e2e_f32, "e2e_terminal_obs": e2e_term,
             "gpu_launches": primary["gpu_launches"], "clocks": primary["clocks"],

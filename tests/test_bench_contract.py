@@ -24,6 +24,12 @@ def test_reference_arm_prints_contract_line():
         assert cb["kind"] == "port"
     assert cb["c_port"]["value"] > cb["value"]          # the C port is reported beside it
     assert line["config"]["workload"].startswith("cfg2: open-divider_tomato, 65536 envs/GPU")
+    # the reference arm runs on OUR arm's config: both print the object bench.headline_config builds (static, so the
+    # driver's same-config check compares like with like)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.headline_config("cfg2", 65536, "rollout", 64, "spread")
+    assert {"mode_desc", "l2", "episode_clocks", "rollout_ring_slots"} <= set(line["config"])
 
 
 def test_nonzero_rank_of_reference_arm_exits_quietly():
