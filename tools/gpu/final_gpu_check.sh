@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-end GPU check: gpurun -- 'bash tools/final_gpu_check.sh [notests]'
+# Round-end GPU check: gpurun -- 'bash tools/gpu/final_gpu_check.sh [notests]'
 # parity suite, smoke, the bench lines kept under profiles/, and the ncu launch list of the bench command.
 mkdir -p gpurun_out
 if [ "$1" != "notests" ]; then

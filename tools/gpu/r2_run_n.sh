@@ -1,5 +1,5 @@
 #!/bin/bash
-# multi-GPU session: bash tools/r2_run_n.sh N
+# multi-GPU session: bash tools/gpu/r2_run_n.sh N
 N=$1
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
