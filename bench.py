@@ -274,6 +274,12 @@ class Bench:
     def do_rollout(self, n):
         self.env.rollout(n, obs_out=self.obs_ring[:n], rew_out=self.rew_ring[:n], done_out=self.done_ring[:n])
 
+    def do_replay(self, n, first):
+        """oc_replay: n steps in ONE launch on a caller-given action sequence (a contiguous slice of the pool)."""
+        first %= max(1, self.P - n + 1)
+        self.env.replay(self.actions[first:first + n], obs_out=self.obs_ring[:n], rew_out=self.rew_ring[:n],
+                        done_out=self.done_ring[:n])
+
     def measure(self, mode, K, W, seconds=0.7, min_reps=30, max_reps=1500, diagnostics=True, clocks=True):
         """Times EXACTLY K steps of `mode` per repeat on the device: gate kernel, event, K steps, event; barrier +
         synchronize on both sides of every repeat; per-repeat max over ranks; median over repeats."""
@@ -281,6 +287,9 @@ class Bench:
         if mode == "step":
             for i in range(W):
                 self.do_step(i)
+        elif mode == "replay":
+            for i in range(W):
+                self.do_replay(1, i)
         else:
             for _ in range(W):
                 self.do_rollout(1)
@@ -321,7 +330,10 @@ class Bench:
             i, n_l = 0, 0
             while i < K:
                 n = min(R, K - i)
-                self.do_rollout(n)
+                if mode == "replay":
+                    self.do_replay(n, rep * K + i)
+                else:
+                    self.do_rollout(n)
                 i += n
                 n_l += 1
             return n_l
@@ -371,12 +383,12 @@ class Bench:
         avg_launch_ms = local_ms / nlaunch
         spl = K / nlaunch
         achieved = float(bpes) * E * spl / (avg_launch_ms / 1e3) / 1e9
-        moved = bpes if mode == "step" else A * 4 * F + A * 4 + 1
+        moved = bpes if mode == "step" else A * 4 * F + A * 4 + 1 + (A * 8 if mode == "replay" else 0)
         tr = self.traffic.get(self.wname + ":" + mode)
         roof = {"bound": "hbm", "achieved": achieved, "peak": self.peak, "unit": "GB/s", "frac": achieved / self.peak,
                 "traffic": (tr["dram_bytes_per_env_step"] * E * spl) if tr else None,
                 "traffic_source": (tr["source"] if tr else None), "peak_source": self.peak_src,
-                "kernel": "oc_step_kernel" if mode == "step" else "oc_rollout_kernel",
+                "kernel": "oc_step_kernel" if mode == "step" else "oc_rollout_kernel",      # oc_replay launches the rollout kernel
                 "bytes_per_env_step": bpes, "envs_per_launch": E, "steps_per_launch": spl,
                 # what this kernel really moves per env-step: the fused rollout keeps state and actions on chip, so
                 # only obs + reward + done cross HBM (that is why its algorithmic frac can exceed 1)
@@ -401,6 +413,8 @@ class Bench:
                 e0.record()
                 if mode == "step":
                     self.do_step(i)
+                elif mode == "replay":
+                    self.do_replay(nfl, i)
                 else:
                     self.do_rollout(nfl)
                 e1.record()
@@ -503,6 +517,10 @@ def main():
         b.chain = False
         plain = b.measure("step", K, W_, seconds=0.3, min_reps=10, diagnostics=False, clocks=False)
         b.chain = True
+    # open-loop sequences in one launch: oc_replay = the fused kernel reading a caller-given action sequence
+    replay = None
+    if not args.single_mode:
+        replay = b.measure("replay", K, W_, seconds=0.3, min_reps=10, diagnostics=False, clocks=False)
 
     # ---- e2e: the reference-facing call with HOST buffers: OvercookedHostVecEnv.step = C ABI oc_step_host*
     # (pinned numpy buffers; every step copies the actions host->device, runs the step kernel, copies
@@ -629,6 +647,12 @@ def main():
                         "waits for the previous one): the closed-loop case, where step N+1's actions depend on step N's output",
                 "value": plain["value"], "unit": "agent-steps/s", "ms_per_step": plain["ms_per_step"],
                 "roofline": plain["roofline"], "repeats": plain["repeats"], "gpu_launches": plain["gpu_launches"]}
+        if replay is not None:
+            line["replay_api"] = {
+                "desc": "C-ABI oc_replay: up to R steps per launch on a caller-given action sequence int32 [n, E, A, 2] read from "
+                        "HBM (recorded / scripted / pre-drawn actions), state on chip, auto-reset on",
+                "value": replay["value"], "unit": "agent-steps/s", "ms_per_step": replay["ms_per_step"],
+                "roofline": replay["roofline"], "repeats": replay["repeats"], "gpu_launches": replay["gpu_launches"]}
         if others:
             line["workloads"] = others
         print(json.dumps(line))

@@ -910,14 +910,13 @@ __device__ __forceinline__ Info rollout_logic(Env<A, NOBJ>& e, const OcParams& p
                                               uint32_t env, uint32_t s, uint32_t step0,
                                               float* __restrict__ rew32, uint8_t* __restrict__ done_out,
                                               int32_t* __restrict__ actions_out,
-                                              const int32_t* __restrict__ actions_in = nullptr) {
+                                              const int2* given = nullptr /* this env's A (nav, comm) pairs of step s */) {
     int nav[A];
     int c0, c1;
-    if (actions_in != nullptr) {                     // oc_replay: open-loop action sequence from HBM
-        const int2* a2 = reinterpret_cast<const int2*>(actions_in) + ((size_t)s * p.E + env) * A;
+    if (given != nullptr) {                          // oc_replay: open-loop action sequence, fetched one step ahead by the kernel
         int cm[A];
 #pragma unroll
-        for (int k = 0; k < A; ++k) { const int2 v = __ldg(a2 + k); nav[k] = v.x & 3; cm[k] = v.y; }
+        for (int k = 0; k < A; ++k) { nav[k] = given[k].x & 3; cm[k] = given[k].y; }
         c0 = ((uint32_t)cm[0] < (uint32_t)p.C) ? cm[0] : (int)OCK_COMM_NONE;
         c1 = ((uint32_t)cm[1] < (uint32_t)p.C) ? cm[1] : (int)OCK_COMM_NONE;
     } else {

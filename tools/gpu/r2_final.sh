@@ -12,6 +12,9 @@ for f in ("r2_bench_n1", "r2_bench_n1_again"):
     d = json.loads(open("gpurun_out/%s.json" % f).read().strip().splitlines()[-1])
     print(f, "rollout %.4g us/step %.3f frac %.3f moved %.3f" % (d["value"], d["ms_per_step"]*1e3, d["roofline"]["frac"], d["roofline"]["frac_moved"]), d["repeats"]["n"], d["clocks"])
     s = d["step_api"]; print("  step_api %.4g us/step %.3f frac %.3f" % (s["value"], s["ms_per_step"]*1e3, s["roofline"]["frac"]))
+    for k in ("step_api_unchained", "replay_api"):
+        s = d.get(k)
+        if s: print("  %s %.4g us/step %.3f frac %.3f moved %.3f" % (k, s["value"], s["ms_per_step"]*1e3, s["roofline"]["frac"], s["roofline"]["frac_moved"]))
     for k in ("e2e", "e2e_f32", "e2e_terminal_obs"):
         e = d.get(k)
         if e: print(" ", k, {a: e.get(a) for a in ("value", "us_per_step", "steps", "error")})
