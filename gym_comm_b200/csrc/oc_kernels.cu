@@ -561,6 +561,12 @@ extern "C" int oc_create(const oc_config* c, oc_env** out) {
             h->chain_threads = ct;
             h->chain_smem = smem_for(p, ct);
             h->chain_grid = (int)std::min<long long>(((long long)p.E + ct - 1) / ct, (long long)num_sm * caps[ct / 32]);
+            // OC_CHAIN_CHUNKS = m: a chained grid of 1/m of the CTAs, each walking m chunk groups.  The table load and the
+            // final drain are then paid once per m chunks, a warp's dynamics of chunk i+1 overlap the drain of chunk i (as
+            // in the fused kernel), and the slots the smaller grid leaves free are taken by the NEXT step of the chain.
+            const char* me = getenv("OC_CHAIN_CHUNKS");
+            const int m = me ? std::min(16, std::max(1, atoi(me))) : 1;
+            h->chain_grid = std::max(1, (h->chain_grid + m - 1) / m);
         }
     }
     // compact rows: small CTAs when the batch is a fraction of a wave (<= 16 warps of work per SM) -- the launch is then
