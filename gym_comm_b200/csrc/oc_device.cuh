@@ -563,6 +563,11 @@ __device__ __forceinline__ void build_rows_i8(const Env<A, NOBJ>& e, const OcPar
     for (int k = 0; k < A; ++k) build_row_u8_one<A, NOBJ, NF, 0u>(e, p, tb, in, k, row + k * (p.F - 1));
 }
 
+// byte offset of row slot `slot` inside a warp's row buffer (grouped rows: grp_pad bytes after every 2^grp_shift rows)
+__device__ __forceinline__ uint32_t row_offset(const OcParams& p, int slot) {
+    return (uint32_t)slot * (uint32_t)p.row_stride + (uint32_t)(slot >> p.grp_shift) * (uint32_t)p.grp_pad;
+}
+
 // warp-cooperative fill of the warp's 32 rows with the "all features 0.0" pattern
 template <bool ROWF>
 __device__ __forceinline__ void warp_clear_rows(uint8_t* wrows, int bytes, int lane) {
@@ -646,21 +651,25 @@ __device__ __forceinline__ void warp_expand_rows(const OcParams& p, const uint8_
             __syncwarp();
             if (p.use_tma == 1) {                    // contiguous rows: one copy for the warp
                 if (lane == 0) tma_store(out, wrows, (uint32_t)(total * 16));
+            } else if (p.use_tma == 3) {             // grouped rows: one copy per group, by the group's first lane
+                const int g = 1 << p.grp_shift;
+                if ((lane & (g - 1)) == 0 && lane < nvalid)
+                    tma_store(out + (size_t)lane * p.row_bytes, wrows + row_offset(p, lane),
+                              (uint32_t)(min(g, nvalid - lane) * p.row_bytes * 4));
             } else if (lane < nvalid) {              // padded rows (use_tma == 2): one copy per env row
                 tma_store(out + (size_t)lane * p.row_bytes, wrows + (size_t)lane * p.row_stride, (uint32_t)(p.row_bytes * 4));
             }
             return;
         }
 #endif
-        if (p.row_stride == p.row_bytes * 4) {      // contiguous rows
+        if (p.row_stride == p.row_bytes * 4 && p.grp_pad == 0) {      // contiguous rows
 #pragma unroll 4
             for (int idx = lane; idx < total; idx += 32) __stcs(o4 + idx, i4[idx]);   // streaming: written once, read later by the learner
-        } else {                                    // padded rows: env = idx / r4 by magic multiply
-            const int s4 = p.row_stride >> 4;
+        } else {                                    // padded / grouped rows: env = idx / r4 by magic multiply
 #pragma unroll 4
             for (int idx = lane; idx < total; idx += 32) {
                 const int env = (int)__umulhi((uint32_t)idx, p.r4_magic);
-                __stcs(o4 + idx, i4[env * s4 + (idx - env * r4)]);
+                __stcs(o4 + idx, i4[(row_offset(p, env) >> 4) + (idx - env * r4)]);
             }
         }
     } else if ((p.row_bytes & 3) == 0) {
@@ -754,7 +763,7 @@ __device__ __forceinline__ void emit_obs(const Env<A, NOBJ>& e, const Info& in, 
             warp_clear_rows<ROWF>(buf, MULTI ? p.buf_bytes : p.warp_row_bytes, lane);
             __syncwarp();
         }
-        uint8_t* myrow = buf + (MULTI ? (lane & (p.nb - 1)) : lane) * p.row_stride;
+        uint8_t* myrow = buf + row_offset(p, MULTI ? (lane & (p.nb - 1)) : lane);
         if (valid && (!MULTI || (lane >> p.nb_shift) == pass)) fill_rows<A, NOBJ, NF, ROWF>(e, p, tb, in, ts, myrow);
         __syncwarp();
         if (pass == 0) chain_release(chain_flag, chain_val, lane);
@@ -797,11 +806,11 @@ __device__ __forceinline__ void warp_terminal_obs(const Env<A, NOBJ>& e, const I
     warp_clear_rows<ROWF>(wrows, p.warp_row_bytes, lane);
     __syncwarp();
     if (MODE != 2) {
-        if (fin) thread_emit_rows<A, NOBJ, NF, ROWF>(e, p, tb, in, wrows + lane * p.row_stride, term_row);
+        if (fin) thread_emit_rows<A, NOBJ, NF, ROWF>(e, p, tb, in, wrows + row_offset(p, lane), term_row);
         __syncwarp();
         return;
     }
-    uint8_t* myrow = wrows + (lane & (p.nb - 1)) * p.row_stride;
+    uint8_t* myrow = wrows + row_offset(p, lane & (p.nb - 1));
     for (int pass = 0; pass < p.obs_passes; ++pass) {
         if (fin && (lane >> p.nb_shift) == pass) thread_emit_rows<A, NOBJ, NF, ROWF>(e, p, tb, in, myrow, term_row);
         __syncwarp();

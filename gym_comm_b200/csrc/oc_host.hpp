@@ -69,6 +69,7 @@ static inline void make_compact_params(OcParams& p) {
     p.row_bytes = p.A * (p.F - 1);
     p.row_stride = p.row_bytes;
     p.nb = 32; p.nb_shift = 5; p.obs_passes = 1; p.nbuf = 1;
+    p.grp_shift = 5; p.grp_pad = 0;
     p.buf_bytes = (int)align_up((size_t)32 * p.row_bytes, 16);
     p.warp_row_bytes = p.buf_bytes;
     p.use_tma = 1;
@@ -138,15 +139,26 @@ static inline int compile_config(const oc_config* c, HostImage& h, std::string& 
     }
     // float rows stay 16-byte aligned, so the best the per-thread scatter can do is a stride of
     // 4 (mod 8) words (8 distinct banks, 4-way conflict); a multiple of 8 words would put all 32 lanes
-    // on 1-4 banks (cfg4: 96 floats -> 32-way), so such rows get 4 floats of padding
+    // on 1-4 banks (cfg4: 96 floats -> 32-way).  Such rows are GROUPED: four rows stay contiguous, 16 bytes of
+    // padding follow every group -- lanes of one group share a bank (4-way, like everybody else), the eight groups
+    // sit on eight different banks, and a group leaves in ONE bulk copy (8 copies per warp and step; padding every
+    // single row, OC_ROW_GROUP=1, needs 32 small copies and made the fill phase of a cfg4 step 2.4x cfg2's).
     // (multi-pass rows stay contiguous: one bulk copy per pass measured faster than conflict-free fills)
     bool pad = (p.row_bytes & 7) == 0 && p.nb == 32;
     if (const char* o = getenv("OC_ROW_PAD")) pad = pad && atoi(o) != 0;
-    if (p.rowf) p.row_stride = (p.row_bytes + (pad ? 4 : 0)) * 4;
-    // 1: one bulk copy per pass (contiguous rows).  Padded rows would need one small copy per row: that
-    // measured slower in the fused rollout but faster in the single-step kernel, which sets 2 itself.
-    p.use_tma = (p.rowf && p.row_stride == p.row_bytes * 4) ? 1 : 0;
-    if (const char* t = getenv("OC_TMA")) p.use_tma = (p.use_tma && atoi(t) != 0) ? 1 : 0;
+    int group = 4;
+    if (const char* o = getenv("OC_ROW_GROUP")) { const int g = atoi(o); if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16) group = g; }
+    p.grp_shift = 5; p.grp_pad = 0;
+    if (p.rowf) {
+        p.row_stride = p.row_bytes * 4;
+        if (pad && group == 1) p.row_stride += 16;                 // every row padded
+        else if (pad) { p.grp_pad = 16; p.grp_shift = group == 2 ? 1 : group == 4 ? 2 : group == 8 ? 3 : 4; }
+    }
+    // 1: one bulk copy per pass (contiguous rows).  3: one bulk copy per row group.  Rows padded one by one would need
+    // one small copy per row: that measured slower in the fused rollout but faster in the single-step kernel, which
+    // sets 2 itself.
+    p.use_tma = !p.rowf ? 0 : (p.grp_pad != 0 ? 3 : (p.row_stride == p.row_bytes * 4 ? 1 : 0));
+    if (const char* t = getenv("OC_TMA")) p.use_tma = (p.use_tma && atoi(t) != 0) ? p.use_tma : 0;
     // A/B knob OC_ROW_BUFS=2: two half-size buffers used alternately, so that a pass only waits for the copy
     // issued two passes ago.  Measured slower everywhere (cfg2 5.1 vs 4.2 us, cfg3 35.4 vs 25.7, cfg5 35.0 vs
     // 33.9): every extra pass re-executes the per-lane fill with half of the lanes idle, which costs more
@@ -156,7 +168,7 @@ static inline int compile_config(const oc_config* c, HostImage& h, std::string& 
         if (atoi(o) == 2 && p.use_tma == 1 && p.nb >= 8) { p.nb /= 2; p.nbuf = 2; }
     p.nb_shift = p.nb == 32 ? 5 : p.nb == 16 ? 4 : p.nb == 8 ? 3 : 2;
     p.obs_passes = 32 / p.nb;
-    p.buf_bytes = p.nb * p.row_stride;
+    p.buf_bytes = p.nb * p.row_stride + (p.grp_pad ? (p.nb >> p.grp_shift) * p.grp_pad : 0);
     p.warp_row_bytes = p.nbuf * p.buf_bytes;
     p.r4_magic = (p.row_bytes >= 4) ? (uint32_t)((1ull << 32) / (uint64_t)(p.row_bytes >> 2)) + 1u : 0u;
     p.rf_magic = (uint32_t)((1ull << 32) / (uint64_t)p.row_bytes) + 1u;

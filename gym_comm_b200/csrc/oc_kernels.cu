@@ -102,10 +102,12 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, co
     // warps clear their rows.  (3) griddepcontrol.wait: everything below may touch what the previous grid wrote
     // (state, actions).  Both griddepcontrol instructions are no-ops when the launch carries no PDL attribute.
     __shared__ __align__(8) uint64_t tbar;
+#ifndef OC_TABLES_GLOBAL      // A/B build (tools/ab_tables_global.sh): tables read from global memory through L1, no staging
     if (threadIdx.x == 0) {
         mbar_init(&tbar, 1);
         tma_load(smem, p.blob, (uint32_t)p.blob_bytes, &tbar);
     }
+#endif
     asm volatile("griddepcontrol.launch_dependents;");
     uint8_t* wrows = smem + p.blob_bytes + (size_t)warp * p.warp_row_bytes;
     warp_clear_rows<MODE != 0>(wrows, p.warp_row_bytes, lane);
@@ -113,7 +115,11 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, co
     OC_PROBE(1, 0u);
     if (io.chain_pos == 0) asm volatile("griddepcontrol.wait;" ::: "memory");     // chained launches wait per chunk, below
     OC_PROBE(2, 0u);
+#ifdef OC_TABLES_GLOBAL
+    const Tables tb = make_tables(p, p.blob);
+#else
     const Tables tb = make_tables(p, smem);
+#endif
     const uint32_t flags = io.flags;
 
     // the grid is sized to ONE resident wave (148 SMs x CTAs that fit); with more envs than that
@@ -147,7 +153,9 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, co
             }
         }
         if (first) {
+#ifndef OC_TABLES_GLOBAL
             mbar_wait(&tbar, 0);                        // tables have landed (long ago, as a rule)
+#endif
             OC_PROBE(3, 0u);
         }
         if (valid) {                                    // dynamics: no row access, may overlap the previous chunk's TMA read
@@ -556,7 +564,7 @@ extern "C" int oc_create(const oc_config* c, oc_env** out) {
     {
         const char* ce = getenv("OC_BLOCK_THREADS_CHAIN");
         const int ct = ce ? atoi(ce) : 128;
-        if (ct >= 32 && ct <= 256 && ct % 32 == 0 && caps[ct / 32] >= 1 && (ce || (p.use_tma == 1 && p.obs_passes == 1 && !tenv &&
+        if (ct >= 32 && ct <= 256 && ct % 32 == 0 && caps[ct / 32] >= 1 && (ce || ((p.use_tma == 1 || p.use_tma == 3) && p.obs_passes == 1 && !tenv &&
             caps[ct / 32] >= 3 && ((long long)p.E + ct - 1) / ct <= (long long)num_sm * caps[ct / 32]))) {
             h->chain_threads = ct;
             h->chain_smem = smem_for(p, ct);

@@ -60,6 +60,10 @@ struct OcParams {
     int32_t obs_passes;                     // 32 / nb: a warp emits its 32 envs in this many passes
     int32_t nbuf, buf_bytes;                // row buffers per warp (1 or 2, used alternately) of nb * row_stride bytes each
     int32_t warp_row_bytes;                 // nbuf * buf_bytes
+    // grouped float rows (row sizes that are a multiple of 8 words would put every lane's scatter on the same bank):
+    // rows stay contiguous in groups of 2^grp_shift, grp_pad bytes follow every group -- a group leaves in ONE bulk copy
+    // and lanes of different groups hit different banks.  grp_pad == 0: no grouping.
+    int32_t grp_shift, grp_pad;
     // observation layout (float offsets inside one observer row)
     int32_t off_a1comm, off_a1loc, off_a2comm, off_a2loc, off_hold, off_completed,
             off_hidden, off_encx, off_ency, off_state, off_ts;

@@ -61,7 +61,7 @@ static void for_each_warp(emu_env* h, float* obs, float* term_obs, Body&& body) 
             if (fin) {
                 if (term_obs)        // warp_terminal_obs: rows clear, finished lanes emit one by one
                     thread_emit_rows<A, NOBJ, NF, ROWF>(we[lane], p, tb, win[lane],
-                                                        rows.data() + (size_t)(lane & (p.nb - 1)) * p.row_stride,
+                                                        rows.data() + row_offset(p, lane & (p.nb - 1)),
                                                         term_obs + (size_t)env * p.row_bytes);
                 finish_episode<A, NOBJ>(we[lane], p, tb, (uint32_t)env);
                 win[lane] = gather_info<A, NOBJ, NF>(we[lane], p, tb);
@@ -76,7 +76,7 @@ static void for_each_warp(emu_env* h, float* obs, float* term_obs, Body&& body) 
             for (int lane = 0; lane < nvalid; ++lane)
                 if ((lane >> p.nb_shift) == pass)
                     fill_rows<A, NOBJ, NF, ROWF>(we[lane], p, tb, win[lane], timestep_of<A, NOBJ>(we[lane], p, tb),
-                                                 buf + (size_t)(lane & (p.nb - 1)) * p.row_stride);
+                                                 buf + row_offset(p, lane & (p.nb - 1)));
             const int first = pass << p.nb_shift;
             const int nv = std::min(p.nb, nvalid - first);
             if (nv > 0)

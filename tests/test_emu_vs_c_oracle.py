@@ -22,6 +22,11 @@ CONFIGS = {
     "random_wide_c100": dict(level="random-salad-superwide", num_agents=2, max_num_timesteps=19,
                              communication_on=True, num_communication=100, ego_led=False, fow_radius=2,
                              ego_config=D, partner_config=D),
+    # rows of 96 floats (a multiple of 8 words): grouped rows -- four contiguous rows, then 16 bytes of padding
+    "salad_c8_grouped": dict(level="random-open-divider_salad_small_cramped", num_agents=2, max_num_timesteps=19,
+                             communication_on=True, num_communication=8, ego_led=False, fow_radius=10,
+                             ego_config=dict(CAN_MOVE=False, ALLERGIC=True, BLIND=False),
+                             partner_config=dict(CAN_MOVE=True, ALLERGIC=False, BLIND=True)),
     "wide3_c60": dict(level="partial-divider_salad", num_agents=3, max_num_timesteps=13, communication_on=True,
                       num_communication=60, ego_led=False, fow_radius=2, ego_config=D, partner_config=D),
     "wide4_c100": dict(level="open-divider_salad", num_agents=4, max_num_timesteps=11, communication_on=True,
@@ -40,6 +45,8 @@ FORMATS = {
     "bytes": dict(OC_ROW_FORMAT="b"),
     "f16x2": dict(OC_ROW_BUFS="2"),
     "f8x2": dict(OC_ROW_FORMAT="f", OC_ROW_ENVS="16", OC_ROW_PAD="0", OC_ROW_BUFS="2"),
+    "group1": dict(OC_ROW_GROUP="1"),          # every row padded (one bulk copy per row on the device)
+    "group8": dict(OC_ROW_GROUP="8"),
 }
 
 
