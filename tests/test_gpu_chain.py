@@ -24,7 +24,9 @@ def _actions(n, E, A, C, seed):
 
 
 @pytest.mark.parametrize("level,A,T,C,E", [("open-divider_tomato", 2, 23, 10, 65536), ("partial-divider_salad", 3, 17, 10, 300000),
-                                           ("random-salad-superwide", 2, 19, 100, 70001), ("open-divider_tomato", 2, 9, 4, 33)])
+                                           ("random-salad-superwide", 2, 19, 100, 70001), ("open-divider_tomato", 2, 9, 4, 33),
+                                           # rows of 96 floats: grouped rows, one bulk copy per group of four
+                                           ("random-open-divider_salad_small_cramped", 2, 21, 8, 65569)])
 def test_chained_steps_equal_plain_steps(level, A, T, C, E):
     from gym_comm_b200.vec_env import OvercookedVecEnv
     n = 36
