@@ -137,18 +137,12 @@ __device__ __forceinline__ uint32_t obj_set_cell(uint32_t o, uint32_t c) { retur
 // drawn uniformly from ALL Counter tiles, rejecting tiles already taken by an earlier phase-4
 // object == sequential sampling without replacement: draw j picks the k-th still-free counter,
 // k = mulhi(Philox word j of counter (env, episode, 'RESE', j / 4), ncounters - j) -- the same
-// algorithm as oracle/oc_oracle.c.  Registers only (a 128-bit "taken" mask, no local arrays, no
-// call): a finishing env holds up its whole warp, and in a launch of a few steps the slowest warp
-// IS the launch (a stack-based version cost cfg4 1.3 us per step of a 20-step rollout).
-__device__ __forceinline__ uint32_t kth_free_counter(uint64_t taken_lo, uint64_t taken_hi, uint32_t k) {
-    uint64_t z = ~taken_lo;
-    uint32_t base = 0;
-    const uint32_t c = (uint32_t)__popcll(z);
-    if (k >= c) { k -= c; z = ~taken_hi; base = 64; }
-    for (; k != 0; --k) z &= z - 1;                      // drop the k lowest free bits
-    return base + (uint32_t)__ffsll((long long)z) - 1u;
-}
-
+// algorithm as oracle/oc_oracle.c.  "The k-th still-free counter" = k, bumped once for every taken index
+// it reaches, the taken indices visited in ascending order; at most five are ever taken, so they live
+// sorted in registers and the whole draw is a few dozen straight-line compare / add / min / max
+// instructions: no loop, no local array, no call.  (A finishing env holds up its whole warp, and in a
+// launch of a few steps the slowest warp IS the launch: a stack-based version cost cfg4 1.3 us per step
+// of a 20-step rollout, a 128-bit taken-mask version spent a data-dependent loop per object on "drop the k lowest free bits".)
 __device__ __forceinline__ void draw_random_cells(const OcParams& p, const uint8_t* __restrict__ counters,
                                                   uint32_t env_id, uint32_t episode, uint32_t (&cell)[OCK_MAX_OBJECTS]) {
     uint32_t r[8];
@@ -157,15 +151,18 @@ __device__ __forceinline__ void draw_random_cells(const OcParams& p, const uint8
         philox4x32_10(env_id, episode, 0x52455345u, 1u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), r + 4);
     else
         r[4] = r[5] = r[6] = r[7] = 0u;
-    // counters beyond ncounters count as taken, so that "the k-th free bit" only ever lands on a real counter
-    uint64_t lo = p.ncounters >= 64 ? 0ull : ~0ull << p.ncounters;
-    uint64_t hi = p.ncounters >= 128 ? 0ull : (p.ncounters <= 64 ? ~0ull : ~0ull << (p.ncounters - 64));
+    uint32_t taken[OCK_MAX_OBJECTS];                         // ascending; fully unrolled -> registers
 #pragma unroll
     for (int j = 0; j < OCK_MAX_OBJECTS; ++j) {
         if (j < p.nrandom) {
-            const uint32_t idx = kth_free_counter(lo, hi, __umulhi(r[j], (uint32_t)(p.ncounters - j)));
-            if (idx < 64) lo |= 1ull << idx; else hi |= 1ull << (idx - 64);
+            uint32_t idx = __umulhi(r[j], (uint32_t)(p.ncounters - j));
+#pragma unroll
+            for (int i = 0; i < j; ++i) idx += (idx >= taken[i]) ? 1u : 0u;
             cell[j] = counters[idx];
+            uint32_t v = idx;                                // insert into the sorted list
+#pragma unroll
+            for (int i = 0; i < j; ++i) { const uint32_t lo = min(taken[i], v); v = max(taken[i], v); taken[i] = lo; }
+            taken[j] = v;
         }
     }
 }
