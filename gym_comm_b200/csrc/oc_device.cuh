@@ -460,16 +460,24 @@ __device__ __forceinline__ void channel_features(const Tables& tb, uint32_t word
     ey = __fmaf_rn(dy, hid, 0.0f);
 }
 
+// `rot`: the observer this thread writes FIRST.  Lanes 8 apart share their banks when the row stride is 4 (mod 8) words
+// (cfg2: 92, cfg3: 156), so the emit path hands lanes of different octets different starting observers: at any one
+// store instruction they then write rows that are F words apart (F is not a multiple of 4 for those strides),
+// i.e. on different banks -- the 4-way conflict of the fixed-offset stores becomes 2-way (A = 2, 3) or none (A = 4).
 template <int A, int NOBJ, int NF>
 __device__ __forceinline__ void build_rows_f32(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
-                                               const Info& in, float ts, float* __restrict__ row /* zero-filled */) {
+                                               const Info& in, float ts, float* __restrict__ row /* zero-filled */,
+                                               int rot = 0) {
     const float2 a0 = tb.xyf[e.acell[0]], a1 = tb.xyf[e.acell[1]];
     const uint32_t c0 = e.comm & 0xFFFFu, c1 = e.comm >> 16;
     const float fow = (float)p.fow;
+    const uint32_t blind_bits = (p.blind[0] ? 1u : 0u) | (p.blind[1] ? 2u : 0u) | (p.blind[2] ? 4u : 0u) | (p.blind[3] ? 8u : 0u);
 #pragma unroll
-    for (int k = 0; k < A; ++k) {
+    for (int k0 = 0; k0 < A; ++k0) {
+        int k = k0 + rot;
+        k -= (k >= A) ? A : 0;
         float* r = row + k * p.F;
-        const bool blind = p.blind[k] != 0;                                    // :115-118
+        const bool blind = ((blind_bits >> k) & 1u) != 0;                      // :115-118
         if (c0 != OCK_COMM_NONE) r[p.off_a1comm + c0] = 1.0f;
         if (c1 != OCK_COMM_NONE) r[p.off_a2comm + c1] = 1.0f;
         if (!blind) {                                                          // :139-143
@@ -481,7 +489,13 @@ __device__ __forceinline__ void build_rows_f32(const Env<A, NOBJ>& e, const OcPa
 #pragma unroll
             for (int c = 0; c < 4; ++c) r[p.off_hidden + c] = 1.0f;            // :109
         } else {
-            const float2 me = (k == 0) ? a0 : ((k == 1) ? a1 : tb.xyf[e.acell[k]]);
+            float2 me = a0;
+            if (k == 1) me = a1;
+            if (A > 2 && k >= 2) {
+                uint32_t cellk = e.acell[2];
+                if (A > 3 && k == 3) cellk = e.acell[A > 3 ? 3 : 2];
+                me = tb.xyf[cellk];
+            }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 if (c < 3 && c >= NF) continue;                 // a food this level never holds: features stay 0
@@ -712,8 +726,8 @@ __device__ __forceinline__ float timestep_of(const Env<A, NOBJ>& e, const OcPara
 
 template <int A, int NOBJ, int NF, bool ROWF>
 __device__ __forceinline__ void fill_rows(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
-                                          const Info& in, float ts, uint8_t* myrow) {
-    if (ROWF) build_rows_f32<A, NOBJ, NF>(e, p, tb, in, ts, reinterpret_cast<float*>(myrow));
+                                          const Info& in, float ts, uint8_t* myrow, int rot = 0) {
+    if (ROWF) build_rows_f32<A, NOBJ, NF>(e, p, tb, in, ts, reinterpret_cast<float*>(myrow), rot);
     else build_rows_u8<A, NOBJ, NF>(e, p, tb, in, myrow);
 }
 
@@ -761,7 +775,9 @@ __device__ __forceinline__ void emit_obs(const Env<A, NOBJ>& e, const Info& in, 
             __syncwarp();
         }
         uint8_t* myrow = buf + row_offset(p, MULTI ? (lane & (p.nb - 1)) : lane);
-        if (valid && (!MULTI || (lane >> p.nb_shift) == pass)) fill_rows<A, NOBJ, NF, ROWF>(e, p, tb, in, ts, myrow);
+        // starting observer per lane octet (single-pass, ungrouped float rows; see build_rows_f32)
+        const int rot = (ROWF && !MULTI && p.grp_pad == 0 && p.obs_rot) ? ((lane >> 3) % A) : 0;
+        if (valid && (!MULTI || (lane >> p.nb_shift) == pass)) fill_rows<A, NOBJ, NF, ROWF>(e, p, tb, in, ts, myrow, rot);
         __syncwarp();
         if (pass == 0) chain_release(chain_flag, chain_val, lane);
         const int first = MULTI ? (pass << p.nb_shift) : 0;

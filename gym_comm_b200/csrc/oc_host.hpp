@@ -168,6 +168,8 @@ static inline int compile_config(const oc_config* c, HostImage& h, std::string& 
         if (atoi(o) == 2 && p.use_tma == 1 && p.nb >= 8) { p.nb /= 2; p.nbuf = 2; }
     p.nb_shift = p.nb == 32 ? 5 : p.nb == 16 ? 4 : p.nb == 8 ? 3 : 2;
     p.obs_passes = 32 / p.nb;
+    p.obs_rot = (p.rowf && ((p.row_stride >> 2) & 7) == 4 && (p.F & 3) != 0) ? 1 : 0;
+    if (const char* o = getenv("OC_OBS_ROT")) p.obs_rot = p.obs_rot && atoi(o) != 0;
     p.buf_bytes = p.nb * p.row_stride + (p.grp_pad ? (p.nb >> p.grp_shift) * p.grp_pad : 0);
     p.warp_row_bytes = p.nbuf * p.buf_bytes;
     p.r4_magic = (p.row_bytes >= 4) ? (uint32_t)((1ull << 32) / (uint64_t)(p.row_bytes >> 2)) + 1u : 0u;

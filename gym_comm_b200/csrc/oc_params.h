@@ -64,6 +64,7 @@ struct OcParams {
     // rows stay contiguous in groups of 2^grp_shift, grp_pad bytes follow every group -- a group leaves in ONE bulk copy
     // and lanes of different groups hit different banks.  grp_pad == 0: no grouping.
     int32_t grp_shift, grp_pad;
+    int32_t obs_rot;                        // 1: lanes of different octets start their rows with different observers (OC_OBS_ROT)
     // observation layout (float offsets inside one observer row)
     int32_t off_a1comm, off_a1loc, off_a2comm, off_a2loc, off_hold, off_completed,
             off_hidden, off_encx, off_ency, off_state, off_ts;
