@@ -464,7 +464,7 @@ __device__ __forceinline__ void channel_features(const Tables& tb, uint32_t word
 // (cfg2: 92, cfg3: 156), so the emit path hands lanes of different octets different starting observers: at any one
 // store instruction they then write rows that are F words apart (F is not a multiple of 4 for those strides),
 // i.e. on different banks -- the 4-way conflict of the fixed-offset stores becomes 2-way (A = 2, 3) or none (A = 4).
-template <int A, int NOBJ, int NF>
+template <int A, int NOBJ, int NF, bool ROT = false /* compile-time: without it k stays a constant of the unrolled loop */>
 __device__ __forceinline__ void build_rows_f32(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
                                                const Info& in, float ts, float* __restrict__ row /* zero-filled */,
                                                int rot = 0) {
@@ -474,8 +474,8 @@ __device__ __forceinline__ void build_rows_f32(const Env<A, NOBJ>& e, const OcPa
     const uint32_t blind_bits = (p.blind[0] ? 1u : 0u) | (p.blind[1] ? 2u : 0u) | (p.blind[2] ? 4u : 0u) | (p.blind[3] ? 8u : 0u);
 #pragma unroll
     for (int k0 = 0; k0 < A; ++k0) {
-        int k = k0 + rot;
-        k -= (k >= A) ? A : 0;
+        int k = k0;
+        if (ROT) { k += rot; k -= (k >= A) ? A : 0; }
         float* r = row + k * p.F;
         const bool blind = ((blind_bits >> k) & 1u) != 0;                      // :115-118
         if (c0 != OCK_COMM_NONE) r[p.off_a1comm + c0] = 1.0f;
@@ -724,10 +724,10 @@ __device__ __forceinline__ float timestep_of(const Env<A, NOBJ>& e, const OcPara
     return (p.o_ts >= 0 && t <= (uint32_t)p.T) ? tb.ts[t] : (float)__ddiv_rn((double)t, (double)p.T);
 }
 
-template <int A, int NOBJ, int NF, bool ROWF>
+template <int A, int NOBJ, int NF, bool ROWF, bool ROT = false>
 __device__ __forceinline__ void fill_rows(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
                                           const Info& in, float ts, uint8_t* myrow, int rot = 0) {
-    if (ROWF) build_rows_f32<A, NOBJ, NF>(e, p, tb, in, ts, reinterpret_cast<float*>(myrow), rot);
+    if (ROWF) build_rows_f32<A, NOBJ, NF, ROT>(e, p, tb, in, ts, reinterpret_cast<float*>(myrow), rot);
     else build_rows_u8<A, NOBJ, NF>(e, p, tb, in, myrow);
 }
 
@@ -756,7 +756,8 @@ __device__ __forceinline__ void chain_release(uint32_t* flag, uint32_t val, int 
 // overlap the copy engine's drain.  Each pass waits for its buffer to be read out, clears it (unless
 // the caller says the rows are clean), fills it, and hands it to the copy engine (or stores it with
 // the warp).
-template <int A, int NOBJ, int NF, int MODE /* 0 byte rows, 1 float rows, 2 float rows in several passes */>
+template <int A, int NOBJ, int NF, int MODE /* 0 byte rows, 1 float rows, 2 float rows in several passes */,
+          bool ROT = false /* the single-step kernel: observer rotation per lane octet, see build_rows_f32 */>
 __device__ __forceinline__ void emit_obs(const Env<A, NOBJ>& e, const Info& in, bool valid, const OcParams& p,
                                          const Tables& tb, uint8_t* wrows, int lane,
                                          float* __restrict__ out_env0 /* warp's first env row */, int nvalid,
@@ -776,8 +777,9 @@ __device__ __forceinline__ void emit_obs(const Env<A, NOBJ>& e, const Info& in, 
         }
         uint8_t* myrow = buf + row_offset(p, MULTI ? (lane & (p.nb - 1)) : lane);
         // starting observer per lane octet (single-pass, ungrouped float rows; see build_rows_f32)
-        const int rot = (ROWF && !MULTI && p.grp_pad == 0 && p.obs_rot) ? ((lane >> 3) % A) : 0;
-        if (valid && (!MULTI || (lane >> p.nb_shift) == pass)) fill_rows<A, NOBJ, NF, ROWF>(e, p, tb, in, ts, myrow, rot);
+        constexpr bool R = ROT && ROWF && !MULTI;
+        const int rot = (R && p.grp_pad == 0 && p.obs_rot) ? ((lane >> 3) % A) : 0;
+        if (valid && (!MULTI || (lane >> p.nb_shift) == pass)) fill_rows<A, NOBJ, NF, ROWF, R>(e, p, tb, in, ts, myrow, rot);
         __syncwarp();
         if (pass == 0) chain_release(chain_flag, chain_val, lane);
         const int first = MULTI ? (pass << p.nb_shift) : 0;
@@ -932,13 +934,14 @@ __device__ __forceinline__ Info rollout_logic(Env<A, NOBJ>& e, const OcParams& p
                                               uint32_t env, uint32_t s, uint32_t step0,
                                               float* __restrict__ rew32, uint8_t* __restrict__ done_out,
                                               int32_t* __restrict__ actions_out,
-                                              const int2* given = nullptr /* this env's A (nav, comm) pairs of step s */) {
+                                              const int32_t* __restrict__ actions_in = nullptr) {
     int nav[A];
     int c0, c1;
-    if (given != nullptr) {                          // oc_replay: open-loop action sequence, fetched one step ahead by the kernel
+    if (actions_in != nullptr) {                     // oc_replay: open-loop action sequence from HBM
+        const int2* a2 = reinterpret_cast<const int2*>(actions_in) + ((size_t)s * p.E + env) * A;
         int cm[A];
 #pragma unroll
-        for (int k = 0; k < A; ++k) { nav[k] = given[k].x & 3; cm[k] = given[k].y; }
+        for (int k = 0; k < A; ++k) { const int2 v = __ldg(a2 + k); nav[k] = v.x & 3; cm[k] = v.y; }
         c0 = ((uint32_t)cm[0] < (uint32_t)p.C) ? cm[0] : (int)OCK_COMM_NONE;
         c1 = ((uint32_t)cm[1] < (uint32_t)p.C) ? cm[1] : (int)OCK_COMM_NONE;
     } else {

@@ -191,7 +191,7 @@ oc_step_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state, co
                                          reinterpret_cast<uint8_t*>(io.obs) + (size_t)env0 * p.row_bytes,
                                          io.ts ? io.ts + env0 : nullptr, nvalid, first, cflag, io.chain_pos + 1u);
         else
-            emit_obs<A, NOBJ, NF, (MODE == 3 ? 0 : MODE)>(e, in, valid, p, tb, wrows, lane,
+            emit_obs<A, NOBJ, NF, (MODE == 3 ? 0 : MODE), true>(e, in, valid, p, tb, wrows, lane,
                                          reinterpret_cast<float*>(io.obs) + (size_t)env0 * p.row_bytes, nvalid, first,
                                          cflag, io.chain_pos + 1u);
         OC_PROBE(7, 0u);
@@ -231,24 +231,11 @@ oc_rollout_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
     const int nvalid = min(32, p.E - env0);
     const size_t step_floats = (size_t)p.E * p.row_bytes;
 
-    // oc_replay: the actions of step s + 1 are loaded while step s's rows are filled and handed to the copy engine, so
-    // the HBM latency of the caller's action sequence is never on a step's critical path
-    int2 given[A];
-    const int2* act2 = reinterpret_cast<const int2*>(actions_in);
-    if (act2 != nullptr && valid && n_steps > 0) {
-#pragma unroll
-        for (int k = 0; k < A; ++k) given[k] = __ldg(act2 + (size_t)env * A + k);
-    }
     for (int s = 0; s < n_steps; ++s) {
         // dynamics first: they do not touch the rows, so the copy engine may still be reading the
         // previous step's rows out of shared memory while this runs
         Info in;
-        if (valid) in = rollout_logic<A, NOBJ, NF, ROWF>(e, p, tb, (uint32_t)env, (uint32_t)s, step0, rew32, done_out, actions_out,
-                                                         act2 != nullptr ? given : nullptr);
-        if (act2 != nullptr && valid && s + 1 < n_steps) {
-#pragma unroll
-            for (int k = 0; k < A; ++k) given[k] = __ldg(act2 + ((size_t)(s + 1) * p.E + env) * A + k);
-        }
+        if (valid) in = rollout_logic<A, NOBJ, NF, ROWF>(e, p, tb, (uint32_t)env, (uint32_t)s, step0, rew32, done_out, actions_out, actions_in);
         if (obs != nullptr) {
             emit_obs<A, NOBJ, NF, MODE>(e, in, valid, p, tb, wrows, lane,
                                     obs + (size_t)s * step_floats + (size_t)env0 * p.row_bytes, nvalid);

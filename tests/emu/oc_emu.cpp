@@ -75,7 +75,7 @@ static void for_each_warp(emu_env* h, float* obs, float* term_obs, Body&& body) 
             for (int lane = 0; lane < 32; ++lane) warp_clear_rows<ROWF>(buf, p.buf_bytes, lane);
             for (int lane = 0; lane < nvalid; ++lane)
                 if ((lane >> p.nb_shift) == pass)
-                    fill_rows<A, NOBJ, NF, ROWF>(we[lane], p, tb, win[lane], timestep_of<A, NOBJ>(we[lane], p, tb),
+                    fill_rows<A, NOBJ, NF, ROWF, true>(we[lane], p, tb, win[lane], timestep_of<A, NOBJ>(we[lane], p, tb),
                                                  buf + row_offset(p, lane & (p.nb - 1)),
                                                  (ROWF && p.obs_passes == 1 && p.grp_pad == 0 && p.obs_rot) ? ((lane >> 3) % A) : 0);
             const int first = pass << p.nb_shift;
