@@ -464,10 +464,17 @@ __device__ __forceinline__ void channel_features(const Tables& tb, uint32_t word
 // (cfg2: 92, cfg3: 156), so the emit path hands lanes of different octets different starting observers: at any one
 // store instruction they then write rows that are F words apart (F is not a multiple of 4 for those strides),
 // i.e. on different banks -- the 4-way conflict of the fixed-offset stores becomes 2-way (A = 2, 3) or none (A = 4).
-template <int A, int NOBJ, int NF, bool ROT = false /* compile-time: without it k stays a constant of the unrolled loop */>
+//
+// UNDO (the fused kernel, single-pass rows): the row is NOT zero-filled but still holds this env's previous
+// observation.  Every feature at a fixed offset is then written unconditionally (zeros included), and the three
+// data-dependent ones are taken back first: the two message one-hots of the previous step (`shown_comm`) and the
+// completed-subtask bits that are no longer set (`shown_completed`, i.e. after an episode boundary).  That replaces
+// the 12 KB row clear of every step (92 shared-memory wavefronts per warp) by a handful of scattered stores.
+template <int A, int NOBJ, int NF, bool ROT = false /* compile-time: without it k stays a constant of the unrolled loop */,
+          bool UNDO = false>
 __device__ __forceinline__ void build_rows_f32(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
                                                const Info& in, float ts, float* __restrict__ row /* zero-filled */,
-                                               int rot = 0) {
+                                               int rot = 0, uint32_t shown_comm = 0, uint32_t shown_completed = 0) {
     const float2 a0 = tb.xyf[e.acell[0]], a1 = tb.xyf[e.acell[1]];
     const uint32_t c0 = e.comm & 0xFFFFu, c1 = e.comm >> 16;
     const float fow = (float)p.fow;
@@ -478,13 +485,19 @@ __device__ __forceinline__ void build_rows_f32(const Env<A, NOBJ>& e, const OcPa
         if (ROT) { k += rot; k -= (k >= A) ? A : 0; }
         float* r = row + k * p.F;
         const bool blind = ((blind_bits >> k) & 1u) != 0;                      // :115-118
+        if (UNDO) {                                                            // the previous step's messages
+            const uint32_t s0 = shown_comm & 0xFFFFu, s1 = shown_comm >> 16;
+            if (s0 != OCK_COMM_NONE) r[p.off_a1comm + s0] = 0.0f;
+            if (s1 != OCK_COMM_NONE) r[p.off_a2comm + s1] = 0.0f;
+        }
         if (c0 != OCK_COMM_NONE) r[p.off_a1comm + c0] = 1.0f;
         if (c1 != OCK_COMM_NONE) r[p.off_a2comm + c1] = 1.0f;
         if (!blind) {                                                          // :139-143
             r[p.off_a1loc] = a0.x; r[p.off_a1loc + 1] = a0.y;
             r[p.off_a2loc] = a1.x; r[p.off_a2loc + 1] = a1.y;
         }
-        if (!p.ego_blind && ((in.holdmask >> k) & 1u)) r[p.off_hold] = 1.0f;   // :154
+        if (UNDO) { if (!p.ego_blind) r[p.off_hold] = ((in.holdmask >> k) & 1u) ? 1.0f : 0.0f; }
+        else if (!p.ego_blind && ((in.holdmask >> k) & 1u)) r[p.off_hold] = 1.0f;   // :154
         if (blind) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) r[p.off_hidden + c] = 1.0f;            // :109
@@ -507,13 +520,25 @@ __device__ __forceinline__ void build_rows_f32(const Env<A, NOBJ>& e, const OcPa
                     r[p.off_encx + c] = ex;
                     r[p.off_ency + c] = ey;
                     if (c < 3) r[p.off_state + c] = st;
+                } else if (UNDO) {                                             // ... unless the row still holds the last step
+                    r[p.off_hidden + c] = 0.0f;
+                    r[p.off_encx + c] = 0.0f;
+                    r[p.off_ency + c] = 0.0f;
+                    if (c < 3) r[p.off_state + c] = 0.0f;
                 }
             }
         }
         r[p.off_ts] = ts;                                                      // :146
     }
+    if (UNDO) {                                     // bits shown last step that are gone (a new episode began)
+        for (uint32_t m = shown_completed & ~e.completed; m != 0; m &= m - 1) {
+            float* r = row + p.off_completed + (__ffs((int)m) - 1);
+#pragma unroll
+            for (int k = 0; k < A; ++k) r[k * p.F] = 0.0f;
+        }
+    }
     // completed_subtasks: the same bits for every observer -- walk the set bits once
-    for (uint32_t m = e.completed; m != 0; m &= m - 1) {
+    for (uint32_t m = (UNDO ? (e.completed & ~shown_completed) : e.completed); m != 0; m &= m - 1) {
         float* r = row + p.off_completed + (__ffs((int)m) - 1);
 #pragma unroll
         for (int k = 0; k < A; ++k) r[k * p.F] = 1.0f;
@@ -727,7 +752,7 @@ __device__ __forceinline__ float timestep_of(const Env<A, NOBJ>& e, const OcPara
 template <int A, int NOBJ, int NF, bool ROWF, bool ROT = false>
 __device__ __forceinline__ void fill_rows(const Env<A, NOBJ>& e, const OcParams& p, const Tables& tb,
                                           const Info& in, float ts, uint8_t* myrow, int rot = 0) {
-    if (ROWF) build_rows_f32<A, NOBJ, NF, ROT>(e, p, tb, in, ts, reinterpret_cast<float*>(myrow), rot);
+    if (ROWF) build_rows_f32<A, NOBJ, NF, ROT, false>(e, p, tb, in, ts, reinterpret_cast<float*>(myrow), rot);
     else build_rows_u8<A, NOBJ, NF>(e, p, tb, in, myrow);
 }
 
@@ -790,6 +815,21 @@ __device__ __forceinline__ void emit_obs(const Env<A, NOBJ>& e, const Info& in, 
         __syncwarp();                               // orders the float4 stores before the timestep patch
         if (valid) store_timesteps<A>(p, out_env0 + (size_t)lane * p.row_bytes, ts);
     }
+}
+
+// The fused kernel's steady state for single-pass float rows: this warp's rows still hold the same envs' previous
+// observation (nobody else ever writes them), so instead of clearing 12 KB the threads take back what the previous fill
+// put at data-dependent places and overwrite the rest (build_rows_f32<UNDO>).
+template <int A, int NOBJ, int NF>
+__device__ __forceinline__ void emit_obs_undo(const Env<A, NOBJ>& e, const Info& in, bool valid, const OcParams& p,
+                                              const Tables& tb, uint8_t* wrows, int lane, float* __restrict__ out_env0,
+                                              int nvalid, uint32_t shown_comm, uint32_t shown_completed) {
+    const float ts = valid ? timestep_of<A, NOBJ>(e, p, tb) : 0.0f;
+    rows_wait_read(p);                              // the copy engine has read the previous step's rows
+    if (valid) build_rows_f32<A, NOBJ, NF, false, true>(e, p, tb, in, ts, reinterpret_cast<float*>(wrows + row_offset(p, lane)),
+                                                        0, shown_comm, shown_completed);
+    __syncwarp();
+    if (nvalid > 0) warp_expand_rows<true>(p, wrows, out_env0, nvalid, lane);
 }
 
 // a single thread emits its own env's rows (rare path: terminal observations); its row must be

@@ -30,6 +30,11 @@ using namespace ock;
 #define OC_STEP_BOUNDS(MODE) __launch_bounds__(256, ((MODE) == 1 || (MODE) == 2) ? 2 : 4)
 #endif
 
+// A/B knob (compile time): -DOC_ROW_UNDO=0 makes the fused kernel clear its single-pass float rows in every step again
+#ifndef OC_ROW_UNDO
+#define OC_ROW_UNDO 1
+#endif
+
 // Phase probe (tools/probe_step.py, -DOC_PHASE_PROBE builds only; never in the shipped library): lane 0 of every
 // warp stamps %clock64 at the phase boundaries of the step kernel and %globaltimer at entry / exit.
 #ifdef OC_PHASE_PROBE
@@ -231,14 +236,35 @@ oc_rollout_kernel(const __grid_constant__ OcParams p, uint4* __restrict__ state,
     const int nvalid = min(32, p.E - env0);
     const size_t step_floats = (size_t)p.E * p.row_bytes;
 
-    for (int s = 0; s < n_steps; ++s) {
+    // Single-pass float rows (MODE 1): after the first step of the launch the warp's rows are never cleared again -- they
+    // still hold the same envs' previous observation, and emit_obs_undo takes back / overwrites it (shown_*: what the row
+    // shows at its data-dependent places).  The first step is peeled off the loop so that the loop body carries ONE copy of
+    // the fill code: the hot loop is far larger than the L0 instruction cache, and its size shows up directly in the step time.
+    constexpr bool UNDO = (MODE == 1) && (OC_ROW_UNDO != 0);
+    uint32_t shown_comm = 0, shown_completed = 0;
+    int s = 0;
+    if (UNDO && n_steps > 0) {
+        Info in;
+        if (valid) in = rollout_logic<A, NOBJ, NF, ROWF>(e, p, tb, (uint32_t)env, 0u, step0, rew32, done_out, actions_out, actions_in);
+        if (obs != nullptr) {
+            emit_obs<A, NOBJ, NF, MODE>(e, in, valid, p, tb, wrows, lane, obs + (size_t)env0 * p.row_bytes, nvalid);
+            shown_comm = e.comm; shown_completed = e.completed;
+        }
+        s = 1;
+    }
+    for (; s < n_steps; ++s) {
         // dynamics first: they do not touch the rows, so the copy engine may still be reading the
         // previous step's rows out of shared memory while this runs
         Info in;
         if (valid) in = rollout_logic<A, NOBJ, NF, ROWF>(e, p, tb, (uint32_t)env, (uint32_t)s, step0, rew32, done_out, actions_out, actions_in);
         if (obs != nullptr) {
-            emit_obs<A, NOBJ, NF, MODE>(e, in, valid, p, tb, wrows, lane,
-                                    obs + (size_t)s * step_floats + (size_t)env0 * p.row_bytes, nvalid);
+            float* out = obs + (size_t)s * step_floats + (size_t)env0 * p.row_bytes;
+            if (UNDO) {
+                emit_obs_undo<A, NOBJ, NF>(e, in, valid, p, tb, wrows, lane, out, nvalid, shown_comm, shown_completed);
+                shown_comm = e.comm; shown_completed = e.completed;
+            } else {
+                emit_obs<A, NOBJ, NF, MODE>(e, in, valid, p, tb, wrows, lane, out, nvalid);
+            }
         }
     }
     if (valid) store_env<A, NOBJ>(e, state, p.E, env);
