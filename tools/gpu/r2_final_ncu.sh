@@ -11,8 +11,11 @@ cap() {
   rm -f gpurun_out/r2_prof_$1.ncu-rep
 }
 cap final_rollout_cfg2 cfg2 rollout oc_rollout_kernel 30
+cap final_rollout_cfg3 cfg3 rollout oc_rollout_kernel 30
+if [ "$1" = "all" ]; then
 cap final_rollout_cfg4 cfg4 rollout oc_rollout_kernel 30
 cap final_step_cfg2 cfg2 step oc_step_kernel 40
 cap final_step_cfg4 cfg4 step oc_step_kernel 40
 C="$B --workload cfg2"
 $C > /dev/null 2>&1 && timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2_final_launches.csv $C > gpurun_out/r2_ncu_launches.log 2>&1; echo "launch list rc=$?"
+fi
