@@ -138,6 +138,43 @@ static int dispatch_shape(int A, int NOBJ, F&& f) {
     return OC_ERR_INVALID;
 }
 
+// oc_rollout_kernel with single-pass float rows (kernel MODE 1), warp by warp: the warp's rows are cleared and filled in
+// the first step only; every later step takes back / overwrites the previous observation (build_rows_f32<UNDO>) exactly
+// as emit_obs_undo does on the device.  (Envs are independent, so walking the steps warp-major gives the same results as
+// the device's step-major order.)
+template <int A, int NOBJ, int NF>
+static void rollout_undo(emu_env* h, int32_t n_steps, float* obs, float* rew32, uint8_t* done, int32_t* actions_out) {
+    const OcParams& p = h->p;
+    const Tables tb = make_tables(p, h->blob.data());
+    const size_t step_floats = (size_t)p.E * p.row_bytes;
+    std::vector<uint8_t> rows((size_t)p.warp_row_bytes);
+    Env<A, NOBJ> we[32];
+    Info win[32];
+    uint32_t shown_comm[32], shown_completed[32];
+    for (int env0 = 0; env0 < p.E; env0 += 32) {
+        const int nvalid = std::min(32, p.E - env0);
+        for (int lane = 0; lane < nvalid; ++lane) load_env<A, NOBJ>(we[lane], h->state.data(), p.E, env0 + lane);
+        for (int s = 0; s < n_steps; ++s) {
+            for (int lane = 0; lane < nvalid; ++lane)
+                win[lane] = rollout_logic<A, NOBJ, NF, true>(we[lane], p, tb, (uint32_t)(env0 + lane), (uint32_t)s, h->rollout_step,
+                                                             rew32, done, actions_out);
+            if (!obs) continue;
+            if (s == 0)
+                for (int lane = 0; lane < 32; ++lane) warp_clear_rows<true>(rows.data(), p.warp_row_bytes, lane);
+            for (int lane = 0; lane < nvalid; ++lane) {
+                float* myrow = reinterpret_cast<float*>(rows.data() + row_offset(p, lane));
+                const float ts = timestep_of<A, NOBJ>(we[lane], p, tb);
+                if (s == 0) build_rows_f32<A, NOBJ, NF, false, false>(we[lane], p, tb, win[lane], ts, myrow);
+                else build_rows_f32<A, NOBJ, NF, false, true>(we[lane], p, tb, win[lane], ts, myrow, 0, shown_comm[lane], shown_completed[lane]);
+                shown_comm[lane] = we[lane].comm; shown_completed[lane] = we[lane].completed;
+            }
+            for (int lane = 0; lane < 32; ++lane)
+                warp_expand_rows<true>(p, rows.data(), obs + (size_t)s * step_floats + (size_t)env0 * p.row_bytes, nvalid, lane);
+        }
+        for (int lane = 0; lane < nvalid; ++lane) store_env<A, NOBJ>(we[lane], h->state.data(), p.E, env0 + lane);
+    }
+}
+
 extern "C" {
 
 const char* emu_last_error(void) { return g_err.c_str(); }
@@ -246,6 +283,10 @@ int emu_rollout(emu_env* h, int32_t n_steps, float* obs, float* rew32, uint8_t* 
     int rc = dispatch(h->p.A, h->p.NOBJ, h->p.rowf, [&](auto a, auto n, auto rf) -> int {
         constexpr int AA = decltype(a)::value, NN = shape_nobj(n), FF = shape_nf(n);
         constexpr bool RF = decltype(rf)::value;
+        if (RF && h->p.obs_passes == 1) {                        // kernel MODE 1: rows keep the previous observation
+            rollout_undo<AA, NN, FF>(h, n_steps, obs, rew32, done, actions_out);
+            return OC_OK;
+        }
         for (int s = 0; s < n_steps; ++s)
             for_each_warp<AA, NN, FF, RF>(h, obs ? obs + (size_t)s * step_floats : nullptr, nullptr,
                                   [&](const Tables& tb, int env, Env<AA, NN>& e, Info& in) {

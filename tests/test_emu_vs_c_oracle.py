@@ -76,11 +76,15 @@ def test_step_autoreset_terminal_obs(name, fmt, monkeypatch):
     assert np.array_equal(term.numpy(), term_o.astype(np.float32))
     assert env.decode_state()["episodes"].min() >= 3
 
-    # the fused rollout continues from the same state with the shared Philox action spec
-    obs = torch.zeros((7, E, n, env.obs_width))
-    done = torch.zeros((7, E), dtype=torch.uint8)
-    env.rollout(7, obs_out=obs, done_out=done)
-    oo, orr, od, _ = ora.rollout(7, want_obs=True, want_actions=True)
+    # the fused rollout continues from the same state with the shared Philox action spec, across an episode boundary
+    # of every env (single-pass float rows are not cleared between the steps of a launch: what an env's row shows of
+    # the finished episode -- message one-hots, completed subtasks -- has to be taken back)
+    R = cfg["max_num_timesteps"] + 3
+    obs = torch.zeros((R, E, n, env.obs_width))
+    done = torch.zeros((R, E), dtype=torch.uint8)
+    env.rollout(R, obs_out=obs, done_out=done)
+    oo, orr, od, _ = ora.rollout(R, want_obs=True, want_actions=True)
     assert np.array_equal(done.numpy(), od) and np.array_equal(obs.numpy(), oo.astype(np.float32))
+    assert done.numpy().any(axis=0).all()
     env.close()
     ora.close()
