@@ -1,6 +1,9 @@
 """One-off long-horizon soak: fused device rollout vs the C oracle twin (same Philox actions, same
 device-RNG resets) for tens of thousands of steps; rewards / dones every step, observations and packed
-state summaries at chunk boundaries.  python tools/soak_parity.py [steps]"""
+state summaries at chunk boundaries.  python tools/soak_parity.py [steps] [obs_every]
+
+`obs_every` (default 10): every that many chunks ALL observations of the chunk's 50 steps are compared too -- inside a
+launch the fused kernel never clears its single-pass float rows, so a stale feature would show up here."""
 import argparse
 import sys
 import time
@@ -25,6 +28,7 @@ CASES = {
                    num_communication=10, ego_led=False, fow_radius=2, ego_config=D, partner_config=D),
 }
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+obs_every = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 E, chunk = 16384, 50
 for name, cfg in CASES.items():
     text = levels_data.LEVELS[cfg["level"]]
@@ -40,8 +44,11 @@ for name, cfg in CASES.items():
     for c in range(steps // chunk):
         env.rollout(chunk, obs_out=obs, rew_out=rew, done_out=done)
         last = (c % 40 == 0) or c == steps // chunk - 1
-        oo, orr, od, _ = ora.rollout(chunk, want_obs=False)
+        check_obs = c % obs_every == 0
+        oo, orr, od, _ = ora.rollout(chunk, want_obs=check_obs)
         assert torch.equal(done.cpu(), torch.from_numpy(od)), (name, c)
+        if check_obs:
+            assert torch.equal(obs.cpu(), torch.from_numpy(oo.astype(np.float32))), (name, c, "observations")
         assert torch.equal(rew.cpu()[:, :, 0], torch.from_numpy(orr.astype(np.float32))), (name, c)
         events += int((orr.astype(np.float32) > -1.0).sum())
         if last:
