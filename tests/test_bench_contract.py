@@ -37,3 +37,18 @@ def test_nonzero_rank_of_reference_arm_exits_quietly():
     out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                                   cwd=ROOT, env=env, timeout=120).decode()
     assert out.strip() == ""
+
+
+def test_spread_stagger_is_a_permutation_of_the_clocks():
+    """bench.py's steady state: env e starts at (e * M) mod T -- every block of T consecutive envs holds every clock
+    exactly once (so exactly E / T envs finish per step, as with e mod T), and neighbours are far apart in time."""
+    sys.path.insert(0, ROOT)
+    import bench
+    for T in (7, 200, 500, 900, 1000):
+        M = bench.spread_multiplier(T)
+        clocks = sorted((e * M) % T for e in range(T))
+        assert clocks == list(range(T)), T
+        if T >= 200:                        # 32 consecutive envs (one warp): few of them finish inside any 20-step launch
+            block = [(e * M) % T for e in range(32)]
+            worst = max(sum(1 for c in block if (c - w) % T < 20) for w in range(T))
+            assert worst <= 5, (T, M, worst)   # e mod T puts 20 of them into one launch
